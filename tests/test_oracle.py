@@ -1,0 +1,158 @@
+"""Pins oracle/nerf_oracle.py against outputs recorded from the unmodified reference
+(tests/golden/make_golden.py) and, when /root/reference is present, against the live
+reference.  CPU only."""
+import argparse
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as orc
+
+REF = "/root/reference/Phase2"
+# MLP outputs were recorded single-threaded; MKL may reorder K-sums with other thread
+# counts, so matmul-bearing comparisons allow a few fp32 ulps instead of bit equality.
+MM_TOL = dict(rtol=0, atol=2e-6)
+
+
+def test_rays_match_reference(golden):
+    g = golden("rays")
+    cam = {"width": 12, "height": 10, "camera_matrix": g["K"]}
+    o, d = [], []
+    for y in range(10):
+        for x in range(12):
+            a, b = orc.pixel_to_ray(cam, g["pose"], (x, y))
+            o.append(a); d.append(b)
+    assert np.array_equal(np.array(o), g["o64"])           # fp64, bit exact
+    assert np.array_equal(np.array(d), g["d64"])
+    o32, d32 = orc.image_rays(cam, g["pose"])
+    assert np.array_equal(o32, g["o64"].astype(np.float32))
+    assert np.array_equal(d32, g["d64"].astype(np.float32))
+
+
+def test_generate_batch_matches_reference(golden):
+    g = golden("rays")
+    cam = {"width": 12, "height": 10, "camera_matrix": g["K"]}
+    random.seed(int(g["py_seed"]))
+    b = orc.generate_batch(g["images"], g["poses"], cam, 64)
+    assert b.dtype == np.float32 and b.shape == (64, 9)
+    assert np.array_equal(b, g["batch"])
+
+
+def test_position_encoding_matches_reference(golden):
+    g = golden("encoding")
+    x = torch.tensor(g["x"])
+    assert np.array_equal(orc.position_encoding(x, 10).numpy(), g["pe10"])
+    assert np.array_equal(orc.position_encoding(x, 4).numpy(), g["pe4"])
+    assert g["pe10"].shape[1] == 63 and g["pe4"].shape[1] == 27
+
+
+def test_init_state_dict_reproduces_reference_init(sd_pe256):
+    sd = orc.init_state_dict(0)
+    assert list(sd.keys()) == list(sd_pe256.keys())
+    assert sum(v.numel() for v in sd.values()) == 661636
+    for k in sd:
+        assert torch.equal(sd[k], sd_pe256[k]), k
+
+
+def test_model_forward_matches_reference(golden, sd_pe256):
+    g = golden("render_pe256")
+    S = int(g["S"])
+    d = torch.tensor(g["d"]).repeat_interleave(S, 0)[:512]
+    dens, cols = orc.model_forward(sd_pe256, torch.tensor(g["pts512"]), d)
+    np.testing.assert_allclose(dens.numpy(), g["dens512"], **MM_TOL)
+    np.testing.assert_allclose(cols.numpy(), g["cols512"], **MM_TOL)
+
+
+def test_render_matches_reference(golden, sd_pe256):
+    g = golden("render_pe256")
+    o, d, S = torch.tensor(g["o"]), torch.tensor(g["d"]), int(g["S"])
+    rgb = orc.render(sd_pe256, o, d, S)
+    np.testing.assert_allclose(rgb.numpy(), g["rgb_det"], **MM_TOL)
+    rgb_j = orc.render(sd_pe256, o, d, S, t_rand=torch.tensor(g["t_rand"]), chunk_size=1000)
+    np.testing.assert_allclose(rgb_j.numpy(), g["rgb_jit"], **MM_TOL)
+
+
+def test_gradients_and_adam_match_reference(golden, sd_pe256):
+    g = golden("render_pe256")
+    o, d, S = torch.tensor(g["o"]), torch.tensor(g["d"]), int(g["S"])
+    target = torch.tensor(g["target"])
+    loss, grads = orc.loss_and_grads(sd_pe256, o, d, target, S)
+    assert abs(loss.item() - float(g["loss"])) < 1e-7
+    for k, gr in grads.items():
+        kk = k.replace(".", "__")
+        ref_n = float(g[kk + "__gnorm"])
+        assert abs(gr.norm().item() - ref_n) <= 1e-4 * ref_n + 1e-9, k
+        samp = gr.flatten()[:: max(1, gr.numel() // 64)][:64].numpy()
+        np.testing.assert_allclose(samp, g[kk + "__g"], rtol=1e-3, atol=1e-8)
+    sd = {k: v.clone() for k, v in sd_pe256.items()}
+    sd = orc.Adam(sd).step(sd, grads)
+    for k, v in sd.items():
+        samp = v.flatten()[:: max(1, v.numel() // 64)][:64].numpy()
+        np.testing.assert_allclose(samp, g[k.replace(".", "__") + "__w1"], rtol=0, atol=2e-7)
+
+
+def test_nope_variant_matches_reference(golden):
+    g = golden("render_nope256")
+    r = golden("render_pe256")
+    sd = orc.init_state_dict(0, pos_encoding=False)
+    assert sum(v.numel() for v in sd.values()) == int(g["n_params"]) == 627844
+    assert np.array_equal(sd["fc1.weight"].numpy(), g["fc1_w"])
+    rgb = orc.render(sd, torch.tensor(r["o"]), torch.tensor(r["d"]), int(r["S"]), pos_encoding=False)
+    np.testing.assert_allclose(rgb.numpy(), g["rgb_det"], **MM_TOL)
+
+
+def test_test_image_matches_reference(golden, sd_pe256):
+    g = golden("test_image")
+    cam = {"width": 16, "height": 12, "camera_matrix": g["K"]}
+    pred, mse = orc.test_image(sd_pe256, g["image"], g["pose"], cam, 32, 50)
+    np.testing.assert_allclose(pred.numpy(), g["pred"], **MM_TOL)
+    assert abs(mse - float(g["mse"])) < 1e-9
+
+
+def test_composite_backward_closed_form():
+    torch.manual_seed(1)
+    N, S = 7, 64
+    sigma = (torch.rand(N, S, dtype=torch.float64) * 8).requires_grad_(True)
+    rgb = torch.rand(N, S, 3, dtype=torch.float64).requires_grad_(True)
+    z = orc.sample_z(N, S, 2.0, 6.0, torch.rand(N, S)).double()
+    g = torch.randn(N, 3, dtype=torch.float64)
+    out = orc.composite(sigma, rgb, z)["rgb"]
+    ds, dc = torch.autograd.grad((out * g).sum(), [sigma, rgb])
+    ds2, dc2 = orc.composite_backward(sigma.detach(), rgb.detach(), z, g)
+    assert (ds - ds2).abs().max() < 1e-12 and (dc - dc2).abs().max() < 1e-12
+
+
+def test_sample_z_edges():
+    z = orc.sample_z(3, 64, 2.0, 6.0)
+    assert z.shape == (3, 64) and z[0, 0] == 2.0 and z[0, -1] == 6.0
+    u = torch.rand(3, 64)
+    zj = orc.sample_z(3, 64, 2.0, 6.0, u)
+    assert (zj[:, 1:] >= zj[:, :-1]).all() and zj.min() >= 2.0 and zj.max() <= 6.0
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="live reference only exists in the build container")
+def test_oracle_against_live_reference():
+    for n in ("imageio", "matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(n, types.ModuleType(n))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.path.insert(0, REF)
+    import train as ref
+    torch.manual_seed(5)
+    model = ref.NeRFmodel()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    cam = orc.make_camera_info(20, 20)
+    pose = orc.look_at_pose(200.0, -45.0)
+    o, d = orc.image_rays(cam, pose)
+    o, d = torch.tensor(o[:96]), torch.tensor(d[:96])
+    args = argparse.Namespace(n_sample=48, perturb=True, chunk_size=999, n_rays_batch=96)
+    torch.manual_seed(9)
+    with torch.no_grad():
+        want = ref.render(model, o, d, args, near=1.5, far=5.0)
+    torch.manual_seed(9)
+    got = orc.render(sd, o, d, 48, 1.5, 5.0, t_rand=torch.rand(96, 48), chunk_size=999)
+    assert torch.equal(got, want)
