@@ -1,0 +1,157 @@
+/* nerf_b200.h -- C ABI of libnerf_b200.so: the B200 (sm_100a) implementation of the
+ * Phase2 NeRF render / train-step hot path of ColinBalfour/SfM-NeRF.
+ *
+ * The reference has no FFI: its boundary is the Python call surface of Phase2/train.py and
+ * Phase2/NeRFModel.py.  Each entry point below replaces the arithmetic of the reference lines
+ * it cites; the Python host (sfm-nerf_b200/train.py, NeRFModel.py) keeps the reference's
+ * names/signatures and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all memory; the library never allocates or frees user-visible buffers
+ *     (sizes of opaque buffers come from the *_bytes() queries);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden syncs;
+ *   - return value: 0 = success, <0 = NERF_ERR_* argument/state error, >0 = cudaError_t;
+ *   - stateless and re-entrant; one device (the current one) per call;
+ *   - there is no CPU fallback: on a device that is not sm_100 every compute entry point
+ *     returns NERF_ERR_ARCH.
+ */
+#ifndef NERF_B200_H_
+#define NERF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERF_ABI_VERSION 1
+
+enum {
+  NERF_OK = 0,
+  NERF_ERR_ARG = -1,      /* null pointer, negative size, unsupported parameter value */
+  NERF_ERR_ALIGN = -2,    /* pointer not aligned as documented */
+  NERF_ERR_ARCH = -3,     /* current device is not compute capability 10.x */
+  NERF_ERR_LAYOUT = -4,   /* unknown model layout id */
+  NERF_ERR_SELFTEST = -5  /* a self test produced wrong results */
+};
+
+/* Model layouts. Hidden width is 256, rgb hidden 128 (NeRFModel.py:116-140). */
+enum {
+  NERF_LAYOUT_LIVE_PE = 0,   /* NeRFmodel(10, 4, 256, pos_encoding=True): 661,636 params */
+  NERF_LAYOUT_LIVE_NOPE = 1  /* NeRFmodel(.., pos_encoding=False):      627,844 params */
+};
+
+int nerf_abi_version(void);
+const char* nerf_error_string(int code);
+/* 0 when the current CUDA device can run the kernels (sm_100), else NERF_ERR_ARCH / cudaError_t. */
+int nerf_device_check(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Parameter vector.  All 26 tensors live in ONE flat fp32 buffer in state_dict order
+ * (fc1.weight, fc1.bias, fc_layers.0.weight, ... rgb_layer2.bias; NeRFModel.py:116-140),
+ * each tensor row-major [out, in] exactly as torch.nn.Linear stores it.  Gradients and Adam
+ * moments use the same layout.
+ * ------------------------------------------------------------------------------------- */
+int64_t nerf_param_count(int layout);                       /* 661636 / 627844, <0 on error */
+/* offset (in floats) of tensor `index` (0..25, weight/bias interleaved) or <0 */
+int64_t nerf_param_offset(int layout, int index);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  ray generation -- replaces PixelToRay (train.py:68-102), the per-pixel loops of
+ * test_image (train.py:735-742) and generateBatch (train.py:104-127).  fp64 arithmetic,
+ * rounded once to fp32 like the reference (train.py:127, 741-742).
+ *   poses   : [n_images,4,4] fp64 camera-to-world, row-major
+ *   fx..cy  : camera_matrix[0][0], [1][1], [0][2], [1][2]
+ * image mode: rays ray_begin .. ray_begin+ray_count-1 of image `pose_index`, ray id = y*W+x.
+ * ------------------------------------------------------------------------------------- */
+int nerf_raygen_image(const double* poses, int pose_index, double fx, double fy, double cx,
+                      double cy, int width, int height, int64_t ray_begin, int64_t ray_count,
+                      float* rays_o, float* rays_d, void* stream);
+/* batch mode: ray i uses (img_idx[i], px[i], py[i]); `images` ([n,H,W,3] fp32) and `target`
+ * ([N,3]) may both be NULL. */
+int nerf_raygen_batch(const double* poses, int n_images, double fx, double fy, double cx,
+                      double cy, int width, int height, const int32_t* img_idx,
+                      const int32_t* px, const int32_t* py, const float* images, int64_t n_rays,
+                      float* rays_o, float* rays_d, float* target, void* stream);
+/* device-side replacement for the three random.randint draws per ray (train.py:120-121);
+ * counter-based, so (seed, offset) fully determine the output. */
+int nerf_draw_pixels(uint64_t seed, uint64_t offset, int n_images, int width, int height,
+                     int64_t n_rays, int32_t* img_idx, int32_t* px, int32_t* py, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2  stratified depths -- train.py:205-217.  z is [n_rays, n_sample] fp32.
+ *   perturb == 0            : t = linspace(0,1,S)
+ *   perturb != 0, t_rand    : jitter with the caller's uniforms [n_rays,n_sample]
+ *   perturb != 0, no t_rand : jitter with counter-based uniforms from (seed, offset)
+ * ------------------------------------------------------------------------------------- */
+int nerf_sample_z(int64_t n_rays, int n_sample, float near, float far, int perturb,
+                  const float* t_rand, uint64_t seed, uint64_t offset, float* z, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3  positional encoding -- NeRFmodel.position_encoding (NeRFModel.py:142-156).
+ *   x [n,3] -> out [n, 3*(2L+1)] fp32, channel order [x, sin0, cos0, sin1, cos1, ...].
+ * ------------------------------------------------------------------------------------- */
+int nerf_encode(const float* x, int64_t n, int L, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4  fused MLP -- NeRFmodel.forward (NeRFModel.py:158-202) and its backward.
+ * Weights are consumed in a packed bf16 image (UMMA operand order) built from the flat fp32
+ * parameter vector; rebuild it after every optimizer step.
+ * ------------------------------------------------------------------------------------- */
+int64_t nerf_mlp_packed_bytes(int layout);
+int nerf_mlp_pack_weights(const float* params, int layout, void* packed, void* stream);
+
+/* activation stash written by the training forward and read by the backward; n_rows is
+ * rounded up to the 128-row tile internally.  16-byte aligned. */
+int64_t nerf_mlp_stash_bytes(int layout, int64_t n_rows);
+int64_t nerf_mlp_dstash_bytes(int layout, int64_t n_rows);   /* backward scratch */
+
+/* per-sample inputs: pos [n,3], dir [n,3] -> sigma_rgb [n,4] = (softplus density, sigmoid rgb).
+ * stash == NULL: inference; otherwise the training forward (stash sized by the query). */
+int nerf_mlp_forward(const void* packed, int layout, const float* pos, const float* dir,
+                     int64_t n_rows, float* sigma_rgb, void* stash, void* stream);
+/* ray inputs (fuses train.py:220-228): row r*S+s evaluates o[r] + d[r]*z[r,s], dir d[r]. */
+int nerf_mlp_forward_rays(const void* packed, int layout, const float* rays_o,
+                          const float* rays_d, const float* z, int64_t n_rays, int n_sample,
+                          float* sigma_rgb, void* stash, void* stream);
+/* backward: d_sigma_rgb [n,4] = dL/d(density, rgb) -> grads (flat fp32 parameter layout).
+ * accumulate == 0 overwrites grads, != 0 adds to them.  dstash is scratch. */
+int nerf_mlp_backward(const void* packed, int layout, const void* stash, const float* sigma_rgb,
+                      const float* d_sigma_rgb, int64_t n_rows, void* dstash, float* grads,
+                      int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K5  volume compositing -- train.py:248-269 (+ depth/acc = sum w*z / sum w, which the
+ * reference does not output) and its backward w.r.t. density and colour.
+ *   sigma_rgb [n_rays,S,4], z [n_rays,S]; depth/acc may be NULL.
+ * ------------------------------------------------------------------------------------- */
+int nerf_composite_forward(const float* sigma_rgb, const float* z, int64_t n_rays, int n_sample,
+                           float* rgb, float* depth, float* acc, void* stream);
+int nerf_composite_backward(const float* sigma_rgb, const float* z, const float* g_rgb,
+                            int64_t n_rays, int n_sample, float* d_sigma_rgb, void* stream);
+/* MSE over n_rays*3 (train.py:460): loss[0] = mean((rgb-target)^2) and, when g_rgb != NULL,
+ * g_rgb = grad_scale * 2*(rgb-target)/(3*n_rays). */
+int nerf_mse_loss(const float* rgb, const float* target, int64_t n_rays, float grad_scale,
+                  float* loss, float* g_rgb, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Optimizer -- torch.optim.Adam defaults of train.py:401 over the flat vectors (one launch
+ * instead of 26).  step is 1-based; grads are multiplied by grad_scale first (1/world for
+ * data-parallel sums).
+ * ------------------------------------------------------------------------------------- */
+int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                   int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
+                   float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Self tests (device): exercise the tcgen05 descriptor encodings used by K4 on a small GEMM.
+ * variant selects the operand layout hypothesis; result_host[0..3] receives max-abs-error
+ * and diagnostics.  Returns 0 when the variant reproduces the fp32 reference product.
+ * ------------------------------------------------------------------------------------- */
+int nerf_selftest_umma(int variant, float* result_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H_ */

@@ -1,0 +1,12 @@
+"""sfm-nerf_b200 -- B200-native (sm_100a) NeRF render / train-step hot path, drop-in for the
+Phase2 call surface of ColinBalfour/SfM-NeRF.  The directory name carries a hyphen (the project
+name); import it as ``sfmnerf_b200`` (alias module at the repo root) or with
+``importlib.import_module("sfm-nerf_b200")``.
+"""
+from . import _lib, engine, synthetic  # noqa: F401
+from .NeRFModel import NeRFmodel  # noqa: F401
+from .train import (PixelToRay, configParser, generateBatch, loadDataset, loss, main, render,  # noqa: F401
+                    render_full, test, test_image, train)
+
+__all__ = ["NeRFmodel", "PixelToRay", "generateBatch", "render", "render_full", "loss", "test_image", "train",
+           "test", "main", "configParser", "loadDataset", "engine", "synthetic"]

@@ -1,0 +1,386 @@
+// api.cu -- the C ABI of libnerf_b200.so (include/nerf_b200.h).  Argument checking, launch
+// geometry and nothing else: every entry point enqueues sm_100a kernels on the caller's stream.
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "composite.cuh"
+#include "mlp_fused.cuh"
+#include "mlp_layout.cuh"
+#include "rays.cuh"
+#include "selftest.cuh"
+#include "wgrad.cuh"
+
+using namespace nerf;
+
+namespace {
+
+struct DeviceInfo { int device = -1; int sms = 0; int cc_major = 0; bool attrs_set = false; };
+thread_local DeviceInfo g_dev;
+
+int device_info(DeviceInfo** out) {
+  int dev = 0;
+  NERF_CUDA_TRY(cudaGetDevice(&dev));
+  if (g_dev.device != dev) {
+    DeviceInfo d;
+    d.device = dev;
+    NERF_CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    NERF_CUDA_TRY(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    g_dev = d;
+  }
+  if (g_dev.cc_major != 10) return NERF_ERR_ARCH;
+  if (!g_dev.attrs_set) {
+    NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
+    NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
+    NERF_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+    NERF_CUDA_TRY(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+    g_dev.attrs_set = true;
+  }
+  *out = &g_dev;
+  return NERF_OK;
+}
+
+inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
+const ModelLayout* get_layout(int layout) {
+  static ModelLayout cache[2];
+  static bool ready[2] = {false, false};
+  if (layout < 0 || layout > 1) return nullptr;
+  if (!ready[layout]) { build_model_layout(layout, cache[layout]); ready[layout] = true; }
+  return &cache[layout];
+}
+
+void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t n_rows) {
+  std::memset(&a, 0, sizeof(a));
+  a.packed = static_cast<const uint8_t*>(packed);
+  a.small = reinterpret_cast<const float*>(a.packed + m.small_off);
+  a.pos_L = m.pos_L; a.dir_L = m.dir_L;
+  a.sm_wd = m.sm_wd; a.sm_bd = m.sm_bd; a.sm_w2 = m.sm_w2; a.sm_b2 = m.sm_b2;
+  a.n_rows = n_rows;
+  a.n_tiles = (int)((n_rows + 127) / 128);
+  a.stash_tile_bytes = m.stash_tile_bytes; a.dstash_tile_bytes = m.dstash_tile_bytes;
+  a.st_pe = m.st_pe; a.st_de = m.st_de; a.st_r1 = m.st_r1; a.ds_y10 = m.ds_y[10]; a.ds_sr = m.ds_sr;
+}
+
+int launch_forward(const void* packed, int layout, const float* pos, const float* dir, const float* z,
+                   int64_t n_rows, int n_sample, float* sigma_rgb, void* stash, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  const ModelLayout* m = get_layout(layout);
+  if (!m) return NERF_ERR_LAYOUT;
+  if (!packed || !pos || !dir || !sigma_rgb || n_rows < 0 || n_rows > (int64_t)128 * 0x7fffff00) return NERF_ERR_ARG;
+  if (!nerf_aligned(packed, 16) || !nerf_aligned(sigma_rgb, 16) || (stash && !nerf_aligned(stash, 16))) return NERF_ERR_ALIGN;
+  if (n_rows == 0) return NERF_OK;
+  MlpArgs a;
+  fill_mlp_args(a, *m, packed, n_rows);
+  a.pos = pos; a.dir = dir; a.z = z; a.n_sample = n_sample;
+  a.sigma_rgb = sigma_rgb;
+  a.stash = static_cast<uint8_t*>(stash);
+  a.prog = m->fwd;
+  const int grid = a.n_tiles < 2 * dev->sms ? a.n_tiles : 2 * dev->sms;
+  mlp_fused_kernel<MODE_FWD><<<grid, 192, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nerf_abi_version(void) { return NERF_ABI_VERSION; }
+
+const char* nerf_error_string(int code) {
+  switch (code) {
+    case NERF_OK: return "ok";
+    case NERF_ERR_ARG: return "invalid argument";
+    case NERF_ERR_ALIGN: return "misaligned pointer";
+    case NERF_ERR_ARCH: return "device is not sm_100 (no CPU or other-arch fallback exists)";
+    case NERF_ERR_LAYOUT: return "unknown model layout";
+    case NERF_ERR_SELFTEST: return "self test failed";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+  }
+}
+
+int nerf_device_check(void) {
+  DeviceInfo* dev;
+  return device_info(&dev);
+}
+
+int64_t nerf_param_count(int layout) {
+  const ModelLayout* m = get_layout(layout);
+  return m ? m->n_params : NERF_ERR_LAYOUT;
+}
+
+int64_t nerf_param_offset(int layout, int index) {
+  const ModelLayout* m = get_layout(layout);
+  if (!m) return NERF_ERR_LAYOUT;
+  if (index < 0 || index >= 2 * kNumLinear) return NERF_ERR_ARG;
+  return (index & 1) ? m->b_off[index >> 1] : m->w_off[index >> 1];
+}
+
+// ------------------------------------------------------------------------------------ K1
+int nerf_raygen_image(const double* poses, int pose_index, double fx, double fy, double cx, double cy,
+                      int width, int height, int64_t ray_begin, int64_t ray_count, float* rays_o,
+                      float* rays_d, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!poses || !rays_o || !rays_d || pose_index < 0 || width <= 0 || height <= 0 || ray_begin < 0 || ray_count < 0 ||
+      ray_begin + ray_count > (int64_t)width * height || fx == 0.0 || fy == 0.0)
+    return NERF_ERR_ARG;
+  if (ray_count == 0) return NERF_OK;
+  raygen_image_kernel<<<blocks_for(ray_count, 256), 256, 0, (cudaStream_t)stream>>>(
+      poses, pose_index, fx, fy, cx, cy, width, ray_begin, ray_count, rays_o, rays_d);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int nerf_raygen_batch(const double* poses, int n_images, double fx, double fy, double cx, double cy,
+                      int width, int height, const int32_t* img_idx, const int32_t* px, const int32_t* py,
+                      const float* images, int64_t n_rays, float* rays_o, float* rays_d, float* target,
+                      void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!poses || !img_idx || !px || !py || !rays_o || !rays_d || n_images <= 0 || width <= 0 || height <= 0 ||
+      n_rays < 0 || fx == 0.0 || fy == 0.0)
+    return NERF_ERR_ARG;
+  if (n_rays == 0) return NERF_OK;
+  raygen_batch_kernel<<<blocks_for(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+      poses, fx, fy, cx, cy, width, height, img_idx, px, py, images, n_rays, rays_o, rays_d, target);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int nerf_draw_pixels(uint64_t seed, uint64_t offset, int n_images, int width, int height, int64_t n_rays,
+                     int32_t* img_idx, int32_t* px, int32_t* py, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!img_idx || !px || !py || n_images <= 0 || width <= 0 || height <= 0 || n_rays < 0) return NERF_ERR_ARG;
+  if (n_rays == 0) return NERF_OK;
+  draw_pixels_kernel<<<blocks_for(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(seed, offset, n_images, width, height,
+                                                                                n_rays, img_idx, px, py);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+// ------------------------------------------------------------------------------------ K2
+int nerf_sample_z(int64_t n_rays, int n_sample, float near, float far, int perturb, const float* t_rand,
+                  uint64_t seed, uint64_t offset, float* z, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!z || n_rays < 0 || n_sample <= 0) return NERF_ERR_ARG;
+  const int64_t total = n_rays * n_sample;
+  if (total == 0) return NERF_OK;
+  sample_z_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(total, n_sample, near, far, perturb,
+                                                                           t_rand, seed, offset, z);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+// ------------------------------------------------------------------------------------ K3
+int nerf_encode(const float* x, int64_t n, int L, float* out, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!x || !out || n < 0 || L < 0 || L > 30) return NERF_ERR_ARG;
+  const int64_t total = n * 3 * (2 * L + 1);
+  if (total == 0) return NERF_OK;
+  encode_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, n, L, out);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+// ------------------------------------------------------------------------------------ K4
+int64_t nerf_mlp_packed_bytes(int layout) {
+  const ModelLayout* m = get_layout(layout);
+  return m ? m->packed_bytes : NERF_ERR_LAYOUT;
+}
+
+int nerf_mlp_pack_weights(const float* params, int layout, void* packed, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  const ModelLayout* m = get_layout(layout);
+  if (!m) return NERF_ERR_LAYOUT;
+  if (!params || !packed) return NERF_ERR_ARG;
+  if (!nerf_aligned(packed, 16)) return NERF_ERR_ALIGN;
+  cudaStream_t s = (cudaStream_t)stream;
+  pack_images_kernel<<<dim3(64, m->fwd.n_steps), 256, 0, s>>>(params, m->fwd, static_cast<uint8_t*>(packed));
+  NERF_LAUNCH_CHECK();
+  pack_images_kernel<<<dim3(64, m->bwd.n_steps), 256, 0, s>>>(params, m->bwd, static_cast<uint8_t*>(packed));
+  NERF_LAUNCH_CHECK();
+  PackSmallArgs p{};
+  p.n_bias = m->fwd.n_steps;
+  const int lin_of_step[11] = {L_FC1, L_FC0, L_FC0 + 1, L_FC0 + 2, L_FC0 + 3, L_SKIP, L_FC2_0, L_FC2_0 + 1, L_FC2_0 + 2, L_FEAT, L_RGB1};
+  for (int i = 0; i < 11; ++i) { p.b_src[i] = m->b_off[lin_of_step[i]]; p.b_n[i] = m->out_f[lin_of_step[i]]; }
+  p.wd_src = m->w_off[L_DENS]; p.bd_src = m->b_off[L_DENS]; p.w2_src = m->w_off[L_RGB2]; p.b2_src = m->b_off[L_RGB2];
+  p.sm_wd = m->sm_wd; p.sm_bd = m->sm_bd; p.sm_w2 = m->sm_w2; p.sm_b2 = m->sm_b2;
+  pack_small_kernel<<<blocks_for(11 * 256, 256), 256, 0, s>>>(params, p, reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + m->small_off));
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int64_t nerf_mlp_stash_bytes(int layout, int64_t n_rows) {
+  const ModelLayout* m = get_layout(layout);
+  if (!m) return NERF_ERR_LAYOUT;
+  if (n_rows < 0) return NERF_ERR_ARG;
+  return ((n_rows + 127) / 128) * (int64_t)m->stash_tile_bytes;
+}
+
+int64_t nerf_mlp_dstash_bytes(int layout, int64_t n_rows) {
+  const ModelLayout* m = get_layout(layout);
+  if (!m) return NERF_ERR_LAYOUT;
+  if (n_rows < 0) return NERF_ERR_ARG;
+  return ((n_rows + 127) / 128) * (int64_t)m->dstash_tile_bytes;
+}
+
+int nerf_mlp_forward(const void* packed, int layout, const float* pos, const float* dir, int64_t n_rows,
+                     float* sigma_rgb, void* stash, void* stream) {
+  return launch_forward(packed, layout, pos, dir, nullptr, n_rows, 0, sigma_rgb, stash, stream);
+}
+
+int nerf_mlp_forward_rays(const void* packed, int layout, const float* rays_o, const float* rays_d, const float* z,
+                          int64_t n_rays, int n_sample, float* sigma_rgb, void* stash, void* stream) {
+  if (!z || n_sample <= 0 || n_rays < 0) return NERF_ERR_ARG;
+  return launch_forward(packed, layout, rays_o, rays_d, z, n_rays * n_sample, n_sample, sigma_rgb, stash, stream);
+}
+
+int nerf_mlp_backward(const void* packed, int layout, const void* stash, const float* sigma_rgb,
+                      const float* d_sigma_rgb, int64_t n_rows, void* dstash, float* grads, int accumulate,
+                      void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  const ModelLayout* m = get_layout(layout);
+  if (!m) return NERF_ERR_LAYOUT;
+  if (!packed || !stash || !sigma_rgb || !d_sigma_rgb || !dstash || !grads || n_rows < 0) return NERF_ERR_ARG;
+  if (!nerf_aligned(packed, 16) || !nerf_aligned(stash, 16) || !nerf_aligned(dstash, 16) || !nerf_aligned(sigma_rgb, 16) ||
+      !nerf_aligned(d_sigma_rgb, 16))
+    return NERF_ERR_ALIGN;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!accumulate) NERF_CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * m->n_params, s));
+  if (n_rows == 0) return NERF_OK;
+
+  // 1. data-gradient chain (emits every dY_l to the dstash)
+  MlpArgs a;
+  fill_mlp_args(a, *m, packed, n_rows);
+  a.sigma_rgb = const_cast<float*>(sigma_rgb);
+  a.d_sigma_rgb = d_sigma_rgb;
+  a.stash = static_cast<uint8_t*>(const_cast<void*>(stash));
+  a.dstash = static_cast<uint8_t*>(dstash);
+  a.prog = m->bwd;
+  const int grid = a.n_tiles < 2 * dev->sms ? a.n_tiles : 2 * dev->sms;
+  mlp_fused_kernel<MODE_BWD><<<grid, 192, MlpSmem::kTotal, s>>>(a);
+  NERF_LAUNCH_CHECK();
+
+  // 2. weight gradients: split the SMs over the work items in proportion to their cost
+  WgradArgs w;
+  std::memset(&w, 0, sizeof(w));
+  w.stash = a.stash; w.dstash = a.dstash; w.grads = grads;
+  w.stash_tile_bytes = m->stash_tile_bytes; w.dstash_tile_bytes = m->dstash_tile_bytes;
+  w.n_tiles = a.n_tiles; w.n_items = m->n_wgrad;
+  int64_t total_cost = 0;
+  for (int i = 0; i < m->n_wgrad; ++i) { w.items[i] = m->wg[i]; total_cost += m->wg[i].cost; }
+  int ctas = 0;
+  for (int i = 0; i < m->n_wgrad; ++i) {
+    int c = (int)((int64_t)dev->sms * m->wg[i].cost / total_cost);
+    if (c < 1) c = 1;
+    if (c > a.n_tiles) c = a.n_tiles;
+    w.cta_begin[i] = ctas;
+    ctas += c;
+  }
+  w.cta_begin[m->n_wgrad] = ctas;
+  wgrad_kernel<<<ctas, 192, kWgSmemBytes, s>>>(w);
+  NERF_LAUNCH_CHECK();
+
+  // 3. head gradients (density_layer, rgb_layer2)
+  HeadGradArgs h{};
+  h.stash = a.stash; h.dstash = a.dstash; h.grads = grads;
+  h.stash_tile_bytes = m->stash_tile_bytes; h.dstash_tile_bytes = m->dstash_tile_bytes; h.n_tiles = a.n_tiles;
+  h.st_h8 = m->st_h[8]; h.st_r1 = m->st_r1; h.ds_sr = m->ds_sr;
+  h.g_wd = m->w_off[L_DENS]; h.g_bd = m->b_off[L_DENS]; h.g_w2 = m->w_off[L_RGB2]; h.g_b2 = m->b_off[L_RGB2];
+  const int hgrid = a.n_tiles < 4 * dev->sms ? a.n_tiles : 4 * dev->sms;
+  head_grad_kernel<<<hgrid, 384, 0, s>>>(h);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+// ------------------------------------------------------------------------------------ K5
+int nerf_composite_forward(const float* sigma_rgb, const float* z, int64_t n_rays, int n_sample, float* rgb,
+                           float* depth, float* acc, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!sigma_rgb || !z || !rgb || n_rays < 0 || n_sample <= 0) return NERF_ERR_ARG;
+  if (!nerf_aligned(sigma_rgb, 16)) return NERF_ERR_ALIGN;
+  if (n_rays == 0) return NERF_OK;
+  composite_forward_kernel<<<blocks_for(n_rays, kCompWarpsPerBlock), kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(sigma_rgb), z, n_rays, n_sample, rgb, depth, acc);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int nerf_composite_backward(const float* sigma_rgb, const float* z, const float* g_rgb, int64_t n_rays, int n_sample,
+                            float* d_sigma_rgb, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!sigma_rgb || !z || !g_rgb || !d_sigma_rgb || n_rays < 0 || n_sample <= 0 || n_sample > 32 * kCompMaxChunks)
+    return NERF_ERR_ARG;
+  if (!nerf_aligned(sigma_rgb, 16) || !nerf_aligned(d_sigma_rgb, 16)) return NERF_ERR_ALIGN;
+  if (n_rays == 0) return NERF_OK;
+  composite_backward_kernel<<<blocks_for(n_rays, kCompWarpsPerBlock), kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(sigma_rgb), z, g_rgb, n_rays, n_sample, reinterpret_cast<float4*>(d_sigma_rgb));
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int nerf_mse_loss(const float* rgb, const float* target, int64_t n_rays, float grad_scale, float* loss, float* g_rgb,
+                  void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!rgb || !target || !loss || n_rays <= 0) return NERF_ERR_ARG;
+  mse_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rgb, target, n_rays * 3, grad_scale, loss, g_rgb);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+// ------------------------------------------------------------------------------------ optimizer
+int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return NERF_ERR_ARG;
+  if (n == 0) return NERF_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                    eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+// ------------------------------------------------------------------------------------ self test
+int nerf_selftest_umma(int variant, float* result_host) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (variant < 0 || variant > 1 || !result_host) return NERF_ERR_ARG;
+  float* d = nullptr;                        // diagnostics only: the one entry point that allocates
+  NERF_CUDA_TRY(cudaMalloc(&d, 4 * sizeof(float)));
+  cudaMemset(d, 0, 4 * sizeof(float));
+  selftest_umma_kernel<<<1, 128, 32768>>>(variant, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(result_host, d, 4 * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return (int)e;
+  return (result_host[0] == 0.0f && result_host[1] > 0.0f) ? NERF_OK : NERF_ERR_SELFTEST;
+}
+
+}  // extern "C"

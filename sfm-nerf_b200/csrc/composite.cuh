@@ -1,0 +1,170 @@
+// composite.cuh -- K5 volume compositing forward/backward (train.py:248-269), MSE, Adam.
+// One warp per ray; lane l handles samples l, l+32, ... so every load is a coalesced float4 /
+// float row segment; the transmittance product is a warp scan with a running carry.
+#pragma once
+#include "common.cuh"
+
+namespace nerf {
+
+constexpr int kCompWarpsPerBlock = 8;
+constexpr int kCompMaxChunks = 8;          // backward keeps per-lane state for S <= 256
+
+__device__ __forceinline__ float warp_incl_prod(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v *= t;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_incl_sum(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// alpha_i = 1 - exp(-sigma_i * delta_i); delta_{S-1} = 1e-3 (train.py:248-254)
+__device__ __forceinline__ void sample_alpha(const float* __restrict__ zr, int s, int S, float sigma,
+                                             float& delta, float& alpha) {
+  delta = (s < S - 1) ? __fsub_rn(zr[s + 1], zr[s]) : 1e-3f;
+  alpha = __fsub_rn(1.0f, expf(-__fmul_rn(sigma, delta)));
+}
+
+__global__ void __launch_bounds__(kCompWarpsPerBlock * 32)
+composite_forward_kernel(const float4* __restrict__ sigma_rgb, const float* __restrict__ z,
+                         int64_t n_rays, int S, float* __restrict__ rgb, float* __restrict__ depth,
+                         float* __restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kCompWarpsPerBlock + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const float4* sr = sigma_rgb + ray * S;
+  const float* zr = z + ray * S;
+  float carry = 1.0f, ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
+  for (int base = 0; base < S; base += 32) {
+    const int s = base + lane;
+    float om = 1.0f, alpha = 0.0f, zz = 0.0f;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < S) {
+      v = __ldg(sr + s);
+      zz = zr[s];
+      float delta;
+      sample_alpha(zr, s, S, v.x, delta, alpha);
+      om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);          // train.py:262
+    }
+    const float incl = warp_incl_prod(om, lane);
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float T = carry * excl;                               // exclusive cumprod (261-263)
+    const float w = alpha * T;                                  // train.py:266
+    ar += w * v.y; ag += w * v.z; ab += w * v.w; ad += w * zz; aa += w;
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+  }
+  ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad); aa = warp_sum(aa);
+  if (lane == 0) {
+    rgb[3 * ray + 0] = ar; rgb[3 * ray + 1] = ag; rgb[3 * ray + 2] = ab;   // train.py:269
+    if (depth) depth[ray] = ad;
+    if (acc) acc[ray] = aa;
+  }
+}
+
+// Backward: with gc_i = g . c_i and suffix_i = sum_{j>i} w_j gc_j
+//   dL/dc_i = w_i g;  dL/dalpha_i = T_i gc_i - suffix_i / om_i;  dL/dsigma_i = delta_i (1-alpha_i) dL/dalpha_i
+__global__ void __launch_bounds__(kCompWarpsPerBlock * 32)
+composite_backward_kernel(const float4* __restrict__ sigma_rgb, const float* __restrict__ z,
+                          const float* __restrict__ g_rgb, int64_t n_rays, int S,
+                          float4* __restrict__ d_sigma_rgb) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kCompWarpsPerBlock + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const float4* sr = sigma_rgb + ray * S;
+  const float* zr = z + ray * S;
+  const float g0 = g_rgb[3 * ray + 0], g1 = g_rgb[3 * ray + 1], g2 = g_rgb[3 * ray + 2];
+  float Tk[kCompMaxChunks], wk[kCompMaxChunks], gck[kCompMaxChunks], fk[kCompMaxChunks], omk[kCompMaxChunks];
+  float carry = 1.0f;
+  const int n_chunks = (S + 31) >> 5;
+#pragma unroll
+  for (int c = 0; c < kCompMaxChunks; ++c) {
+    if (c < n_chunks) {
+      const int s = c * 32 + lane;
+      float om = 1.0f, alpha = 0.0f, delta = 0.0f, gc = 0.0f;
+      if (s < S) {
+        const float4 v = __ldg(sr + s);
+        sample_alpha(zr, s, S, v.x, delta, alpha);
+        om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+        gc = g0 * v.y + g1 * v.z + g2 * v.w;
+      }
+      const float incl = warp_incl_prod(om, lane);
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      Tk[c] = carry * excl;
+      wk[c] = alpha * Tk[c];
+      gck[c] = gc;
+      fk[c] = delta * (1.0f - alpha);
+      omk[c] = om;
+      carry *= __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  // reverse pass: suffix sums of w*gc
+  float tail = 0.0f;
+#pragma unroll
+  for (int c = kCompMaxChunks - 1; c >= 0; --c) {
+    if (c < n_chunks) {
+      const int s = c * 32 + lane;
+      const float wgc = wk[c] * gck[c];
+      const float incl = warp_incl_sum(wgc, lane);
+      const float total = __shfl_sync(0xffffffffu, incl, 31);
+      const float suffix = tail + (total - incl);               // sum over j > i
+      if (s < S) {
+        const float dalpha = Tk[c] * gck[c] - suffix / omk[c];
+        d_sigma_rgb[ray * S + s] = make_float4(fk[c] * dalpha, wk[c] * g0, wk[c] * g1, wk[c] * g2);
+      }
+      tail += total;
+    }
+  }
+}
+
+// train.py:460 nn.MSELoss (mean over n*3) and its gradient; single block.
+__global__ void __launch_bounds__(1024)
+mse_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ target, int64_t n3,
+                float grad_scale, float* __restrict__ loss, float* __restrict__ g_rgb) {
+  __shared__ float red[32];
+  float acc = 0.0f;
+  const float gs = grad_scale * 2.0f / (float)n3;
+  for (int64_t i = threadIdx.x; i < n3; i += blockDim.x) {
+    const float d = rgb[i] - target[i];
+    acc += d * d;
+    if (g_rgb) g_rgb[i] = gs * d;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) loss[0] = v / (float)n3;
+  }
+}
+
+// torch.optim.Adam (train.py:401) over the flat parameter vector.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2_sqrt, float grad_scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * grad_scale;
+  const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
+  const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = p[i] - (lr / bc1) * (mi / denom);
+}
+
+}  // namespace nerf

@@ -1,0 +1,435 @@
+// mlp_fused.cuh -- K4: the fused NeRF MLP (NeRFModel.py:158-202) as ONE tcgen05 kernel, used for
+//   MODE_FWD : positions/directions (or rays + depths) -> encoding -> 11 chained UMMA layers ->
+//              density/rgb heads; activations never leave the SM (training additionally bulk-stores
+//              a bf16 stash of every layer input for the weight-gradient kernel).
+//   MODE_BWD : the data-gradient chain dY_l = (dY_{l+1} . W_{l+1}) * relu'(h_l), same machinery
+//              with transposed weight images; emits every dY_l to the dstash.
+//
+// One CTA = one 128-row tile in flight, 2 CTAs per SM (each owns 256 TMEM columns and ~105 KB of
+// shared memory) so one CTA's epilogue overlaps the other's MMAs.  Warp roles:
+//   warps 0-3 : epilogue (thread = row = TMEM lane): TMEM -> regs -> bias/ReLU -> bf16 -> next A tile
+//   warp  4   : weight loader, 1-D bulk copies (TMA engine) of 8 KB K=16 weight images into a ring
+//   warp  5   : MMA issuer (one thread), tcgen05.mma kind::f16 128xNx16, accumulator in TMEM
+#pragma once
+#include "common.cuh"
+#include "mlp_layout.cuh"
+#include "tc.cuh"
+
+namespace nerf {
+
+constexpr int MODE_FWD = 0;
+constexpr int MODE_BWD = 1;
+
+struct MlpArgs {
+  const uint8_t* packed;     // weight images
+  const float* small;        // biases + heads (fp32)
+  // forward inputs: per-row (pos, dir) or per-ray (rays_o, rays_d, z) with n_sample > 0
+  const float* pos;
+  const float* dir;
+  const float* z;
+  int32_t n_sample;
+  int32_t pos_L, dir_L;
+  int32_t sm_wd, sm_bd, sm_w2, sm_b2;
+  int64_t n_rows;
+  int32_t n_tiles;
+  float* sigma_rgb;          // fwd out [n_rows,4]; bwd in
+  const float* d_sigma_rgb;  // bwd in [n_rows,4]
+  uint8_t* stash;            // fwd: written when non-null; bwd: read
+  uint8_t* dstash;           // bwd: written
+  int32_t stash_tile_bytes, dstash_tile_bytes;
+  int32_t st_pe, st_de, st_r1, ds_y10, ds_sr;
+  Program prog;
+};
+
+struct MlpSmem {
+  static constexpr int kAct = 0;
+  static constexpr int kEnc = kAct + kActBytes;
+  static constexpr int kRing = kEnc + kEncBytes;
+  static constexpr int kBars = kRing + kRingSlots * kRingSlotBytes;
+  static constexpr int kTotal = kBars + 128;
+};
+
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// sin/cos positional encoding of one scalar for level `i` from the exact decomposition
+// a_i = 2^i * fl32(fl32(pi) * x) (NeRFModel.py:151-156): the angle is carried in
+// turns as a two-term fp32 number, scaled by 2^i exactly, reduced to [-0.5,0.5] exactly, and only
+// then handed to the SFU (abs error ~5e-7, far below the bf16 operand rounding that follows).
+struct TurnsF { float hi, lo; };
+__device__ __forceinline__ TurnsF pe_turns_f(float x) {
+  const float a0 = __fmul_rn(3.14159274101257324f, x);
+  const float c_hi = 0.15915493667125702f;          // fl32(1/(2*pi))
+  const float c_lo = 6.4206383e-09f;                // 1/(2*pi) - c_hi
+  TurnsF t;
+  t.hi = __fmul_rn(a0, c_hi);
+  t.lo = __fmaf_rn(a0, c_hi, -t.hi) + a0 * c_lo;
+  return t;
+}
+__device__ __forceinline__ void pe_sincos(const TurnsF& t, int level, float& s, float& c) {
+  const float sc = __uint_as_float((uint32_t)(127 + level) << 23);   // 2^level
+  const float h = t.hi * sc;
+  const float r = (h - rintf(h)) + t.lo * sc;
+  const float a = 6.28318530717958647692f * r;
+  s = __sinf(a);
+  c = __cosf(a);
+}
+
+// Encodes v[3] with L levels into bf16 channels [v, sin0(v), cos0(v), ...] padded with zeros to
+// 8*n_kcores channels, stored at enc + kcore*2048 + row*16.
+template <int L, int NKC>
+__device__ __forceinline__ void write_encoding(uint32_t enc_smem, int row, const float v[3]) {
+  float e[NKC * 8];
+#pragma unroll
+  for (int i = 0; i < NKC * 8; ++i) e[i] = 0.0f;
+  e[0] = v[0]; e[1] = v[1]; e[2] = v[2];
+  if (L > 0) {
+    TurnsF t[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t[k] = pe_turns_f(v[k]);
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float s, c;
+        pe_sincos(t[k], i, s, c);
+        e[3 + 6 * i + k] = s;
+        e[6 + 6 * i + k] = c;
+      }
+    }
+  }
+#pragma unroll
+  for (int kc = 0; kc < NKC; ++kc) {
+    tc::st_shared_v4(enc_smem + kc * kKcoreBytes + row * 16,
+                     tc::pack_bf16x2(e[8 * kc + 0], e[8 * kc + 1]), tc::pack_bf16x2(e[8 * kc + 2], e[8 * kc + 3]),
+                     tc::pack_bf16x2(e[8 * kc + 4], e[8 * kc + 5]), tc::pack_bf16x2(e[8 * kc + 6], e[8 * kc + 7]));
+  }
+}
+
+__device__ __forceinline__ float softplus_f(float x) {        // torch default beta=1, threshold=20
+  return x > 20.0f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int MODE>
+__global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant__ MlpArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t s_base = tc::smem_u32(smem);
+  const uint32_t s_act = s_base + MlpSmem::kAct;
+  const uint32_t s_enc = s_base + MlpSmem::kEnc;
+  const uint32_t s_ring = s_base + MlpSmem::kRing;
+  const uint32_t s_bar = s_base + MlpSmem::kBars;
+  // barrier slots (8 B each): full[3] @0, empty[3] @24, acc_full @48, act_ready @56; tmem ptr @64
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 24, bar_acc = s_bar + 48, bar_act = s_bar + 56;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kBars + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRingSlots; ++i) { tc::mbar_init(bar_full + 8 * i, 1); tc::mbar_init(bar_empty + 8 * i, 1); }
+    tc::mbar_init(bar_acc, 1);
+    tc::mbar_init(bar_act, 128);
+    tc::fence_mbar_init();
+  }
+  if (warp == 4) tc::tmem_alloc(tc::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 256);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const Program& P = a.prog;
+
+  if (warp == 4) {
+    // ===================== weight loader =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        for (int si = 0; si < P.n_steps; ++si) {
+          const Step& st = P.s[si];
+          const uint32_t bytes = (uint32_t)st.n * 32u;
+          const int total = st.act_ksteps + st.enc_ksteps;
+          const uint8_t* src = a.packed + st.w_off;
+          for (int k = 0; k < total; ++k, ++it) {
+            const uint32_t slot = it % kRingSlots, ph = (it / kRingSlots) & 1u;
+            tc::mbar_wait(bar_empty + 8 * slot, ph ^ 1u);
+            tc::mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+            tc::bulk_g2s(s_ring + slot * kRingSlotBytes, src + (size_t)k * bytes, bytes, bar_full + 8 * slot);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0, act_phase = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        for (int si = 0; si < P.n_steps; ++si) {
+          const Step& st = P.s[si];
+          const int total = st.act_ksteps + st.enc_ksteps;
+          const uint32_t idesc = tc::umma_idesc_bf16(128, st.n, 0, 0);
+          tc::mbar_wait(bar_act, act_phase & 1u); ++act_phase;
+          tc::tc_fence_after();
+          for (int k = 0; k < total; ++k, ++it) {
+            const uint32_t slot = it % kRingSlots, ph = (it / kRingSlots) & 1u;
+            tc::mbar_wait(bar_full + 8 * slot, ph);
+            tc::tc_fence_after();
+            const uint32_t a_addr = (k < st.act_ksteps) ? (s_act + k * 2 * kKcoreBytes)
+                                                        : (s_enc + (k - st.act_ksteps) * 2 * kKcoreBytes);
+            const uint64_t adesc = tc::umma_smem_desc(a_addr, kKcoreBytes, 128);
+            const uint64_t bdesc = tc::umma_smem_desc(s_ring + slot * kRingSlotBytes, (uint32_t)st.n * 16u, 128);
+            tc::umma_bf16(tmem_base, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
+            tc::umma_commit(bar_empty + 8 * slot);
+          }
+          tc::umma_commit(bar_acc);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (thread = row) =====================
+    const int row = threadIdx.x;                       // 0..127 == TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool train = (a.stash != nullptr);
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const int64_t grow = (int64_t)tile * 128 + row;
+      const bool valid = grow < a.n_rows;
+      uint8_t* stash_tile = train ? a.stash + (size_t)tile * a.stash_tile_bytes : nullptr;
+      uint8_t* dstash_tile = (MODE == MODE_BWD) ? a.dstash + (size_t)tile * a.dstash_tile_bytes : nullptr;
+      float dirv[3] = {0.f, 0.f, 0.f};
+      float sigma_keep = 0.0f, dsp = 0.0f;
+      (void)sigma_keep; (void)dsp;
+
+      if (MODE == MODE_FWD ? train : true) {           // previous tile's bulk stores must have read ACT/ENC
+        if (row == 0) tc::bulk_wait_read0();
+        tc::named_bar_sync(1, 128);
+      }
+      // ---------------- prologue ----------------
+      if (MODE == MODE_FWD) {
+        float p[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          if (a.n_sample > 0) {                        // train.py:220-228: pts = o + d * z
+            const int64_t ray = grow / a.n_sample;
+            const float zz = a.z[grow];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              dirv[k] = a.dir[3 * ray + k];
+              p[k] = __fadd_rn(a.pos[3 * ray + k], __fmul_rn(dirv[k], zz));
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { p[k] = a.pos[3 * grow + k]; dirv[k] = a.dir[3 * grow + k]; }
+          }
+        }
+        if (a.pos_L == 10) write_encoding<10, 8>(s_enc, row, p);
+        else write_encoding<0, 8>(s_enc, row, p);
+        tc::fence_proxy_async_smem();
+        if (train) {
+          tc::named_bar_sync(1, 128);
+          if (row == 0) { tc::bulk_s2g(stash_tile + a.st_pe, s_enc, kEncBytes); tc::bulk_commit(); }
+        }
+      } else {
+        // backward prologue: d(rgb2 pre-act), d(density pre-act), dR1 = d_rgb_pre . W2 masked by r1 > 0
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f), o = make_float4(0.f, 0.5f, 0.5f, 0.5f);
+        if (valid) {
+          d = reinterpret_cast<const float4*>(a.d_sigma_rgb)[grow];
+          o = reinterpret_cast<const float4*>(a.sigma_rgb)[grow];
+        }
+        dsp = d.x * (1.0f - expf(-o.x));               // softplus'(x) = 1 - exp(-softplus(x))
+        const float d0 = d.y * o.y * (1.0f - o.y), d1 = d.z * o.z * (1.0f - o.z), d2 = d.w * o.w * (1.0f - o.w);
+        reinterpret_cast<float4*>(dstash_tile + a.ds_sr)[row] = make_float4(dsp, d0, d1, d2);
+        const float* w2 = a.small + a.sm_w2;
+        const uint4* r1 = reinterpret_cast<const uint4*>(stash_tile + a.st_r1);
+#pragma unroll 4
+        for (int kc = 0; kc < 16; ++kc) {
+          const uint4 m = __ldg(r1 + kc * 128 + row);
+          const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+          float g[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = kc * 8 + j;
+            const float v = d0 * __ldg(w2 + c) + d1 * __ldg(w2 + 128 + c) + d2 * __ldg(w2 + 256 + c);
+            const float h = (j & 1) ? bf16hi(mw[j >> 1]) : bf16lo(mw[j >> 1]);
+            g[j] = h > 0.0f ? v : 0.0f;
+          }
+          tc::st_shared_v4(s_act + kc * kKcoreBytes + row * 16, tc::pack_bf16x2(g[0], g[1]),
+                           tc::pack_bf16x2(g[2], g[3]), tc::pack_bf16x2(g[4], g[5]), tc::pack_bf16x2(g[6], g[7]));
+        }
+        tc::fence_proxy_async_smem();
+        tc::named_bar_sync(1, 128);
+        if (row == 0) { tc::bulk_s2g(dstash_tile + a.ds_y10, s_act, 16 * kKcoreBytes); tc::bulk_commit(); }
+      }
+      tc::mbar_arrive(bar_act);
+
+      // ---------------- layer steps ----------------
+      for (int si = 0; si < P.n_steps; ++si) {
+        const Step& st = P.s[si];
+        tc::mbar_wait(bar_acc, acc_phase & 1u); ++acc_phase;
+        tc::tc_fence_after();
+        const bool store_out = (MODE == MODE_BWD) || train;
+        if (store_out) {                               // an earlier bulk store may still be reading ACT/ENC
+          if (row == 0) tc::bulk_wait_read0();
+          tc::named_bar_sync(1, 128);
+        }
+        const int n_chunks = st.n >> 5;
+        if (MODE == MODE_FWD) {
+          const float* bias = a.small + st.bias_off;
+          float dens = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+          const bool is_rgb = (st.flags & EPI_RGB) != 0;
+          const bool is_dens = (st.flags & EPI_DENSITY) != 0;
+          for (int ch = 0; ch < n_chunks; ++ch) {
+            uint32_t v[32];
+            tc::tmem_ld32(t_lane + ch * 32, v);
+            tc::tmem_wait_ld();
+            float y[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ch * 32 + j));
+              y[j + 0] = fmaxf(__uint_as_float(v[j + 0]) + b4.x, 0.0f);
+              y[j + 1] = fmaxf(__uint_as_float(v[j + 1]) + b4.y, 0.0f);
+              y[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + b4.z, 0.0f);
+              y[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + b4.w, 0.0f);
+            }
+            if (is_dens) {
+              const float* wd = a.small + a.sm_wd + ch * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(wd + j));
+                dens = fmaf(y[j], w4.x, dens); dens = fmaf(y[j + 1], w4.y, dens);
+                dens = fmaf(y[j + 2], w4.z, dens); dens = fmaf(y[j + 3], w4.w, dens);
+              }
+            }
+            if (is_rgb) {
+              const float* w2 = a.small + a.sm_w2 + ch * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 wa = __ldg(reinterpret_cast<const float4*>(w2 + j));
+                const float4 wb = __ldg(reinterpret_cast<const float4*>(w2 + 128 + j));
+                const float4 wc = __ldg(reinterpret_cast<const float4*>(w2 + 256 + j));
+                c0 = fmaf(y[j], wa.x, c0); c0 = fmaf(y[j + 1], wa.y, c0); c0 = fmaf(y[j + 2], wa.z, c0); c0 = fmaf(y[j + 3], wa.w, c0);
+                c1 = fmaf(y[j], wb.x, c1); c1 = fmaf(y[j + 1], wb.y, c1); c1 = fmaf(y[j + 2], wb.z, c1); c1 = fmaf(y[j + 3], wb.w, c1);
+                c2 = fmaf(y[j], wc.x, c2); c2 = fmaf(y[j + 1], wc.y, c2); c2 = fmaf(y[j + 2], wc.z, c2); c2 = fmaf(y[j + 3], wc.w, c2);
+              }
+            }
+            if (!is_rgb || train) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                tc::st_shared_v4(s_act + (ch * 4 + q) * kKcoreBytes + row * 16,
+                                 tc::pack_bf16x2(y[8 * q + 0], y[8 * q + 1]), tc::pack_bf16x2(y[8 * q + 2], y[8 * q + 3]),
+                                 tc::pack_bf16x2(y[8 * q + 4], y[8 * q + 5]), tc::pack_bf16x2(y[8 * q + 6], y[8 * q + 7]));
+            }
+          }
+          if (is_dens) sigma_keep = softplus_f(dens + __ldg(a.small + a.sm_bd));
+          if (is_rgb && valid) {
+            const float* b2 = a.small + a.sm_b2;
+            reinterpret_cast<float4*>(a.sigma_rgb)[grow] =
+                make_float4(sigma_keep, sigmoid_f(c0 + __ldg(b2)), sigmoid_f(c1 + __ldg(b2 + 1)), sigmoid_f(c2 + __ldg(b2 + 2)));
+          }
+          if (st.flags & EPI_WRITE_DIR) {
+            if (a.dir_L == 4) write_encoding<4, 4>(s_enc, row, dirv);
+            else write_encoding<0, 4>(s_enc, row, dirv);
+          }
+        } else {
+          const uint4* hm = reinterpret_cast<const uint4*>(stash_tile + st.mask_off);
+          const bool add_sigma = (st.flags & EPI_BWD_SIGMA) != 0;
+          for (int ch = 0; ch < n_chunks; ++ch) {
+            uint4 m[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m[q] = __ldg(hm + (ch * 4 + q) * 128 + row);
+            uint32_t v[32];
+            tc::tmem_ld32(t_lane + ch * 32, v);
+            tc::tmem_wait_ld();
+            float y[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
+            if (add_sigma) {                           // density head: d h8 += d_sigma_pre * w_d
+              const float* wd = a.small + a.sm_wd + ch * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(wd + j));
+                y[j] = fmaf(dsp, w4.x, y[j]); y[j + 1] = fmaf(dsp, w4.y, y[j + 1]);
+                y[j + 2] = fmaf(dsp, w4.z, y[j + 2]); y[j + 3] = fmaf(dsp, w4.w, y[j + 3]);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t mw[4] = {m[q].x, m[q].y, m[q].z, m[q].w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float h = (j & 1) ? bf16hi(mw[j >> 1]) : bf16lo(mw[j >> 1]);
+                if (!(h > 0.0f)) y[8 * q + j] = 0.0f;
+              }
+              tc::st_shared_v4(s_act + (ch * 4 + q) * kKcoreBytes + row * 16,
+                               tc::pack_bf16x2(y[8 * q + 0], y[8 * q + 1]), tc::pack_bf16x2(y[8 * q + 2], y[8 * q + 3]),
+                               tc::pack_bf16x2(y[8 * q + 4], y[8 * q + 5]), tc::pack_bf16x2(y[8 * q + 6], y[8 * q + 7]));
+            }
+          }
+        }
+        tc::tc_fence_before();                         // TMEM reads retired before the next MMA overwrites
+        tc::fence_proxy_async_smem();                  // ACT/ENC writes visible to UMMA / bulk stores
+        if (store_out) {
+          tc::named_bar_sync(1, 128);
+          if (row == 0) {
+            uint8_t* dst = (MODE == MODE_FWD ? stash_tile : dstash_tile) + st.stash_off;
+            tc::bulk_s2g(dst, s_act, (uint32_t)st.n * 256u);          // n channels x 128 rows x 2 B
+            if (MODE == MODE_FWD && (st.flags & EPI_WRITE_DIR)) tc::bulk_s2g(stash_tile + a.st_de, s_enc, 4 * kKcoreBytes);
+            tc::bulk_commit();
+          }
+        }
+        if (!(st.flags & EPI_LAST)) tc::mbar_arrive(bar_act);
+      }
+    }
+    if (row == 0) tc::bulk_wait0();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight packing: flat fp32 parameters -> bf16 UMMA images (fwd + transposed dgrad) + fp32 table.
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_images_kernel(const float* __restrict__ params, Program prog, uint8_t* __restrict__ packed) {
+  const Step st = prog.s[blockIdx.y];
+  const int total_k = (st.act_ksteps + st.enc_ksteps) * 16;
+  const int n_elems = total_k * st.n;
+  __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(packed + st.w_off);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_elems; idx += gridDim.x * blockDim.x) {
+    // idx enumerates the destination linearly: [kstep][kc][n][8]
+    const int j = idx & 7;
+    const int n = (idx >> 3) % st.n;
+    const int kc_lin = (idx >> 3) / st.n;              // = kstep*2 + kc
+    const int kk = kc_lin * 8 + j;
+    float v = 0.0f;
+    if (n < st.p_rows) {
+      if (st.p_transpose) {
+        if (kk < st.act_cols) v = params[st.p_w + (int64_t)kk * st.p_in + n];
+      } else {
+        const int act_k = st.act_ksteps * 16;
+        if (kk < act_k) { if (kk < st.act_cols) v = params[st.p_w + (int64_t)n * st.p_in + kk]; }
+        else { const int e = kk - act_k; if (e < st.enc_cols) v = params[st.p_w + (int64_t)n * st.p_in + st.enc_col0 + e]; }
+      }
+    }
+    img[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+struct PackSmallArgs {
+  int32_t n_bias;                    // forward steps
+  int32_t b_src[kMaxSteps];          // float offsets of the step biases in the flat vector
+  int32_t b_n[kMaxSteps];
+  int32_t wd_src, bd_src, w2_src, b2_src;
+  int32_t sm_wd, sm_bd, sm_w2, sm_b2;
+};
+__global__ void pack_small_kernel(const float* __restrict__ params, PackSmallArgs p, float* __restrict__ small) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.n_bias * 256) {
+    const int s = i >> 8, c = i & 255;
+    small[i] = c < p.b_n[s] ? params[p.b_src[s] + c] : 0.0f;
+  }
+  if (i < 256) small[p.sm_wd + i] = params[p.wd_src + i];
+  if (i < 384) small[p.sm_w2 + i] = params[p.w2_src + i];
+  if (i < 3) small[p.sm_b2 + i] = params[p.b2_src + i];
+  if (i == 0) { small[p.sm_bd] = params[p.bd_src]; small[p.sm_bd + 1] = 0.f; small[p.sm_bd + 2] = 0.f; small[p.sm_bd + 3] = 0.f; small[p.sm_b2 + 3] = 0.f; }
+}
+
+}  // namespace nerf

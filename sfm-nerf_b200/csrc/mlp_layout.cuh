@@ -1,0 +1,221 @@
+// mlp_layout.cuh -- parameter layout of the live NeRFmodel (NeRFModel.py:102-140) and the
+// "layer programs" the fused tcgen05 kernels interpret (host + device).
+//
+// On-chip activation tiles and every HBM stash block use ONE blocked layout
+//     [k_core = channel/8][row 0..127][8 channels]   (16 B per (k_core,row), 2 KB per k_core)
+// which is simultaneously
+//   * the no-swizzle K-major UMMA canonical layout (LBO = 2048 B, SBO = 128 B) when the channel
+//     axis is the contraction axis (forward / dgrad A operands), and
+//   * the no-swizzle MN-major canonical layout (LBO = 128 B, SBO = row_count*16 B) when the row
+//     (sample) axis is the contraction axis (wgrad operands),
+// so tiles move between SMEM and HBM with plain 1-D bulk copies and no re-tiling.
+// Packed weights use the same form with rows = output features, one image per K=16 step:
+//     [k_step][k_core 0..1][n][8]   (n*32 B per k-step).
+#pragma once
+#include <stdint.h>
+
+namespace nerf {
+
+constexpr int kMaxSteps = 12;
+constexpr int kNumLinear = 13;          // fc1, fc_layers x4, skip, fc_layers2 x3, density, feature, rgb1, rgb2
+constexpr int kKcoreBytes = 2048;       // 128 rows x 16 B
+constexpr int kActBytes = 32 * kKcoreBytes;   // 256 channels = 64 KB
+constexpr int kEncBytes = 8 * kKcoreBytes;    // 64 channels  = 16 KB
+constexpr int kRingSlots = 3;
+constexpr int kRingSlotBytes = 256 * 32;      // one K=16 step of an N=256 layer = 8 KB
+
+// epilogue flags
+enum : int32_t {
+  EPI_WRITE_DIR = 2,      // fwd: also place the direction encoding into ENC (after the skip layer)
+  EPI_DENSITY = 4,        // fwd: density head from fp32 registers (NeRFModel.py:192)
+  EPI_RGB = 8,            // fwd: rgb head + sigmoid (NeRFModel.py:199-200), writes sigma_rgb
+  EPI_BWD_SIGMA = 16,     // bwd: add d_sigma_pre * w_density before masking
+  EPI_LAST = 32           // no further step consumes ACT
+};
+
+struct Step {
+  int32_t n;            // UMMA N
+  int32_t act_ksteps;   // K=16 steps read from ACT (k_cores 0..)
+  int32_t enc_ksteps;   // K=16 steps read from ENC
+  int32_t w_off;        // byte offset of this step's weight image inside the packed buffer
+  int32_t bias_off;     // float offset inside the packed "small" table, -1 = none
+  int32_t flags;
+  int32_t stash_off;    // byte offset of the OUTPUT block inside a tile's stash (fwd) / dstash (bwd)
+  int32_t mask_off;     // bwd: byte offset (fwd stash) of the activation whose sign masks the output
+  // pack-time description of the B operand (rows n, contraction index kk):
+  int32_t p_w;          // float offset of the Linear weight in the flat parameter vector
+  int32_t p_in;         // its in_features (row stride)
+  int32_t p_transpose;  // 0: B[n][kk] = W[n][col(kk)];  1: B[n][kk] = W[kk][n]  (dgrad)
+  int32_t act_cols;     // kk < 16*act_ksteps maps to source column kk (valid if < act_cols)
+  int32_t enc_col0;     // kk >= 16*act_ksteps maps to source column enc_col0 + (kk - 16*act_ksteps)
+  int32_t enc_cols;     //   valid if (kk - 16*act_ksteps) < enc_cols
+  int32_t p_rows;       // valid rows n
+  int32_t pad_;
+};
+
+struct Program {
+  int32_t n_steps;
+  int32_t image_bytes;     // total bytes of the steps' weight images
+  int32_t total_ksteps;    // sum over steps of (act_ksteps + enc_ksteps)
+  int32_t pad_;
+  Step s[kMaxSteps];
+};
+
+// One wgrad work item: dW[m][n] = sum_rows dY[row][m] * X[row][n]
+struct WgradItem {
+  int32_t dy_off;       // byte offset of the dY block inside a dstash tile
+  int32_t m_kcores;     // 32 (M = 256, two UMMA halves) or 16 (M = 128)
+  int32_t x_off;        // byte offset of the input block inside a (fwd) stash tile
+  int32_t n;            // UMMA N (multiple of 16, <= 256)
+  int32_t n_valid;      // columns actually written
+  int32_t w_off;        // float offset of the Linear weight in the flat vector
+  int32_t in_f;         // its row stride
+  int32_t col0;         // first column written
+  int32_t b_off;        // float offset of the bias (-1: this item does not own the bias)
+  int32_t cost;         // relative cost per tile (for CTA partitioning)
+};
+constexpr int kMaxWgradItems = 16;
+
+struct ModelLayout {
+  int32_t layout;
+  int32_t pos_in, dir_in;            // 63/27 or 3/3
+  int32_t pos_L, dir_L;              // 10/4 or 0/0
+  int32_t n_params;
+  int32_t w_off[kNumLinear], b_off[kNumLinear], out_f[kNumLinear], in_f[kNumLinear];
+  // packed buffer: [fwd image][bwd image][small fp32 table]
+  Program fwd, bwd;
+  int32_t small_off;                 // byte offset of the fp32 table
+  int32_t small_floats;
+  int32_t packed_bytes;
+  // small table (float offsets): biases of the 11 MMA layers at 256*i, then heads
+  int32_t sm_wd, sm_bd, sm_w2, sm_b2;
+  // per-tile stash (bytes): PE, DE, H0..H9 (h0..h8, feature), R1
+  int32_t st_pe, st_de, st_h[10], st_r1, stash_tile_bytes;
+  // per-tile dstash: dY0..dY9 (64 KB each), dY10 (32 KB), dsr fp32 [128][4]
+  int32_t ds_y[11], ds_sr, dstash_tile_bytes;
+  int32_t n_wgrad;
+  WgradItem wg[kMaxWgradItems];
+};
+
+enum { L_FC1 = 0, L_FC0 = 1, L_SKIP = 5, L_FC2_0 = 6, L_DENS = 9, L_FEAT = 10, L_RGB1 = 11, L_RGB2 = 12 };
+
+inline bool build_model_layout(int layout, ModelLayout& m) {
+  if (layout != 0 && layout != 1) return false;
+  m = ModelLayout{};
+  m.layout = layout;
+  const bool pe = (layout == 0);
+  m.pos_L = pe ? 10 : 0; m.dir_L = pe ? 4 : 0;
+  m.pos_in = pe ? 63 : 3; m.dir_in = pe ? 27 : 3;
+  const int C = 256;
+  const int outs[kNumLinear] = {C, C, C, C, C, C, C, C, C, 1, C, 128, 3};
+  const int ins[kNumLinear] = {m.pos_in, C, C, C, C, C + m.pos_in, C, C, C, C, C, C + m.dir_in, 128};
+  int off = 0;
+  for (int i = 0; i < kNumLinear; ++i) {
+    m.out_f[i] = outs[i]; m.in_f[i] = ins[i];
+    m.w_off[i] = off; off += outs[i] * ins[i];
+    m.b_off[i] = off; off += outs[i];
+  }
+  m.n_params = off;
+
+  const int pos_ks = (m.pos_in + 15) / 16;     // 4 (PE) or 1
+  const int dir_ks = (m.dir_in + 15) / 16;     // 2 (PE) or 1
+
+  // stash
+  int so = 0;
+  m.st_pe = so; so += 8 * kKcoreBytes;
+  m.st_de = so; so += 4 * kKcoreBytes;
+  for (int i = 0; i < 10; ++i) { m.st_h[i] = so; so += kActBytes; }
+  m.st_r1 = so; so += 16 * kKcoreBytes;
+  m.stash_tile_bytes = so;
+  int dso = 0;
+  for (int i = 0; i < 10; ++i) { m.ds_y[i] = dso; dso += kActBytes; }
+  m.ds_y[10] = dso; dso += 16 * kKcoreBytes;
+  m.ds_sr = dso; dso += 128 * 16;
+  m.dstash_tile_bytes = dso;
+
+  auto add = [](Program& p, Step st) {
+    st.w_off = p.image_bytes;
+    p.image_bytes += (st.act_ksteps + st.enc_ksteps) * st.n * 32;
+    p.total_ksteps += st.act_ksteps + st.enc_ksteps;
+    p.s[p.n_steps++] = st;
+  };
+  // ---- forward program ------------------------------------------------------------------
+  int bias_slot = 0;
+  auto fstep = [&](int lin, int n, int act_ks, int enc_ks, int enc_col0, int enc_cols, int flags,
+                   int stash_off) {
+    Step st{};
+    st.n = n; st.act_ksteps = act_ks; st.enc_ksteps = enc_ks;
+    st.bias_off = 256 * bias_slot++;
+    st.flags = flags; st.stash_off = stash_off; st.mask_off = -1;
+    st.p_w = m.w_off[lin]; st.p_in = m.in_f[lin]; st.p_transpose = 0;
+    st.act_cols = act_ks ? 256 : 0; st.enc_col0 = enc_col0; st.enc_cols = enc_cols;
+    st.p_rows = m.out_f[lin];
+    return st;
+  };
+  Program& f = m.fwd;
+  add(f, fstep(L_FC1, 256, 0, pos_ks, 0, m.pos_in, 0, m.st_h[0]));
+  for (int i = 0; i < 4; ++i) add(f, fstep(L_FC0 + i, 256, 16, 0, 0, 0, 0, m.st_h[1 + i]));
+  add(f, fstep(L_SKIP, 256, 16, pos_ks, 256, m.pos_in, EPI_WRITE_DIR, m.st_h[5]));
+  for (int i = 0; i < 3; ++i)
+    add(f, fstep(L_FC2_0 + i, 256, 16, 0, 0, 0, (i == 2 ? EPI_DENSITY : 0), m.st_h[6 + i]));
+  add(f, fstep(L_FEAT, 256, 16, 0, 0, 0, 0, m.st_h[9]));
+  add(f, fstep(L_RGB1, 128, 16, dir_ks, 256, m.dir_in, EPI_RGB | EPI_LAST, m.st_r1));
+
+  // ---- backward (dgrad) program: dX = dY . W, masked by relu'(x) ---------------------------
+  auto bstep = [&](int lin, int act_ks, int flags, int dstash_off, int mask_off) {
+    Step st{};
+    st.n = 256; st.act_ksteps = act_ks; st.enc_ksteps = 0;
+    st.bias_off = -1; st.flags = flags; st.stash_off = dstash_off; st.mask_off = mask_off;
+    st.p_w = m.w_off[lin]; st.p_in = m.in_f[lin]; st.p_transpose = 1;
+    st.act_cols = m.out_f[lin]; st.enc_col0 = 0; st.enc_cols = 0;
+    st.p_rows = 256;                    // only the first 256 input columns carry gradient
+    return st;
+  };
+  Program& b = m.bwd;
+  // dY10 (rgb1 pre-activation grad, 128 ch) is produced by the prologue.  Step j outputs the
+  // masked gradient w.r.t. the pre-activation of forward step (9-j): dY9 (feature) ... dY0 (fc1).
+  add(b, bstep(L_RGB1, 8, 0, m.ds_y[9], m.st_h[9]));
+  add(b, bstep(L_FEAT, 16, EPI_BWD_SIGMA, m.ds_y[8], m.st_h[8]));
+  add(b, bstep(L_FC2_0 + 2, 16, 0, m.ds_y[7], m.st_h[7]));
+  add(b, bstep(L_FC2_0 + 1, 16, 0, m.ds_y[6], m.st_h[6]));
+  add(b, bstep(L_FC2_0 + 0, 16, 0, m.ds_y[5], m.st_h[5]));
+  add(b, bstep(L_SKIP, 16, 0, m.ds_y[4], m.st_h[4]));
+  add(b, bstep(L_FC0 + 3, 16, 0, m.ds_y[3], m.st_h[3]));
+  add(b, bstep(L_FC0 + 2, 16, 0, m.ds_y[2], m.st_h[2]));
+  add(b, bstep(L_FC0 + 1, 16, 0, m.ds_y[1], m.st_h[1]));
+  add(b, bstep(L_FC0 + 0, 16, EPI_LAST, m.ds_y[0], m.st_h[0]));
+
+  // packed buffer
+  const int fwd_bytes = f.image_bytes, bwd_bytes = b.image_bytes;
+  for (int i = 0; i < b.n_steps; ++i) b.s[i].w_off += fwd_bytes;
+  m.sm_wd = 256 * 11; m.sm_bd = m.sm_wd + 256; m.sm_w2 = m.sm_bd + 4; m.sm_b2 = m.sm_w2 + 384;
+  m.small_floats = m.sm_b2 + 4;
+  m.small_off = fwd_bytes + bwd_bytes;
+  m.packed_bytes = m.small_off + m.small_floats * 4;
+
+  // ---- wgrad work items -------------------------------------------------------------------
+  auto wadd = [&](int lin, int dy_off, int m_kcores, int x_off, int n, int n_valid, int col0,
+                  bool owns_bias) {
+    WgradItem w{};
+    w.dy_off = dy_off; w.m_kcores = m_kcores; w.x_off = x_off; w.n = n; w.n_valid = n_valid;
+    w.w_off = m.w_off[lin]; w.in_f = m.in_f[lin]; w.col0 = col0;
+    w.b_off = owns_bias ? m.b_off[lin] : -1;
+    // cost ~ MMA cycles (m_halves * n/2 per k-step) vs. load bytes (both per 64 rows), whichever binds
+    const int mma = (m_kcores / 16) * n * 2;
+    const int ld = (m_kcores + n / 8) * 8;
+    w.cost = mma > ld ? mma : ld;
+    m.wg[m.n_wgrad++] = w;
+  };
+  const int pos_n = pos_ks * 16, dir_n = dir_ks * 16;
+  wadd(L_FC1, m.ds_y[0], 32, m.st_pe, pos_n, m.pos_in, 0, true);
+  for (int i = 0; i < 4; ++i) wadd(L_FC0 + i, m.ds_y[1 + i], 32, m.st_h[i], 256, 256, 0, true);
+  wadd(L_SKIP, m.ds_y[5], 32, m.st_h[4], 256, 256, 0, true);
+  wadd(L_SKIP, m.ds_y[5], 32, m.st_pe, pos_n, m.pos_in, 256, false);
+  for (int i = 0; i < 3; ++i) wadd(L_FC2_0 + i, m.ds_y[6 + i], 32, m.st_h[5 + i], 256, 256, 0, true);
+  wadd(L_FEAT, m.ds_y[9], 32, m.st_h[8], 256, 256, 0, true);
+  wadd(L_RGB1, m.ds_y[10], 16, m.st_h[9], 256, 256, 0, true);
+  wadd(L_RGB1, m.ds_y[10], 16, m.st_de, dir_n, m.dir_in, 256, false);
+  return true;
+}
+
+}  // namespace nerf

@@ -1,0 +1,222 @@
+// wgrad.cuh -- K4b weight gradients: dW_l[o][i] = sum_rows dY_l[row][o] * X_l[row][i] on tcgen05.
+// The contraction axis is the SAMPLE axis, so both operands are read MN-major straight from the
+// blocked stash/dstash tiles ([k_core][row][8]); the fp32 accumulator (up to 256x256) lives in the
+// whole 512-column TMEM of one SM for the CTA's entire row range and is added into the flat
+// gradient vector once at the end (split-K over CTAs, red.global.add.f32).
+//   warp 0    : loader -- 64-row half tiles of dY and X, 1 KB bulk copies per k_core, 3-stage ring
+//   warp 1    : MMA issuer (one thread)
+//   warps 2-5 : bias gradients (column sums of dY from the staged tile) + final TMEM -> HBM epilogue
+// Head gradients (density_layer, rgb_layer2: N < 16, not UMMA shapes) run on CUDA cores.
+#pragma once
+#include "common.cuh"
+#include "mlp_layout.cuh"
+#include "tc.cuh"
+
+namespace nerf {
+
+constexpr int kWgStages = 3;
+constexpr int kWgStageBytes = 65536;       // dY half tile (<= 32 KB) + X half tile (<= 32 KB)
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 128;
+
+struct WgradArgs {
+  const uint8_t* stash;
+  const uint8_t* dstash;
+  float* grads;
+  int32_t stash_tile_bytes, dstash_tile_bytes;
+  int32_t n_tiles, n_items;
+  int32_t cta_begin[kMaxWgradItems + 1];   // CTAs [cta_begin[i], cta_begin[i+1]) work on item i
+  WgradItem items[kMaxWgradItems];
+};
+
+__global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t s_base = tc::smem_u32(smem);
+  const uint32_t s_bar = s_base + kWgStages * kWgStageBytes;
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 24, bar_acc = s_bar + 48;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kWgStages * kWgStageBytes + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) { tc::mbar_init(bar_full + 8 * i, 1); tc::mbar_init(bar_empty + 8 * i, 5); }
+    tc::mbar_init(bar_acc, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(tc::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // which item / row range is mine
+  int item = 0;
+  while (item + 1 < a.n_items && (int)blockIdx.x >= a.cta_begin[item + 1]) ++item;
+  const WgradItem& W = a.items[item];
+  const int splits = a.cta_begin[item + 1] - a.cta_begin[item];
+  const int split = (int)blockIdx.x - a.cta_begin[item];
+  const int t0 = (int)(((int64_t)a.n_tiles * split) / splits);
+  const int t1 = (int)(((int64_t)a.n_tiles * (split + 1)) / splits);
+  const int n_stages_total = (t1 - t0) * 2;
+  const int m_halves = W.m_kcores / 16;
+  const int x_kcores = W.n / 8;
+
+  if (warp == 0) {
+    // ===================== loader =====================
+    for (int s = 0; s < n_stages_total; ++s) {
+      const int tile = t0 + (s >> 1), half = s & 1;
+      const uint32_t slot = s % kWgStages, ph = (s / kWgStages) & 1u;
+      const uint32_t stage = s_base + slot * kWgStageBytes;
+      if (lane == 0) {
+        tc::mbar_wait(bar_empty + 8 * slot, ph ^ 1u);
+        tc::mbar_arrive_expect_tx(bar_full + 8 * slot, (uint32_t)(W.m_kcores + x_kcores) * 1024u);
+      }
+      __syncwarp();
+      const uint8_t* dy = a.dstash + (size_t)tile * a.dstash_tile_bytes + W.dy_off + half * 1024;
+      const uint8_t* x = a.stash + (size_t)tile * a.stash_tile_bytes + W.x_off + half * 1024;
+      for (int c = lane; c < W.m_kcores; c += 32) tc::bulk_g2s(stage + c * 1024, dy + (size_t)c * kKcoreBytes, 1024, bar_full + 8 * slot);
+      for (int c = lane; c < x_kcores; c += 32) tc::bulk_g2s(stage + 32768 + c * 1024, x + (size_t)c * kKcoreBytes, 1024, bar_full + 8 * slot);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc::umma_idesc_bf16(128, W.n, 1, 1);
+      for (int s = 0; s < n_stages_total; ++s) {
+        const uint32_t slot = s % kWgStages, ph = (s / kWgStages) & 1u;
+        const uint32_t stage = s_base + slot * kWgStageBytes;
+        tc::mbar_wait(bar_full + 8 * slot, ph);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t bdesc = tc::umma_smem_desc(stage + 32768 + ks * 256, 128, 1024);
+          for (int mh = 0; mh < m_halves; ++mh) {
+            const uint64_t adesc = tc::umma_smem_desc(stage + mh * 16384 + ks * 256, 128, 1024);
+            tc::umma_bf16(tmem_base + mh * W.n, adesc, bdesc, idesc, (s > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        tc::umma_commit(bar_empty + 8 * slot);
+      }
+      tc::umma_commit(bar_acc);
+    }
+    __syncwarp();
+  } else {
+    // ===================== bias sums + epilogue =====================
+    const int q = warp - 2;                       // k_cores q, q+4, ...
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    for (int s = 0; s < n_stages_total; ++s) {
+      const uint32_t slot = s % kWgStages, ph = (s / kWgStages) & 1u;
+      const uint32_t stage = s_base + slot * kWgStageBytes;
+      tc::mbar_wait(bar_full + 8 * slot, ph);
+      if (W.b_off >= 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i * 4 < W.m_kcores) {
+            const int kc = q + 4 * i;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              uint32_t u0, u1, u2, u3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(stage + kc * 1024 + (lane + 32 * rr) * 16));
+              acc[i][0] += __uint_as_float(u0 << 16); acc[i][1] += __uint_as_float(u0 & 0xffff0000u);
+              acc[i][2] += __uint_as_float(u1 << 16); acc[i][3] += __uint_as_float(u1 & 0xffff0000u);
+              acc[i][4] += __uint_as_float(u2 << 16); acc[i][5] += __uint_as_float(u2 & 0xffff0000u);
+              acc[i][6] += __uint_as_float(u3 << 16); acc[i][7] += __uint_as_float(u3 & 0xffff0000u);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(bar_empty + 8 * slot);
+    }
+    if (W.b_off >= 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i * 4 < W.m_kcores) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v = acc[i][j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) atomicAdd(a.grads + W.b_off + (q + 4 * i) * 8 + j, v);
+          }
+        }
+      }
+    }
+    // final epilogue: TMEM accumulator -> gradient vector
+    tc::mbar_wait(bar_acc, 0);
+    tc::tc_fence_after();
+    const int lq = warp & 3;                      // TMEM lane quarter this warp may read
+    const int n_chunks = (W.n + 31) >> 5;
+    if (n_stages_total > 0) {
+      for (int mh = 0; mh < m_halves; ++mh) {
+        const int o = mh * 128 + lq * 32 + lane;
+        float* dst = a.grads + W.w_off + (int64_t)o * W.in_f + W.col0;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          uint32_t v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + mh * W.n + ch * 32, v);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (ch * 32 + j < W.n_valid) atomicAdd(dst + ch * 32 + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// Head gradients on CUDA cores (train: dL/d density_layer, dL/d rgb_layer2).
+//   d w_d[j]   = sum_rows dsp[row] * h8[row][j]      d b_d    = sum_rows dsp[row]
+//   d W2[c][j] = sum_rows drgb_pre[c][row] * r1[row][j]   d b2[c] = sum_rows drgb_pre[c][row]
+// Thread t < 256: density channel t; 256 <= t < 384: rgb1 channel t-256.
+struct HeadGradArgs {
+  const uint8_t* stash;
+  const uint8_t* dstash;
+  float* grads;
+  int32_t stash_tile_bytes, dstash_tile_bytes, n_tiles;
+  int32_t st_h8, st_r1, ds_sr;
+  int32_t g_wd, g_bd, g_w2, g_b2;     // float offsets in the flat gradient vector
+};
+__global__ void __launch_bounds__(384) head_grad_kernel(const HeadGradArgs a) {
+  __shared__ float4 dsr[128];
+  const int t = threadIdx.x;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accb = 0.f, accb1 = 0.f, accb2 = 0.f;
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const uint8_t* st = a.stash + (size_t)tile * a.stash_tile_bytes;
+    __syncthreads();
+    if (t < 128) dsr[t] = reinterpret_cast<const float4*>(a.dstash + (size_t)tile * a.dstash_tile_bytes + a.ds_sr)[t];
+    __syncthreads();
+    if (t < 256) {
+      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(st + a.st_h8) + (t >> 3) * 1024 + (t & 7);
+#pragma unroll 8
+      for (int r = 0; r < 128; ++r) acc0 = fmaf(dsr[r].x, __bfloat162float(h[r * 8]), acc0);
+      if (t == 0) for (int r = 0; r < 128; ++r) accb += dsr[r].x;
+    } else {
+      const int c = t - 256;
+      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(st + a.st_r1) + (c >> 3) * 1024 + (c & 7);
+#pragma unroll 8
+      for (int r = 0; r < 128; ++r) {
+        const float v = __bfloat162float(h[r * 8]);
+        const float4 d = dsr[r];
+        acc0 = fmaf(d.y, v, acc0); acc1 = fmaf(d.z, v, acc1); acc2 = fmaf(d.w, v, acc2);
+      }
+      if (c == 0) for (int r = 0; r < 128; ++r) { accb += dsr[r].y; accb1 += dsr[r].z; accb2 += dsr[r].w; }
+    }
+  }
+  if (t < 256) {
+    atomicAdd(a.grads + a.g_wd + t, acc0);
+    if (t == 0) atomicAdd(a.grads + a.g_bd, accb);
+  } else {
+    const int c = t - 256;
+    atomicAdd(a.grads + a.g_w2 + c, acc0);
+    atomicAdd(a.grads + a.g_w2 + 128 + c, acc1);
+    atomicAdd(a.grads + a.g_w2 + 256 + c, acc2);
+    if (c == 0) { atomicAdd(a.grads + a.g_b2, accb); atomicAdd(a.grads + a.g_b2 + 1, accb1); atomicAdd(a.grads + a.g_b2 + 2, accb2); }
+  }
+}
+
+}  // namespace nerf

@@ -1,0 +1,335 @@
+"""Host-side glue between torch tensors (device memory, streams, autograd, torch.distributed) and the
+C ABI of libnerf_b200.so.  No arithmetic of the hot path happens here: every function below
+validates shapes, allocates outputs and enqueues kernels on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and t.device.type != "cuda":
+            raise _lib.NerfB200Error("libnerf_b200 needs CUDA tensors (no CPU fallback); got a tensor on %s" % t.device)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# Model state: flat fp32 parameters (state_dict order) + packed bf16 UMMA weight images
+# ------------------------------------------------------------------------------------------
+class ModelState:
+    def __init__(self, layout, flat):
+        lib = _lib.load()
+        self.layout = int(layout)
+        self.flat = flat
+        self.device = flat.device
+        self.n_params = int(lib.nerf_param_count(self.layout))
+        assert flat.numel() == self.n_params
+        self.offsets = [int(lib.nerf_param_offset(self.layout, i)) for i in range(26)]
+        self.packed = torch.empty(int(lib.nerf_mlp_packed_bytes(self.layout)), dtype=torch.uint8, device=flat.device)
+        self.frozen = False          # fast paths set this while they manage repacking themselves
+
+    @classmethod
+    def adopt(cls, layout, params):
+        """Move the 26 parameter tensors into one flat buffer and re-point them at views of it."""
+        lib = _lib.load()
+        n = int(lib.nerf_param_count(layout))
+        if n < 0:
+            _lib.check(n, "nerf_param_count")
+        dev = params[0].device
+        _need_cuda(params[0])
+        flat = torch.empty(n, dtype=torch.float32, device=dev)
+        offs = [int(lib.nerf_param_offset(layout, i)) for i in range(26)]
+        if sum(p.numel() for p in params) != n:
+            raise _lib.NerfB200Error("parameter shapes do not match layout %d" % layout)
+        with torch.no_grad():
+            for p, off in zip(params, offs):
+                view = flat[off:off + p.numel()].view(p.shape)
+                view.copy_(p.detach().to(torch.float32))
+                p.data = view
+        return cls(layout, flat)
+
+    def owns(self, params):
+        base = self.flat.data_ptr()
+        return all(p.data_ptr() == base + 4 * off for p, off in zip(params, self.offsets))
+
+    def pack(self):
+        call("nerf_mlp_pack_weights", ptr(self.flat), self.layout, ptr(self.packed), stream_ptr())
+
+    def refresh_packed(self, params=None):
+        if not self.frozen:
+            self.pack()
+
+    def split(self, flat_like):
+        """Views of a flat vector shaped like the 26 parameters."""
+        out = []
+        for i, off in enumerate(self.offsets):
+            nxt = self.offsets[i + 1] if i + 1 < 26 else self.n_params
+            out.append(flat_like[off:nxt])
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# K1-K3, K5 wrappers
+# ------------------------------------------------------------------------------------------
+def encode(x, L):
+    """NeRFModel.py:142-156 via nerf_encode."""
+    _need_cuda(x)
+    lead = x.shape[:-1]
+    xf = _f32c(x.reshape(-1, 3))
+    out = torch.empty((xf.shape[0], 3 * (2 * L + 1)), dtype=torch.float32, device=x.device)
+    call("nerf_encode", ptr(xf), xf.shape[0], int(L), ptr(out), stream_ptr())
+    return out.reshape(*lead, 3 * (2 * L + 1))
+
+
+def _intrinsics(camera_info):
+    K = camera_info["camera_matrix"]
+    return float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
+
+
+def poses_to_device(poses, device):
+    """[n,4,4] (or [4,4]) camera-to-world matrices -> fp64 device tensor (the dtype K1 computes in)."""
+    t = torch.as_tensor(poses, dtype=torch.float64)
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    return t.contiguous().to(device)
+
+
+def raygen_image(poses_dev, pose_index, camera_info, ray_begin=0, ray_count=None):
+    """All (or a contiguous slice of) the rays of one image, ray id = y*W + x (train.py:735-742)."""
+    _need_cuda(poses_dev)
+    W, H = int(camera_info["width"]), int(camera_info["height"])
+    if ray_count is None:
+        ray_count = W * H - ray_begin
+    fx, fy, cx, cy = _intrinsics(camera_info)
+    o = torch.empty((ray_count, 3), dtype=torch.float32, device=poses_dev.device)
+    d = torch.empty_like(o)
+    call("nerf_raygen_image", ptr(poses_dev), int(pose_index), fx, fy, cx, cy, W, H, int(ray_begin), int(ray_count),
+         ptr(o), ptr(d), stream_ptr())
+    return o, d
+
+
+def raygen_batch(poses_dev, camera_info, img_idx, px, py, images_dev=None):
+    """Rays (and target colours) for pre-drawn (image, x, y) triples (train.py:119-127)."""
+    _need_cuda(poses_dev, img_idx)
+    W, H = int(camera_info["width"]), int(camera_info["height"])
+    fx, fy, cx, cy = _intrinsics(camera_info)
+    n = img_idx.numel()
+    o = torch.empty((n, 3), dtype=torch.float32, device=poses_dev.device)
+    d = torch.empty_like(o)
+    tgt = torch.empty_like(o) if images_dev is not None else None
+    call("nerf_raygen_batch", ptr(poses_dev), int(poses_dev.shape[0]), fx, fy, cx, cy, W, H, ptr(img_idx), ptr(px), ptr(py),
+         ptr(images_dev), n, ptr(o), ptr(d), ptr(tgt), stream_ptr())
+    return o, d, tgt
+
+
+def draw_pixels(seed, offset, n_images, W, H, n_rays, device):
+    idx = torch.empty((3, n_rays), dtype=torch.int32, device=device)
+    call("nerf_draw_pixels", int(seed), int(offset), int(n_images), int(W), int(H), int(n_rays),
+         ptr(idx[0]), ptr(idx[1]), ptr(idx[2]), stream_ptr())
+    return idx[0], idx[1], idx[2]
+
+
+def sample_z(n_rays, n_sample, near, far, device, perturb=False, t_rand=None, seed=0, offset=0):
+    """train.py:205-217."""
+    z = torch.empty((n_rays, n_sample), dtype=torch.float32, device=device)
+    if t_rand is not None:
+        t_rand = _f32c(t_rand)
+        _need_cuda(t_rand)
+    call("nerf_sample_z", int(n_rays), int(n_sample), float(near), float(far), 1 if perturb else 0, ptr(t_rand),
+         int(seed), int(offset), ptr(z), stream_ptr())
+    return z
+
+
+def composite_forward(sigma_rgb, z, extras=True):
+    n_rays, S = z.shape
+    rgb = torch.empty((n_rays, 3), dtype=torch.float32, device=z.device)
+    depth = torch.empty((n_rays,), dtype=torch.float32, device=z.device) if extras else None
+    acc = torch.empty((n_rays,), dtype=torch.float32, device=z.device) if extras else None
+    call("nerf_composite_forward", ptr(sigma_rgb), ptr(z), n_rays, S, ptr(rgb), ptr(depth), ptr(acc), stream_ptr())
+    return rgb, depth, acc
+
+
+def composite_backward(sigma_rgb, z, g_rgb):
+    n_rays, S = z.shape
+    d = torch.empty((n_rays, S, 4), dtype=torch.float32, device=z.device)
+    call("nerf_composite_backward", ptr(sigma_rgb), ptr(z), ptr(_f32c(g_rgb)), n_rays, S, ptr(d), stream_ptr())
+    return d
+
+
+# ------------------------------------------------------------------------------------------
+# K4 wrappers
+# ------------------------------------------------------------------------------------------
+def alloc_stash(st, n_rows):
+    lib = _lib.load()
+    return torch.empty(int(lib.nerf_mlp_stash_bytes(st.layout, int(n_rows))), dtype=torch.uint8, device=st.device)
+
+
+def alloc_dstash(st, n_rows):
+    lib = _lib.load()
+    return torch.empty(int(lib.nerf_mlp_dstash_bytes(st.layout, int(n_rows))), dtype=torch.uint8, device=st.device)
+
+
+def mlp_forward(st, pos, dirs, stash=None):
+    n = pos.shape[0]
+    out = torch.empty((n, 4), dtype=torch.float32, device=pos.device)
+    call("nerf_mlp_forward", ptr(st.packed), st.layout, ptr(pos), ptr(dirs), n, ptr(out), ptr(stash), stream_ptr())
+    return out
+
+
+def mlp_forward_rays(st, rays_o, rays_d, z, stash=None):
+    n_rays, S = z.shape
+    out = torch.empty((n_rays, S, 4), dtype=torch.float32, device=z.device)
+    call("nerf_mlp_forward_rays", ptr(st.packed), st.layout, ptr(rays_o), ptr(rays_d), ptr(z), n_rays, S, ptr(out),
+         ptr(stash), stream_ptr())
+    return out
+
+
+def mlp_backward(st, stash, sigma_rgb, d_sigma_rgb, grads, dstash=None, accumulate=False):
+    n_rows = sigma_rgb.numel() // 4
+    if dstash is None:
+        dstash = alloc_dstash(st, n_rows)
+    call("nerf_mlp_backward", ptr(st.packed), st.layout, ptr(stash), ptr(sigma_rgb), ptr(d_sigma_rgb), n_rows, ptr(dstash),
+         ptr(grads), 1 if accumulate else 0, stream_ptr())
+    return grads
+
+
+class MLPFunction(torch.autograd.Function):
+    """NeRFmodel.forward: (pos [n,3], dir [n,3]) -> sigma_rgb [n,4]; gradients reach the parameters."""
+
+    @staticmethod
+    def forward(ctx, st, pos, dirs, *params):
+        _need_cuda(pos, dirs)
+        need = any(ctx.needs_input_grad[3:])
+        stash = alloc_stash(st, pos.shape[0]) if need else None
+        out = mlp_forward(st, pos, dirs, stash)
+        ctx.st, ctx.stash = st, stash
+        ctx.shapes = [p.shape for p in params]
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        st = ctx.st
+        grads = torch.empty(st.n_params, dtype=torch.float32, device=out.device)
+        mlp_backward(st, ctx.stash, out, _f32c(g), grads)
+        ctx.stash = None
+        return (None, None, None) + tuple(v.view(s) for v, s in zip(st.split(grads), ctx.shapes))
+
+
+class RenderFunction(torch.autograd.Function):
+    """render (train.py:187-271) for given rays and depths: -> (rgb [N,3], depth [N], acc [N])."""
+
+    @staticmethod
+    def forward(ctx, st, rays_o, rays_d, z, *params):
+        _need_cuda(rays_o, rays_d, z)
+        need = any(ctx.needs_input_grad[4:])
+        n_rays, S = z.shape
+        stash = alloc_stash(st, n_rays * S) if need else None
+        sigma_rgb = mlp_forward_rays(st, rays_o, rays_d, z, stash)
+        rgb, depth, acc = composite_forward(sigma_rgb, z, extras=True)
+        ctx.st, ctx.stash = st, stash
+        ctx.shapes = [p.shape for p in params]
+        if need:
+            ctx.save_for_backward(sigma_rgb, z)
+        ctx.mark_non_differentiable(depth, acc)
+        return rgb, depth, acc
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_acc):
+        sigma_rgb, z = ctx.saved_tensors
+        st = ctx.st
+        d = composite_backward(sigma_rgb, z, g_rgb)
+        grads = torch.empty(st.n_params, dtype=torch.float32, device=z.device)
+        mlp_backward(st, ctx.stash, sigma_rgb, d, grads)
+        ctx.stash = None
+        return (None, None, None, None) + tuple(v.view(s) for v, s in zip(st.split(grads), ctx.shapes))
+
+
+# ------------------------------------------------------------------------------------------
+# Fused train step (train.py:447-465) over the flat buffers: one call = one optimisation step.
+# ------------------------------------------------------------------------------------------
+class Trainer:
+    """generateBatch -> render -> MSE -> backward -> [allreduce] -> Adam -> repack, all on device.
+
+    ``images_dev`` [n,H,W,3] fp32 and ``poses_dev`` [n,4,4] fp64 stay resident in HBM; rays are drawn
+    on the GPU (counter-based RNG: (seed, step, rank) fully determine the batch), so a step moves no
+    bytes across PCIe unless the caller asks for the loss.  With ``world > 1`` each rank renders
+    ``n_rays`` of the global batch and the flat fp32 gradient is sum-allreduced over NCCL before
+    Adam (scaled by 1/world) -- weights stay bit-identical on every rank.
+    """
+
+    def __init__(self, model, images_dev, poses_dev, camera_info, n_rays, n_sample, near=2.0, far=6.0, lr=5e-4,
+                 betas=(0.9, 0.999), eps=1e-8, lr_decay_steps=50000, lr_decay=0.1, perturb=True, seed=0, rank=0, world=1,
+                 process_group=None):
+        self.model = model
+        self.st = model.kernel_state()
+        self.st.frozen = True                      # this class repacks right after each Adam step
+        self.images, self.poses, self.cam = images_dev, poses_dev, camera_info
+        self.n_rays, self.n_sample, self.near, self.far = int(n_rays), int(n_sample), float(near), float(far)
+        self.lr0, self.betas, self.eps = float(lr), betas, float(eps)
+        self.lr_decay_steps, self.lr_decay = int(lr_decay_steps), float(lr_decay)
+        self.perturb, self.seed, self.rank, self.world, self.pg = bool(perturb), int(seed), int(rank), int(world), process_group
+        dev = self.st.device
+        n = self.st.n_params
+        self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        rows = self.n_rays * self.n_sample
+        self.stash = alloc_stash(self.st, rows)
+        self.dstash = alloc_dstash(self.st, rows)
+        self.g_rgb = torch.empty((self.n_rays, 3), dtype=torch.float32, device=dev)
+        self.iteration = 0
+        self.launches_per_step = 0
+
+    def lr(self):
+        return self.lr0 * self.lr_decay ** (self.iteration // self.lr_decay_steps)
+
+    def close(self):
+        self.st.frozen = False
+
+    def step(self, rays=None):
+        """One optimisation step.  ``rays`` = optional (rays_o, rays_d, target) device tensors (e.g. a
+        batch uploaded from the host like train.py:448); default draws the batch on the GPU."""
+        st, S = self.st, self.n_sample
+        W, H = int(self.cam["width"]), int(self.cam["height"])
+        dev = st.device
+        launches = 0
+        ctr = (self.iteration * self.world + self.rank)
+        if rays is None:
+            k, x, y = draw_pixels(self.seed, ctr * self.n_rays, self.images.shape[0], W, H, self.n_rays, dev)
+            o, d, tgt = raygen_batch(self.poses, self.cam, k, x, y, self.images)
+            launches += 2
+        else:
+            o, d, tgt = rays
+        n_rays = o.shape[0]
+        z = sample_z(n_rays, S, self.near, self.far, dev, perturb=self.perturb, seed=self.seed ^ 0x5bd1e995,
+                     offset=ctr * ((n_rays * S + 3) // 4))
+        sigma_rgb = mlp_forward_rays(st, o, d, z, self.stash)
+        rgb, _, _ = composite_forward(sigma_rgb, z, extras=False)
+        # local mean over this rank's rays; the allreduce sum is scaled by 1/world inside Adam
+        call("nerf_mse_loss", ptr(rgb), ptr(tgt), n_rays, 1.0, ptr(self.loss), ptr(self.g_rgb), stream_ptr())
+        dsr = composite_backward(sigma_rgb, z, self.g_rgb[:n_rays])
+        mlp_backward(st, self.stash, sigma_rgb, dsr, self.grads, self.dstash)
+        launches += 9                               # sample, mlp fwd, comp fwd, mse, comp bwd, memset, dgrad, wgrad, heads
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.pg)
+        lr = self.lr()
+        self.iteration += 1
+        call("nerf_adam_step", ptr(st.flat), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), st.n_params,
+             lr, self.betas[0], self.betas[1], self.eps, self.iteration, 1.0 / self.world, stream_ptr())
+        st.pack()
+        launches += 4
+        self.launches_per_step = launches
+        return self.loss

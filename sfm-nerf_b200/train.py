@@ -1,0 +1,313 @@
+"""Drop-in for the reference ``Phase2/train.py`` call surface: ``PixelToRay``, ``generateBatch``,
+``render``, ``loss``, ``test_image``, ``train``, ``test``, ``main``, ``configParser`` keep their names,
+argument meaning and return types; the arithmetic runs in libnerf_b200.so (sm_100a kernels).
+
+Differences a caller can observe (all deliberate, listed in INTEGRATION.md):
+  * a CUDA sm_100 device is required -- there is no CPU path;
+  * ``PixelToRay`` returns the fp32-rounded value of the reference's fp64 computation;
+  * ``args.chunk_size`` is accepted and ignored (the fused kernel tiles 128 samples at a time and
+    never materialises per-sample activations, so there is nothing to chunk);
+  * jitter (``args.perturb``) comes from a counter-based device RNG seeded from torch's seed;
+  * ``render_full`` additionally returns depth and accumulated alpha (the reference returns RGB only).
+"""
+from __future__ import annotations
+
+import argparse
+import glob
+import json
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import engine
+from .NeRFModel import NeRFmodel
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+_jitter_counter = [0]
+_image_cache = {}
+
+
+# ------------------------------------------------------------------------------------------
+# data
+# ------------------------------------------------------------------------------------------
+def loadDataset(data_path, mode):
+    """Blender-format loader with the reference's return contract (train.py:19-65):
+    (images [n,H,W,3] float64 in [0,1], poses [n,4,4], camera_info{width,height,camera_matrix})."""
+    import cv2  # host IO only
+    with open(os.path.join(data_path, f"transforms_{mode}.json")) as f:
+        meta = json.load(f)
+    images, poses = [], []
+    for frame in meta["frames"]:
+        img = cv2.imread(os.path.join(data_path, frame["file_path"] + ".png"), cv2.IMREAD_UNCHANGED)
+        img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB) / 255.0
+        images.append(img[..., :3])
+        poses.append(frame["transform_matrix"])
+    h, w = images[-1].shape[:2]
+    a = meta["camera_angle_x"]
+    focal = 0.5 * a * w / np.tan(0.5 * a)          # the reference's focal convention (train.py:53)
+    K = np.array([[focal, 0, w / 2], [0, focal, h / 2], [0, 0, 1]])
+    return np.array(images), np.array(poses), {"width": w, "height": h, "camera_matrix": K}
+
+
+def _images_on_device(images, dev):
+    """Upload the image stack once per array object (fp32, [n,H,W,3])."""
+    key = (id(images), str(dev))
+    hit = _image_cache.get(key)
+    if hit is None or hit[0] is not images:
+        _image_cache.clear()
+        t = images if torch.is_tensor(images) else torch.as_tensor(np.asarray(images))
+        hit = (images, t.to(device=dev, dtype=torch.float32).contiguous())
+        _image_cache[key] = hit
+    return hit[1]
+
+
+# ------------------------------------------------------------------------------------------
+# rays
+# ------------------------------------------------------------------------------------------
+def PixelToRay(camera_info, pose, pixelPosition, args=None):
+    """Ray through one pixel (train.py:68-102): origin = pose[:3,3], direction = normalised
+    R @ [(px-cx)/fx, (py-cy)/fy, 1]; computed in fp64 by the K1 kernel and rounded once to fp32."""
+    dev = device
+    poses_dev = engine.poses_to_device(np.asarray(pose, dtype=np.float64), dev)
+    one = lambda v: torch.tensor([int(v)], dtype=torch.int32, device=dev)
+    o, d, _ = engine.raygen_batch(poses_dev, camera_info, one(0), one(pixelPosition[0]), one(pixelPosition[1]))
+    return o[0].cpu().numpy(), d[0].cpu().numpy()
+
+
+def generateBatch(images, poses, camera_info, args):
+    """float32 [n_rays_batch, 9] = origin | direction | rgb for random (image, pixel) draws
+    (train.py:104-127).  The draws use Python's ``random`` in the reference's order, so seeding
+    ``random`` reproduces the reference's batches; ray generation and the colour gather run on the GPU."""
+    dev = device
+    W, H = int(camera_info["width"]), int(camera_info["height"])
+    n = int(args.n_rays_batch)
+    idx = np.empty((3, n), dtype=np.int32)
+    for i in range(n):
+        idx[0, i] = random.randint(0, len(images) - 1)
+        idx[1, i] = random.randint(0, W - 1)
+        idx[2, i] = random.randint(0, H - 1)
+    idx_dev = torch.from_numpy(idx).to(dev)
+    poses_dev = engine.poses_to_device(np.asarray(poses, dtype=np.float64), dev)
+    o, d, tgt = engine.raygen_batch(poses_dev, camera_info, idx_dev[0], idx_dev[1], idx_dev[2], _images_on_device(images, dev))
+    return torch.cat([o, d, tgt], dim=1).cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------
+# render
+# ------------------------------------------------------------------------------------------
+def render_full(model, rays_origin, rays_direction, args, near=2.0, far=6.0, t_rand=None):
+    """(rgb [N,3], depth [N], acc [N]) -- train.py:187-271 plus depth = sum w*z and acc = sum w."""
+    st = model.kernel_state()
+    o = rays_origin.to(torch.float32).contiguous()
+    d = rays_direction.to(torch.float32).contiguous()
+    n_rays, S = o.shape[0], int(args.n_sample)
+    perturb = bool(getattr(args, "perturb", False))
+    off = _jitter_counter[0]
+    if perturb and t_rand is None:
+        _jitter_counter[0] += (n_rays * S + 3) // 4
+    z = engine.sample_z(n_rays, S, near, far, o.device, perturb=perturb or t_rand is not None, t_rand=t_rand,
+                        seed=torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, offset=off)
+    return engine.RenderFunction.apply(st, o, d, z, *model.ordered_parameters())
+
+
+def render(model, rays_origin, rays_direction, args, near=2.0, far=6.0):
+    """RGB [N,3] of the rays (train.py:187-271); reads args.n_sample / args.perturb."""
+    return render_full(model, rays_origin, rays_direction, args, near, far)[0]
+
+
+def loss(groundtruth, prediction):
+    """Mean squared error over all elements (train.py:274-275)."""
+    return torch.nn.functional.mse_loss(groundtruth, prediction)
+
+
+def test_image(model, image, pose, camera_info, args):
+    """Render one full view and compare with ground truth (train.py:714-763):
+    returns (prediction [H,W,3] tensor on the model's device, mse float)."""
+    dev = next(model.parameters()).device
+    W, H = int(camera_info["width"]), int(camera_info["height"])
+    poses_dev = engine.poses_to_device(np.asarray(pose, dtype=np.float64), dev)
+    prediction = torch.zeros((H * W, 3), device=dev)
+    step = int(args.n_rays_batch)
+    st = model.kernel_state()
+    with torch.no_grad():
+        st.frozen = True                     # weights do not change inside this loop: pack once
+        try:
+            for i in range(0, H * W, step):
+                o, d = engine.raygen_image(poses_dev, 0, camera_info, i, min(step, H * W - i))
+                prediction[i:i + step] = render(model, o, d, args, near=args.near, far=args.far)
+        finally:
+            st.frozen = False
+    gt = torch.as_tensor(np.asarray(image).reshape(-1, 3)).to(dev)
+    mse = torch.mean((gt - prediction.to(gt.dtype)) ** 2)
+    return prediction.reshape(H, W, 3), mse.item()
+
+
+# ------------------------------------------------------------------------------------------
+# checkpoints in the reference's format (train.py:510-528)
+# ------------------------------------------------------------------------------------------
+def _adam_state_dict(trainer, model):
+    """torch.optim.Adam-compatible state_dict from the trainer's flat moment buffers."""
+    params = model.ordered_parameters()
+    st = trainer.st
+    m, v = st.split(trainer.exp_avg), st.split(trainer.exp_avg_sq)
+    state = {i: {"step": torch.tensor(float(trainer.iteration)), "exp_avg": m[i].view(p.shape).clone(),
+                 "exp_avg_sq": v[i].view(p.shape).clone()} for i, p in enumerate(params)}
+    group = {"lr": trainer.lr(), "betas": trainer.betas, "eps": trainer.eps, "weight_decay": 0, "amsgrad": False,
+             "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+             "initial_lr": trainer.lr0, "params": list(range(len(params)))}
+    return {"state": state, "param_groups": [group]}
+
+
+def _load_adam_state(trainer, sd):
+    st = trainer.st
+    m, v = st.split(trainer.exp_avg), st.split(trainer.exp_avg_sq)
+    for i, s in sd.get("state", {}).items():
+        m[int(i)].copy_(s["exp_avg"].reshape(-1))
+        v[int(i)].copy_(s["exp_avg_sq"].reshape(-1))
+
+
+def save_checkpoint(path, model, trainer, iteration, loss_value):
+    torch.save({"iteration": iteration, "model_state_dict": model.state_dict(),
+                "optimizer_state_dict": _adam_state_dict(trainer, model), "loss": loss_value}, path)
+
+
+def _psnr(mse):
+    return -10.0 * np.log10(max(mse, 1e-12))
+
+
+# ------------------------------------------------------------------------------------------
+# train / test drivers
+# ------------------------------------------------------------------------------------------
+def train(images, poses, camera_info, args):
+    """Train the NeRF model (train.py:380-533).  The per-iteration body (generateBatch, render,
+    MSE, backward, Adam, StepLR; train.py:447-465) is one ``engine.Trainer.step`` on the GPU."""
+    dev = device
+    model = NeRFmodel(embed_pos_L=int(args.n_pos_freq), embed_direction_L=int(args.n_dirc_freq),
+                      num_channels=int(args.hidden_size), pos_encoding=True).to(dev)
+    start_iter = 0
+    ckpt = None
+    if getattr(args, "load_checkpoint", False):
+        os.makedirs(args.checkpoint_path, exist_ok=True)
+        found = sorted(glob.glob(os.path.join(args.checkpoint_path, "model_*.pth")))
+        if found:
+            print(f"Loading checkpoint from {found[-1]}")
+            ckpt = torch.load(found[-1], map_location=dev, weights_only=False)
+            model.load_state_dict(ckpt["model_state_dict"])
+            start_iter = ckpt["iteration"] + 1
+        else:
+            print("No checkpoint found, starting from scratch")
+    images_dev = _images_on_device(images, dev)
+    poses_dev = engine.poses_to_device(np.asarray(poses, dtype=np.float64), dev)
+    trainer = engine.Trainer(model, images_dev, poses_dev, camera_info, int(args.n_rays_batch), int(args.n_sample),
+                             near=float(args.near), far=float(args.far), lr=float(args.lrate),
+                             lr_decay_steps=int(args.lrate_decay_steps), lr_decay=float(args.lrate_decay),
+                             perturb=bool(args.perturb), seed=int(getattr(args, "seed", 0)))
+    trainer.iteration = start_iter
+    if ckpt is not None and "optimizer_state_dict" in ckpt:
+        _load_adam_state(trainer, ckpt["optimizer_state_dict"])
+    writer = None
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+        log_dir = os.path.join(args.logs_path, f"{args.exp_name}")
+        os.makedirs(log_dir, exist_ok=True)
+        writer = SummaryWriter(log_dir)
+    except Exception:  # tensorboard is optional host tooling
+        writer = None
+    val_indices = np.random.choice(len(images), size=min(5, len(images)), replace=False)
+    log_every = int(getattr(args, "log_every", 100))
+    val_every = int(getattr(args, "val_every", 1000))
+    running, last = 0.0, float("nan")
+    loss_acc = torch.zeros(1, device=dev)
+    for iteration in range(start_iter, int(args.max_iters)):
+        loss_acc += trainer.step()                  # no host sync inside the loop body
+        if iteration % log_every == 0 and iteration > start_iter:
+            running = loss_acc.item() / log_every   # one D2H read per log_every steps
+            loss_acc.zero_()
+            last = running
+            if writer:
+                writer.add_scalar("Loss/train_avg", running, iteration)
+                writer.add_scalar("Learning Rate", trainer.lr(), iteration)
+            print(f"iter {iteration}: loss {running:.6f} psnr {_psnr(running):.2f} lr {trainer.lr():.2e}")
+        if iteration % val_every == 0 and iteration > 0:
+            trainer.st.frozen = False
+            for i, vi in enumerate(val_indices):
+                _, val_loss = test_image(model, images[vi], poses[vi], camera_info, args)
+                if writer:
+                    writer.add_scalar(f"Loss/val_{i}", val_loss, iteration)
+            trainer.st.frozen = True
+            if iteration % int(args.save_ckpt_iter) == 0:
+                os.makedirs(args.checkpoint_path, exist_ok=True)
+                save_checkpoint(os.path.join(args.checkpoint_path, f"model_{iteration:06d}.pth"), model, trainer, iteration, last)
+    os.makedirs(args.checkpoint_path, exist_ok=True)
+    save_checkpoint(os.path.join(args.checkpoint_path, "final_model.pth"), model, trainer, int(args.max_iters) - 1, last)
+    trainer.close()
+    if writer:
+        writer.close()
+    return model
+
+
+def test(images, poses, camera_info, args):
+    """Evaluate on up to 5 random views (train.py:586-680); PNGs are written with cv2 when present."""
+    dev = device
+    model = NeRFmodel(embed_pos_L=int(args.n_pos_freq), embed_direction_L=int(args.n_dirc_freq),
+                      num_channels=int(args.hidden_size), pos_encoding=True).to(dev)
+    final = os.path.join(args.checkpoint_path, "final_model.pth")
+    found = [final] if os.path.exists(final) else sorted(glob.glob(os.path.join(args.checkpoint_path, "model_*.pth")))[-1:]
+    if not found:
+        raise FileNotFoundError(f"no checkpoint under {args.checkpoint_path}")
+    ckpt = torch.load(found[0], map_location=dev, weights_only=False)
+    model.load_state_dict(ckpt["model_state_dict"] if "model_state_dict" in ckpt else ckpt)
+    model.eval()
+    picks = np.random.choice(len(images), size=min(5, len(images)), replace=False)
+    os.makedirs(args.images_path, exist_ok=True)
+    results = []
+    for n, vi in enumerate(picks):
+        pred, mse = test_image(model, images[vi], poses[vi], camera_info, args)
+        results.append((int(vi), mse, _psnr(mse)))
+        print(f"view {vi}: mse {mse:.6f} psnr {_psnr(mse):.2f} dB")
+        try:
+            import cv2
+            both = np.concatenate([np.asarray(images[vi], dtype=np.float32), pred.cpu().numpy()], axis=1)
+            cv2.imwrite(os.path.join(args.images_path, f"test_{n}.png"), (np.clip(both[..., ::-1], 0, 1) * 255).astype(np.uint8))
+        except ImportError:
+            pass
+    return results
+
+
+def main(args):
+    print("Loading data...")
+    images, poses, camera_info = loadDataset(args.data_path, args.mode)
+    for name, cast in (("n_rays_batch", int), ("n_sample", int), ("max_iters", int), ("n_pos_freq", int), ("n_dirc_freq", int),
+                       ("perturb", bool), ("hidden_size", int), ("chunk_size", int), ("lrate", float), ("save_ckpt_iter", int)):
+        setattr(args, name, cast(getattr(args, name)))
+    args.checkpoint_path = os.path.join(args.checkpoint_path, args.data_path.split("/")[-2])
+    if args.mode == "train":
+        print("Start training")
+        train(images, poses, camera_info, args)
+    elif args.mode == "test":
+        print("Start testing")
+        args.load_checkpoint = True
+        test(images, poses, camera_info, args)
+
+
+def configParser():
+    """Flag names and defaults of the reference CLI (train.py:792-816)."""
+    p = argparse.ArgumentParser()
+    for flag, default, extra in (
+            ("--data_path", "./Phase2/nerf_synthetic/lego/", {}), ("--mode", "train", {}), ("--lrate", 5e-4, {}),
+            ("--n_pos_freq", 10, {}), ("--n_dirc_freq", 4, {}), ("--n_rays_batch", 32 * 32 * 8, {}), ("--n_sample", 256, {}),
+            ("--max_iters", 200001, {}), ("--logs_path", "./logs/", {}), ("--log_id", "", {}),
+            ("--exp_name", "lego_experiment", {}), ("--checkpoint_path", "./Phase2/checkpoints_new_2/", {}),
+            ("--load_checkpoint", True, {}), ("--save_ckpt_iter", 1000, {}), ("--images_path", "./image/", {}),
+            ("--perturb", True, {"type": bool}), ("--near", 2.0, {"type": float}), ("--far", 6.0, {"type": float}),
+            ("--chunk_size", 1024 * 32, {"type": int}), ("--hidden_size", 256, {"type": int}),
+            ("--lrate_decay", 0.1, {"type": float}), ("--lrate_decay_steps", 50000, {"type": int})):
+        p.add_argument(flag, default=default, **extra)
+    return p
+
+
+if __name__ == "__main__":
+    main(configParser().parse_args())

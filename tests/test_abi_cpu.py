@@ -1,0 +1,96 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol include/nerf_b200.h
+declares (no compute calls -- there is no GPU here), the parameter layout matches the reference
+class, and the drop-in Python surface has the reference's names and defaults."""
+import ctypes
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libmod():
+    mod = importlib.import_module("sfm-nerf_b200._lib")
+    mod.build()
+    return mod
+
+
+def test_header_symbols_are_exported(libmod):
+    header = open(os.path.join(ROOT, "include", "nerf_b200.h")).read()
+    declared = set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(libmod.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in nerf_b200.h but not exported"
+    assert declared == set(libmod.PROTOTYPES), declared ^ set(libmod.PROTOTYPES)
+
+
+def test_abi_queries_without_gpu(libmod):
+    lib = libmod.load()
+    assert lib.nerf_abi_version() == 1
+    assert lib.nerf_param_count(0) == 661636 and lib.nerf_param_count(1) == 627844
+    assert lib.nerf_param_count(2) == -4
+    assert b"sm_100" in lib.nerf_error_string(-3)
+    # tile rounding of the stash queries
+    assert lib.nerf_mlp_stash_bytes(0, 1) == lib.nerf_mlp_stash_bytes(0, 128)
+    assert lib.nerf_mlp_stash_bytes(0, 129) == 2 * lib.nerf_mlp_stash_bytes(0, 128)
+    assert lib.nerf_mlp_stash_bytes(0, 0) == 0
+    assert lib.nerf_mlp_packed_bytes(0) % 16 == 0
+
+
+def test_param_offsets_follow_state_dict_order(libmod):
+    import sfmnerf_b200 as s
+    lib = libmod.load()
+    for layout, kw in ((0, {}), (1, {"pos_encoding": False})):
+        m = s.NeRFmodel(**kw)
+        off = 0
+        for i, p in enumerate(m.ordered_parameters()):
+            assert lib.nerf_param_offset(layout, i) == off
+            off += p.numel()
+        assert off == lib.nerf_param_count(layout)
+        assert [id(p) for p in m.ordered_parameters()] == [id(p) for p in m.state_dict(keep_vars=True).values()]
+
+
+def test_no_gpu_means_loud_failure(libmod):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = libmod.load()
+    assert lib.nerf_device_check() != 0                 # cudaError / NERF_ERR_ARCH, never a silent fallback
+    import sfmnerf_b200 as s
+    with pytest.raises(s._lib.NerfB200Error):
+        s.NeRFmodel()(torch.zeros(2, 3), torch.zeros(2, 3))
+    with pytest.raises(s._lib.NerfB200Error):
+        s.engine.encode(torch.zeros(2, 3), 4)
+
+
+def test_cli_flags_match_reference_defaults():
+    import sfmnerf_b200 as s
+    a = s.configParser().parse_args([])
+    assert (a.lrate, a.n_pos_freq, a.n_dirc_freq, a.n_rays_batch, a.n_sample, a.max_iters) == (5e-4, 10, 4, 8192, 256, 200001)
+    assert (a.near, a.far, a.chunk_size, a.hidden_size, a.lrate_decay, a.lrate_decay_steps) == (2.0, 6.0, 32768, 256, 0.1, 50000)
+    assert a.perturb is True and a.mode == "train" and a.save_ckpt_iter == 1000
+    for name in ("PixelToRay", "generateBatch", "render", "loss", "test_image", "train", "test", "main", "configParser", "NeRFmodel"):
+        assert hasattr(s, name)
+
+
+def test_product_does_not_import_oracle():
+    pkg_dir = os.path.join(ROOT, "sfm-nerf_b200")
+    for fn in os.listdir(pkg_dir):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg_dir, fn)).read()
+            assert "oracle" not in src.replace("oracle/", ""), fn
+
+
+def test_synthetic_scene_and_poses():
+    import sfmnerf_b200 as s
+    from oracle import nerf_oracle as orc
+    np.testing.assert_allclose(s.synthetic.look_at_pose(30, -30), orc.look_at_pose(30, -30), atol=1e-12)
+    cam = s.synthetic.make_camera_info(100, 100)
+    assert abs(cam["camera_matrix"][0][0] - 95.987661) < 1e-5
+    imgs = s.synthetic.render_lego_images(s.synthetic.sphere_poses(1), s.synthetic.make_camera_info(24, 24), n_sample=96)
+    assert imgs.shape == (1, 24, 24, 3) and 0.01 < float(imgs.mean()) < 0.5
