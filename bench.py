@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: NeRF train-step (and render) rays/s at 64 samples/ray.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+Workload (BASELINE.json configs[1]): lego-shaped synthetic scene, 400x400 views, train step of
+4096 rays x 64 stratified samples (jittered), live PE model (661,636 params), Adam.  A "step" is
+generateBatch + render + MSE + backward + Adam + weight repack.  `value` = rays/s of the whole job
+with every input resident in HBM (rays are drawn on the GPU); `e2e` = the same step fed from a pinned
+HOST ray batch (H2D copy inside the timed region) with the loss read back to the host every step,
+i.e. the reference's train.py:447-468 loop body.  N > 1: data-parallel, 4096 rays per rank (weak
+scaling) + NCCL allreduce of the flat fp32 gradient.  Timing: CUDA events on the launch stream,
+barrier + synchronize on both sides, max over ranks.  The per-step working set (activation stash +
+gradient stash, ~2.8 GB) is far larger than the 126 MB L2, so no explicit L2 flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAYS, N_SAMPLE, IMG = 4096, 64, 400
+FLOP_FWD = 2 * 658944            # per sample, unpadded, biases/activations excluded
+FLOP_DGRAD = 2 * 623232
+FLOP_WGRAD = 2 * 658944
+BYTES_COMPOSITE_FWD = 20         # sigma 4 + rgb 12 + z 4 per sample (jittered)
+BYTES_COMPOSITE_BWD = 36
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=100)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--rays", type=int, default=N_RAYS)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"tflops": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "tflops_burst": float(d["bf16_tflops"]),
+                "hbm": float(d["hbm_gbs"]), "src": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks": 0x2}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port of train.py:447-465) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_train_steps(n_rays, steps, warmup):
+    """Times `steps` train steps (render + MSE + autograd backward + Adam) of the oracle on CPU."""
+    import numpy as np
+    import torch
+    from oracle import nerf_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = orc.init_state_dict(0)
+    opt = orc.Adam(sd)
+    cam = orc.make_camera_info(IMG, IMG)
+    poses = orc.sphere_poses(8, seed=0)
+    rng = np.random.default_rng(0)
+    images = rng.random((8, 16, 16, 3))            # colours only feed the loss; content is irrelevant to timing
+    gen = torch.Generator().manual_seed(0)
+    times = []
+    for it in range(warmup + steps):
+        k = rng.integers(0, 8, n_rays); x = rng.integers(0, IMG, n_rays); y = rng.integers(0, IMG, n_rays)
+        t0 = time.perf_counter()
+        rays = orc.rays_from_indices(images, poses, cam, k, x % 16, y % 16) if False else None
+        # ray generation as the reference does it (per-ray Python, train.py:119-125) is timed too
+        batch = np.empty((n_rays, 9), np.float32)
+        for i in range(n_rays):
+            o, d = orc.pixel_to_ray(cam, poses[k[i]], (int(x[i]), int(y[i])))
+            batch[i, 0:3], batch[i, 3:6], batch[i, 6:9] = o, d, images[k[i]][y[i] % 16, x[i] % 16]
+        o, d, tgt = (torch.tensor(batch[:, j:j + 3]) for j in (0, 3, 6))
+        t_rand = torch.rand(n_rays, N_SAMPLE, generator=gen)
+        loss, grads = orc.loss_and_grads(sd, o, d, tgt, N_SAMPLE, t_rand=t_rand)
+        sd = opt.step(sd, grads)
+        _ = loss.item()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    # calibrate the bounded sample: keep the whole run within ~2.5 minutes
+    cal, threads = cpu_train_steps(256, 1, 1)
+    per_ray = cal[0] / 256
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n_rays = int(min(args.rays, max(256, budget / per_ray)))
+    n_rays -= n_rays % 64
+    times, threads = cpu_train_steps(n_rays, args.steps, args.warmup)
+    total = sum(times)
+    value = n_rays * len(times) / total
+    line = {
+        "metric": "train_step_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"lego-shaped synthetic scene {IMG}x{IMG}, train step {args.rays} rays x {N_SAMPLE} samples, live PE model, Adam",
+                   "samples_per_ray": N_SAMPLE},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port",
+                         "sample": f"{len(times)} train steps of {n_rays} rays x {N_SAMPLE} samples (oracle port of train.py:447-465, "
+                                   f"torch CPU, {threads} threads; per-ray Python ray generation included as in the reference)"},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import sfmnerf_b200 as s
+    E = s.engine
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    s._lib.check(s._lib.load().nerf_device_check(), "nerf_device_check")
+    n_rays = args.rays
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- synthetic scene (data generation, untimed) ---------------------------------------
+    cam = s.synthetic.make_camera_info(IMG, IMG)
+    poses_np = s.synthetic.sphere_poses(20, seed=0)
+    images = s.synthetic.render_lego_images(poses_np, cam, n_sample=128, device=dev).contiguous()
+    poses = E.poses_to_device(poses_np, dev)
+    torch.manual_seed(0)
+    model = s.NeRFmodel().to(dev)
+    trainer = E.Trainer(model, images, poses, cam, n_rays, N_SAMPLE, perturb=True, seed=0, rank=rank, world=world)
+
+    # ---- device-resident train steps ------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        trainer.step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    timers = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        trainer.step(timers=timers)
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = (trainer.launches_per_step - 1) * args.steps      # my kernels only (the memset is the driver's)
+    final_loss = float(trainer.loss.item())
+
+    # ---- end to end through the public API with host buffers --------------------------------
+    host_batches = []
+    rng = np.random.default_rng(1234 + rank)
+    for _ in range(4):
+        k = torch.from_numpy(rng.integers(0, len(poses_np), n_rays).astype(np.int32)).to(dev)
+        x = torch.from_numpy(rng.integers(0, IMG, n_rays).astype(np.int32)).to(dev)
+        y = torch.from_numpy(rng.integers(0, IMG, n_rays).astype(np.int32)).to(dev)
+        o, d, tgt = E.raygen_batch(poses, cam, k, x, y, images)          # a generateBatch() result ...
+        host_batches.append(torch.cat([o, d, tgt], 1).cpu().pin_memory())  # ... living in pinned host memory
+    e2e_steps = args.steps
+    loss_host = 0.0
+    for i in range(3):
+        b = host_batches[i % 4].to(dev, non_blocking=True)
+        loss_host = trainer.step(rays=(b[:, 0:3].contiguous(), b[:, 3:6].contiguous(), b[:, 6:9].contiguous())).item()
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev2.record()
+    for i in range(e2e_steps):
+        b = host_batches[i % 4].to(dev, non_blocking=True)               # H2D: n_rays x 9 fp32
+        loss_t = trainer.step(rays=(b[:, 0:3].contiguous(), b[:, 3:6].contiguous(), b[:, 6:9].contiguous()))
+        loss_host = loss_t.item()                                         # D2H: 4 bytes, syncs (train.py:468)
+    ev3.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(ev2.elapsed_time(ev3), 1e3 * (time.perf_counter() - t_wall0)))
+    clocks = sampler.result()
+
+    # ---- render throughput (inference, no stash) for the same metric family -----------------
+    args_r = argparse.Namespace(n_sample=N_SAMPLE, perturb=True, chunk_size=32768, n_rays_batch=IMG * IMG, near=2.0, far=6.0)
+    per_rank = IMG * IMG // world
+    with torch.no_grad():
+        st = model.kernel_state()
+        for _ in range(2):
+            o, d = E.raygen_image(poses, 0, cam, rank * per_rank, per_rank)
+            s.render(model, o, d, args_r)
+        barrier()
+        ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_frames = 10
+        ev4.record()
+        for f in range(n_frames):
+            o, d = E.raygen_image(poses, f % len(poses_np), cam, rank * per_rank, per_rank)
+            s.render(model, o, d, args_r)
+        ev5.record()
+        barrier()
+    render_ms = max_over_ranks(ev4.elapsed_time(ev5))
+    render_rays_s = per_rank * world * n_frames / render_ms * 1e3
+    trainer.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel averages and roofline -------------------------------------------------
+    peaks = measured_peaks()
+    rows = n_rays * N_SAMPLE
+    work = {"mlp_fwd": rows * FLOP_FWD, "mlp_dgrad": rows * FLOP_DGRAD, "mlp_wgrad": rows * FLOP_WGRAD}
+    kern = {}
+    for name, pairs in timers.items():
+        ms = sum(a.elapsed_time(b) for a, b in pairs) / len(pairs)
+        kern[name] = {"ms": round(ms, 4)}
+        if name in work:
+            kern[name]["tflops"] = round(work[name] / ms / 1e9, 1)
+            kern[name]["frac_of_peak"] = round(work[name] / ms / 1e9 / peaks["tflops"], 4)
+        elif name == "composite_fwd":
+            kern[name]["gbs"] = round(rows * BYTES_COMPOSITE_FWD / ms / 1e6, 1)
+        elif name == "composite_bwd":
+            kern[name]["gbs"] = round(rows * BYTES_COMPOSITE_BWD / ms / 1e6, 1)
+    dom = max(work, key=lambda k: kern[k]["ms"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": kern[dom]["tflops"], "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": kern[dom]["frac_of_peak"], "traffic": traffic, "peak_source": peaks["src"],
+                "flop_per_sample": {"mlp_fwd": FLOP_FWD, "mlp_dgrad": FLOP_DGRAD, "mlp_wgrad": FLOP_WGRAD}[dom],
+                "step_tflops": round(rows * (FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD) * args.steps / ms_total / 1e9, 1)}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        times, threads = cpu_train_steps(n_rays, 3, 1)
+        v = n_rays * len(times) / sum(times)
+        cpu_baseline = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
+                        "sample": f"3 train steps of {n_rays} rays x {N_SAMPLE} samples (oracle port of train.py:447-465 on torch CPU, "
+                                  f"{threads} threads, per-ray Python ray generation included as in the reference)"}
+
+    value = n_rays * world * args.steps / ms_total * 1e3
+    line = {
+        "metric": "train_step_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"lego-shaped synthetic scene {IMG}x{IMG} (20 views), train step {n_rays} rays x {N_SAMPLE} samples per GPU, "
+                               "live PE model 661,636 params, Adam; rays drawn on-GPU",
+                   "samples_per_ray": N_SAMPLE, "parallelism": f"dp{world}" if world > 1 else "single",
+                   "l2": "working set (stash+dstash ~2.8 GB/step) >> 126 MB L2; no explicit flush"},
+        "samples_per_s": value * N_SAMPLE,
+        "render": {"rays_per_s": render_rays_s, "samples_per_s": render_rays_s * N_SAMPLE,
+                   "workload": f"{IMG}x{IMG} frame x {N_SAMPLE} samples, rays sharded over {world} GPU(s), ray-gen included"},
+        "e2e": {"value": n_rays * world * e2e_steps / e2e_ms * 1e3, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 9 * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / e2e_steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kern,
+        "cpu_baseline": cpu_baseline,
+        "final_loss": final_loss, "loss_e2e": loss_host,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

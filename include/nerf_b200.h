@@ -120,6 +120,13 @@ int nerf_mlp_forward_rays(const void* packed, int layout, const float* rays_o,
 int nerf_mlp_backward(const void* packed, int layout, const void* stash, const float* sigma_rgb,
                       const float* d_sigma_rgb, int64_t n_rows, void* dstash, float* grads,
                       int accumulate, void* stream);
+/* the two halves of nerf_mlp_backward, callable (and timeable) on their own:
+ *   dgrad: data-gradient chain through the layers; fills dstash with every layer's dY (bf16);
+ *   wgrad: weight/bias gradients from (stash, dstash) into the flat fp32 gradient vector. */
+int nerf_mlp_dgrad(const void* packed, int layout, const void* stash, const float* sigma_rgb,
+                   const float* d_sigma_rgb, int64_t n_rows, void* dstash, void* stream);
+int nerf_mlp_wgrad(int layout, const void* stash, const void* dstash, int64_t n_rows, float* grads,
+                   int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K5  volume compositing -- train.py:248-269 (+ depth/acc = sum w*z / sum w, which the
@@ -148,6 +155,7 @@ int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
  * Self tests (device): exercise the tcgen05 descriptor encodings used by K4 on a small GEMM.
  * variant selects the operand layout hypothesis; result_host[0..3] receives max-abs-error
  * and diagnostics.  Returns 0 when the variant reproduces the fp32 reference product.
+ * Diagnostics only: synchronises the device and is the one entry point that allocates.
  * ------------------------------------------------------------------------------------- */
 int nerf_selftest_umma(int variant, float* result_host);
 

@@ -159,29 +159,46 @@ def position_encoding(x, L):
 # (a7) MLP -- NeRFModel.py:158-202, functional over a state_dict.
 # ----------------------------------------------------------------------------------------
 
+def _round_st(x, dtype):
+    """Round to ``dtype`` and back with a straight-through gradient (identity when dtype is None)."""
+    if dtype is None:
+        return x
+    return x + (x.to(dtype).float() - x).detach()
+
+
 def model_forward(sd, pos, direction, embed_pos_L=10, embed_direction_L=4, pos_encoding=True,
-                  return_hidden=False):
+                  return_hidden=False, operand_dtype=None):
     """density [...,1] (softplus), rgb [...,3] (sigmoid).  ``return_hidden`` also returns the
-    post-activation tensors in layer order (used by per-layer parity tests)."""
-    lin = lambda name, x: F.linear(x, sd[name + ".weight"], sd[name + ".bias"])
+    post-activation tensors in layer order (used by per-layer parity tests).
+
+    ``operand_dtype=torch.bfloat16`` restates the SAME network with the operand rounding of a
+    bf16-tensor-core evaluation (weights and inputs of the eleven 128/256-wide layers rounded to
+    bf16, fp32 accumulation, fp32 density / rgb heads).  It is NOT reference behaviour; tests use it
+    to separate "kernel is wrong" from "bf16 operands differ from fp32" when comparing gradients,
+    whose element-wise error is dominated by ReLU masks flipping for near-zero pre-activations."""
+    q = lambda x: _round_st(x, operand_dtype)
+    lin = lambda name, x: F.linear(x, q(sd[name + ".weight"]), sd[name + ".bias"])
+    head = lambda name, x: F.linear(x, sd[name + ".weight"], sd[name + ".bias"])
     if pos_encoding:
         pe = position_encoding(pos, embed_pos_L)
         de = position_encoding(direction, embed_direction_L)
     else:
         pe, de = pos, direction
+    pe, de = q(pe), q(de)
     hidden = []
-    h = F.relu(lin("fc1", pe)); hidden.append(h)
+    h = q(F.relu(lin("fc1", pe))); hidden.append(h)
     for i in range(4):
-        h = F.relu(lin(f"fc_layers.{i}", h)); hidden.append(h)
+        h = q(F.relu(lin(f"fc_layers.{i}", h))); hidden.append(h)
         if i == 3:
             h = torch.cat([h, pe], dim=-1)
-            h = F.relu(lin("skip_layer", h)); hidden.append(h)
+            h = q(F.relu(lin("skip_layer", h))); hidden.append(h)
     for i in range(3):
-        h = F.relu(lin(f"fc_layers2.{i}", h)); hidden.append(h)
-    density = F.softplus(lin("density_layer", h))
-    feature = F.relu(lin("feature_layer", h)); hidden.append(feature)
+        h_full = F.relu(lin(f"fc_layers2.{i}", h))
+        h = q(h_full); hidden.append(h)
+    density = F.softplus(head("density_layer", h_full))        # head reads the unrounded activation
+    feature = q(F.relu(lin("feature_layer", h))); hidden.append(feature)
     r = F.relu(lin("rgb_layer1", torch.cat([feature, de], dim=-1))); hidden.append(r)
-    rgb = torch.sigmoid(lin("rgb_layer2", r))
+    rgb = torch.sigmoid(head("rgb_layer2", r))
     if return_hidden:
         return density, rgb, hidden
     return density, rgb

@@ -59,7 +59,7 @@ void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t
   a.n_rows = n_rows;
   a.n_tiles = (int)((n_rows + 127) / 128);
   a.stash_tile_bytes = m.stash_tile_bytes; a.dstash_tile_bytes = m.dstash_tile_bytes;
-  a.st_pe = m.st_pe; a.st_de = m.st_de; a.st_r1 = m.st_r1; a.ds_y10 = m.ds_y[10]; a.ds_sr = m.ds_sr;
+  a.st_pe = m.st_pe; a.st_de = m.st_de; a.st_r1 = m.st_r1; a.st_mask = m.st_mask; a.ds_y10 = m.ds_y[10]; a.ds_sr = m.ds_sr;
 }
 
 int launch_forward(const void* packed, int layout, const float* pos, const float* dir, const float* z,
@@ -69,9 +69,10 @@ int launch_forward(const void* packed, int layout, const float* pos, const float
   if (rc != NERF_OK) return rc;
   const ModelLayout* m = get_layout(layout);
   if (!m) return NERF_ERR_LAYOUT;
-  if (!packed || !pos || !dir || !sigma_rgb || n_rows < 0 || n_rows > (int64_t)128 * 0x7fffff00) return NERF_ERR_ARG;
+  if (!packed || n_rows < 0 || n_rows > (int64_t)128 * 0x7fffff00) return NERF_ERR_ARG;
+  if (n_rows == 0) return NERF_OK;                      /* empty batch: nothing to read or write */
+  if (!pos || !dir || !sigma_rgb) return NERF_ERR_ARG;
   if (!nerf_aligned(packed, 16) || !nerf_aligned(sigma_rgb, 16) || (stash && !nerf_aligned(stash, 16))) return NERF_ERR_ALIGN;
-  if (n_rows == 0) return NERF_OK;
   MlpArgs a;
   fill_mlp_args(a, *m, packed, n_rows);
   a.pos = pos; a.dir = dir; a.z = z; a.n_sample = n_sample;
@@ -249,23 +250,18 @@ int nerf_mlp_forward_rays(const void* packed, int layout, const float* rays_o, c
   return launch_forward(packed, layout, rays_o, rays_d, z, n_rays * n_sample, n_sample, sigma_rgb, stash, stream);
 }
 
-int nerf_mlp_backward(const void* packed, int layout, const void* stash, const float* sigma_rgb,
-                      const float* d_sigma_rgb, int64_t n_rows, void* dstash, float* grads, int accumulate,
-                      void* stream) {
+int nerf_mlp_dgrad(const void* packed, int layout, const void* stash, const float* sigma_rgb,
+                   const float* d_sigma_rgb, int64_t n_rows, void* dstash, void* stream) {
   DeviceInfo* dev;
   int rc = device_info(&dev);
   if (rc != NERF_OK) return rc;
   const ModelLayout* m = get_layout(layout);
   if (!m) return NERF_ERR_LAYOUT;
-  if (!packed || !stash || !sigma_rgb || !d_sigma_rgb || !dstash || !grads || n_rows < 0) return NERF_ERR_ARG;
+  if (!packed || !stash || !sigma_rgb || !d_sigma_rgb || !dstash || n_rows < 0) return NERF_ERR_ARG;
   if (!nerf_aligned(packed, 16) || !nerf_aligned(stash, 16) || !nerf_aligned(dstash, 16) || !nerf_aligned(sigma_rgb, 16) ||
       !nerf_aligned(d_sigma_rgb, 16))
     return NERF_ERR_ALIGN;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (!accumulate) NERF_CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * m->n_params, s));
   if (n_rows == 0) return NERF_OK;
-
-  // 1. data-gradient chain (emits every dY_l to the dstash)
   MlpArgs a;
   fill_mlp_args(a, *m, packed, n_rows);
   a.sigma_rgb = const_cast<float*>(sigma_rgb);
@@ -274,22 +270,38 @@ int nerf_mlp_backward(const void* packed, int layout, const void* stash, const f
   a.dstash = static_cast<uint8_t*>(dstash);
   a.prog = m->bwd;
   const int grid = a.n_tiles < 2 * dev->sms ? a.n_tiles : 2 * dev->sms;
-  mlp_fused_kernel<MODE_BWD><<<grid, 192, MlpSmem::kTotal, s>>>(a);
+  mlp_fused_kernel<MODE_BWD><<<grid, 192, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
   NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
 
-  // 2. weight gradients: split the SMs over the work items in proportion to their cost
+int nerf_mlp_wgrad(int layout, const void* stash, const void* dstash, int64_t n_rows, float* grads, int accumulate,
+                   void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  const ModelLayout* m = get_layout(layout);
+  if (!m) return NERF_ERR_LAYOUT;
+  if (!stash || !dstash || !grads || n_rows < 0) return NERF_ERR_ARG;
+  if (!nerf_aligned(stash, 16) || !nerf_aligned(dstash, 16)) return NERF_ERR_ALIGN;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!accumulate) NERF_CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * m->n_params, s));
+  if (n_rows == 0) return NERF_OK;
+  const int n_tiles = (int)((n_rows + 127) / 128);
+
+  // weight gradients: split the SMs over the work items in proportion to their cost
   WgradArgs w;
   std::memset(&w, 0, sizeof(w));
-  w.stash = a.stash; w.dstash = a.dstash; w.grads = grads;
+  w.stash = static_cast<const uint8_t*>(stash); w.dstash = static_cast<const uint8_t*>(dstash); w.grads = grads;
   w.stash_tile_bytes = m->stash_tile_bytes; w.dstash_tile_bytes = m->dstash_tile_bytes;
-  w.n_tiles = a.n_tiles; w.n_items = m->n_wgrad;
+  w.n_tiles = n_tiles; w.n_items = m->n_wgrad;
   int64_t total_cost = 0;
   for (int i = 0; i < m->n_wgrad; ++i) { w.items[i] = m->wg[i]; total_cost += m->wg[i].cost; }
   int ctas = 0;
   for (int i = 0; i < m->n_wgrad; ++i) {
     int c = (int)((int64_t)dev->sms * m->wg[i].cost / total_cost);
     if (c < 1) c = 1;
-    if (c > a.n_tiles) c = a.n_tiles;
+    if (c > n_tiles) c = n_tiles;
     w.cta_begin[i] = ctas;
     ctas += c;
   }
@@ -297,16 +309,25 @@ int nerf_mlp_backward(const void* packed, int layout, const void* stash, const f
   wgrad_kernel<<<ctas, 192, kWgSmemBytes, s>>>(w);
   NERF_LAUNCH_CHECK();
 
-  // 3. head gradients (density_layer, rgb_layer2)
+  // head gradients (density_layer, rgb_layer2)
   HeadGradArgs h{};
-  h.stash = a.stash; h.dstash = a.dstash; h.grads = grads;
-  h.stash_tile_bytes = m->stash_tile_bytes; h.dstash_tile_bytes = m->dstash_tile_bytes; h.n_tiles = a.n_tiles;
+  h.stash = w.stash; h.dstash = w.dstash; h.grads = grads;
+  h.stash_tile_bytes = m->stash_tile_bytes; h.dstash_tile_bytes = m->dstash_tile_bytes; h.n_tiles = n_tiles;
   h.st_h8 = m->st_h[8]; h.st_r1 = m->st_r1; h.ds_sr = m->ds_sr;
   h.g_wd = m->w_off[L_DENS]; h.g_bd = m->b_off[L_DENS]; h.g_w2 = m->w_off[L_RGB2]; h.g_b2 = m->b_off[L_RGB2];
-  const int hgrid = a.n_tiles < 4 * dev->sms ? a.n_tiles : 4 * dev->sms;
+  const int hgrid = n_tiles < 4 * dev->sms ? n_tiles : 4 * dev->sms;
   head_grad_kernel<<<hgrid, 384, 0, s>>>(h);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
+}
+
+int nerf_mlp_backward(const void* packed, int layout, const void* stash, const float* sigma_rgb,
+                      const float* d_sigma_rgb, int64_t n_rows, void* dstash, float* grads, int accumulate,
+                      void* stream) {
+  if (!grads) return NERF_ERR_ARG;
+  int rc = nerf_mlp_dgrad(packed, layout, stash, sigma_rgb, d_sigma_rgb, n_rows, dstash, stream);
+  if (rc != NERF_OK) return rc;
+  return nerf_mlp_wgrad(layout, stash, dstash, n_rows, grads, accumulate, stream);
 }
 
 // ------------------------------------------------------------------------------------ K5

@@ -34,7 +34,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // alpha_i = 1 - exp(-sigma_i * delta_i); delta_{S-1} = 1e-3 (train.py:248-254)
 __device__ __forceinline__ void sample_alpha(const float* __restrict__ zr, int s, int S, float sigma,
                                              float& delta, float& alpha) {
-  delta = (s < S - 1) ? __fsub_rn(zr[s + 1], zr[s]) : 1e-3f;
+  // last delta = 1e-3 (train.py:250); with S == 1 the reference's `dists` is EMPTY (its ones_like of an
+  // empty slice) and every output is 0 -- reproduced by a zero delta.
+  delta = (s < S - 1) ? __fsub_rn(zr[s + 1], zr[s]) : (S == 1 ? 0.0f : 1e-3f);
   alpha = __fsub_rn(1.0f, expf(-__fmul_rn(sigma, delta)));
 }
 

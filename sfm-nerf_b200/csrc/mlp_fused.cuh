@@ -37,7 +37,7 @@ struct MlpArgs {
   uint8_t* stash;            // fwd: written when non-null; bwd: read
   uint8_t* dstash;           // bwd: written
   int32_t stash_tile_bytes, dstash_tile_bytes;
-  int32_t st_pe, st_de, st_r1, ds_y10, ds_sr;
+  int32_t st_pe, st_de, st_r1, st_mask, ds_y10, ds_sr;
   Program prog;
 };
 
@@ -104,6 +104,18 @@ __device__ __forceinline__ void write_encoding(uint32_t enc_smem, int row, const
                      tc::pack_bf16x2(e[8 * kc + 0], e[8 * kc + 1]), tc::pack_bf16x2(e[8 * kc + 2], e[8 * kc + 3]),
                      tc::pack_bf16x2(e[8 * kc + 4], e[8 * kc + 5]), tc::pack_bf16x2(e[8 * kc + 6], e[8 * kc + 7]));
   }
+}
+
+// word `i` (runtime) of eight mask words held in registers, without dynamic register indexing
+__device__ __forceinline__ uint32_t pick8(const uint4& a, const uint4& b, int i) {
+  uint32_t r = a.x;
+  r = (i == 1) ? a.y : r; r = (i == 2) ? a.z : r; r = (i == 3) ? a.w : r;
+  r = (i == 4) ? b.x : r; r = (i == 5) ? b.y : r; r = (i == 6) ? b.z : r; r = (i == 7) ? b.w : r;
+  return r;
+}
+__device__ __forceinline__ void put8(uint4& a, uint4& b, int i, uint32_t v) {
+  a.x = (i == 0) ? v : a.x; a.y = (i == 1) ? v : a.y; a.z = (i == 2) ? v : a.z; a.w = (i == 3) ? v : a.w;
+  b.x = (i == 4) ? v : b.x; b.y = (i == 5) ? v : b.y; b.z = (i == 6) ? v : b.z; b.w = (i == 7) ? v : b.w;
 }
 
 __device__ __forceinline__ float softplus_f(float x) {        // torch default beta=1, threshold=20
@@ -238,18 +250,16 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
         const float d0 = d.y * o.y * (1.0f - o.y), d1 = d.z * o.z * (1.0f - o.z), d2 = d.w * o.w * (1.0f - o.w);
         reinterpret_cast<float4*>(dstash_tile + a.ds_sr)[row] = make_float4(dsp, d0, d1, d2);
         const float* w2 = a.small + a.sm_w2;
-        const uint4* r1 = reinterpret_cast<const uint4*>(stash_tile + a.st_r1);
-#pragma unroll 4
+        const uint4 r1m = __ldg(reinterpret_cast<const uint4*>(stash_tile + a.st_mask + 10 * 4096) + row * 2);
+        const uint32_t r1w[4] = {r1m.x, r1m.y, r1m.z, r1m.w};
+#pragma unroll
         for (int kc = 0; kc < 16; ++kc) {
-          const uint4 m = __ldg(r1 + kc * 128 + row);
-          const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
           float g[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int c = kc * 8 + j;
             const float v = d0 * __ldg(w2 + c) + d1 * __ldg(w2 + 128 + c) + d2 * __ldg(w2 + 256 + c);
-            const float h = (j & 1) ? bf16hi(mw[j >> 1]) : bf16lo(mw[j >> 1]);
-            g[j] = h > 0.0f ? v : 0.0f;
+            g[j] = ((r1w[kc >> 2] >> ((kc & 3) * 8 + j)) & 1u) ? v : 0.0f;
           }
           tc::st_shared_v4(s_act + kc * kKcoreBytes + row * 16, tc::pack_bf16x2(g[0], g[1]),
                            tc::pack_bf16x2(g[2], g[3]), tc::pack_bf16x2(g[4], g[5]), tc::pack_bf16x2(g[6], g[7]));
@@ -263,6 +273,11 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
       // ---------------- layer steps ----------------
       for (int si = 0; si < P.n_steps; ++si) {
         const Step& st = P.s[si];
+        uint4 mk_a = make_uint4(0u, 0u, 0u, 0u), mk_b = make_uint4(0u, 0u, 0u, 0u);   // this row's ReLU mask words
+        if (MODE == MODE_BWD) {                        // fetched while the MMAs of this step still run
+          const uint4* mp = reinterpret_cast<const uint4*>(stash_tile + st.mask_off) + row * 2;
+          mk_a = __ldg(mp); mk_b = __ldg(mp + 1);
+        }
         tc::mbar_wait(bar_acc, acc_phase & 1u); ++acc_phase;
         tc::tc_fence_after();
         const bool store_out = (MODE == MODE_BWD) || train;
@@ -310,6 +325,12 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
                 c2 = fmaf(y[j], wc.x, c2); c2 = fmaf(y[j + 1], wc.y, c2); c2 = fmaf(y[j + 2], wc.z, c2); c2 = fmaf(y[j + 3], wc.w, c2);
               }
             }
+            if (train) {
+              uint32_t word = 0u;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) word |= (y[j] > 0.0f) ? (1u << j) : 0u;
+              put8(mk_a, mk_b, ch, word);
+            }
             if (!is_rgb || train) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
@@ -317,6 +338,10 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
                                  tc::pack_bf16x2(y[8 * q + 0], y[8 * q + 1]), tc::pack_bf16x2(y[8 * q + 2], y[8 * q + 3]),
                                  tc::pack_bf16x2(y[8 * q + 4], y[8 * q + 5]), tc::pack_bf16x2(y[8 * q + 6], y[8 * q + 7]));
             }
+          }
+          if (train) {
+            uint4* mp = reinterpret_cast<uint4*>(stash_tile + st.mask_off) + row * 2;
+            mp[0] = mk_a; mp[1] = mk_b;
           }
           if (is_dens) sigma_keep = softplus_f(dens + __ldg(a.small + a.sm_bd));
           if (is_rgb && valid) {
@@ -329,12 +354,9 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
             else write_encoding<0, 4>(s_enc, row, dirv);
           }
         } else {
-          const uint4* hm = reinterpret_cast<const uint4*>(stash_tile + st.mask_off);
           const bool add_sigma = (st.flags & EPI_BWD_SIGMA) != 0;
           for (int ch = 0; ch < n_chunks; ++ch) {
-            uint4 m[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) m[q] = __ldg(hm + (ch * 4 + q) * 128 + row);
+            const uint32_t word = pick8(mk_a, mk_b, ch);
             uint32_t v[32];
             tc::tmem_ld32(t_lane + ch * 32, v);
             tc::tmem_wait_ld();
@@ -351,17 +373,12 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
               }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t mw[4] = {m[q].x, m[q].y, m[q].z, m[q].w};
+            for (int j = 0; j < 32; ++j) y[j] = ((word >> j) & 1u) ? y[j] : 0.0f;     // relu'(h)
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float h = (j & 1) ? bf16hi(mw[j >> 1]) : bf16lo(mw[j >> 1]);
-                if (!(h > 0.0f)) y[8 * q + j] = 0.0f;
-              }
+            for (int q = 0; q < 4; ++q)
               tc::st_shared_v4(s_act + (ch * 4 + q) * kKcoreBytes + row * 16,
                                tc::pack_bf16x2(y[8 * q + 0], y[8 * q + 1]), tc::pack_bf16x2(y[8 * q + 2], y[8 * q + 3]),
                                tc::pack_bf16x2(y[8 * q + 4], y[8 * q + 5]), tc::pack_bf16x2(y[8 * q + 6], y[8 * q + 7]));
-            }
           }
         }
         tc::tc_fence_before();                         // TMEM reads retired before the next MMA overwrites

@@ -41,7 +41,7 @@ struct Step {
   int32_t bias_off;     // float offset inside the packed "small" table, -1 = none
   int32_t flags;
   int32_t stash_off;    // byte offset of the OUTPUT block inside a tile's stash (fwd) / dstash (bwd)
-  int32_t mask_off;     // bwd: byte offset (fwd stash) of the activation whose sign masks the output
+  int32_t mask_off;     // byte offset (fwd stash) of the ReLU bit mask: written (fwd) / applied to the output (bwd)
   // pack-time description of the B operand (rows n, contraction index kk):
   int32_t p_w;          // float offset of the Linear weight in the flat parameter vector
   int32_t p_in;         // its in_features (row stride)
@@ -89,8 +89,9 @@ struct ModelLayout {
   int32_t packed_bytes;
   // small table (float offsets): biases of the 11 MMA layers at 256*i, then heads
   int32_t sm_wd, sm_bd, sm_w2, sm_b2;
-  // per-tile stash (bytes): PE, DE, H0..H9 (h0..h8, feature), R1
-  int32_t st_pe, st_de, st_h[10], st_r1, stash_tile_bytes;
+  // per-tile stash (bytes): PE, DE, H0..H9 (h0..h8, feature), R1, then 11 ReLU bit masks
+  // ([row][8 x u32] = 4 KB each; bit c of a row = output channel c of that layer was > 0)
+  int32_t st_pe, st_de, st_h[10], st_r1, st_mask, stash_tile_bytes;
   // per-tile dstash: dY0..dY9 (64 KB each), dY10 (32 KB), dsr fp32 [128][4]
   int32_t ds_y[11], ds_sr, dstash_tile_bytes;
   int32_t n_wgrad;
@@ -126,6 +127,7 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
   m.st_de = so; so += 4 * kKcoreBytes;
   for (int i = 0; i < 10; ++i) { m.st_h[i] = so; so += kActBytes; }
   m.st_r1 = so; so += 16 * kKcoreBytes;
+  m.st_mask = so; so += 11 * 4096;
   m.stash_tile_bytes = so;
   int dso = 0;
   for (int i = 0; i < 10; ++i) { m.ds_y[i] = dso; dso += kActBytes; }
@@ -160,6 +162,7 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
     add(f, fstep(L_FC2_0 + i, 256, 16, 0, 0, 0, (i == 2 ? EPI_DENSITY : 0), m.st_h[6 + i]));
   add(f, fstep(L_FEAT, 256, 16, 0, 0, 0, 0, m.st_h[9]));
   add(f, fstep(L_RGB1, 128, 16, dir_ks, 256, m.dir_in, EPI_RGB | EPI_LAST, m.st_r1));
+  for (int i = 0; i < f.n_steps; ++i) f.s[i].mask_off = m.st_mask + i * 4096;
 
   // ---- backward (dgrad) program: dX = dY . W, masked by relu'(x) ---------------------------
   auto bstep = [&](int lin, int act_ks, int flags, int dstash_off, int mask_off) {
@@ -174,16 +177,16 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
   Program& b = m.bwd;
   // dY10 (rgb1 pre-activation grad, 128 ch) is produced by the prologue.  Step j outputs the
   // masked gradient w.r.t. the pre-activation of forward step (9-j): dY9 (feature) ... dY0 (fc1).
-  add(b, bstep(L_RGB1, 8, 0, m.ds_y[9], m.st_h[9]));
-  add(b, bstep(L_FEAT, 16, EPI_BWD_SIGMA, m.ds_y[8], m.st_h[8]));
-  add(b, bstep(L_FC2_0 + 2, 16, 0, m.ds_y[7], m.st_h[7]));
-  add(b, bstep(L_FC2_0 + 1, 16, 0, m.ds_y[6], m.st_h[6]));
-  add(b, bstep(L_FC2_0 + 0, 16, 0, m.ds_y[5], m.st_h[5]));
-  add(b, bstep(L_SKIP, 16, 0, m.ds_y[4], m.st_h[4]));
-  add(b, bstep(L_FC0 + 3, 16, 0, m.ds_y[3], m.st_h[3]));
-  add(b, bstep(L_FC0 + 2, 16, 0, m.ds_y[2], m.st_h[2]));
-  add(b, bstep(L_FC0 + 1, 16, 0, m.ds_y[1], m.st_h[1]));
-  add(b, bstep(L_FC0 + 0, 16, EPI_LAST, m.ds_y[0], m.st_h[0]));
+  add(b, bstep(L_RGB1, 8, 0, m.ds_y[9], m.st_mask + 9 * 4096));
+  add(b, bstep(L_FEAT, 16, EPI_BWD_SIGMA, m.ds_y[8], m.st_mask + 8 * 4096));
+  add(b, bstep(L_FC2_0 + 2, 16, 0, m.ds_y[7], m.st_mask + 7 * 4096));
+  add(b, bstep(L_FC2_0 + 1, 16, 0, m.ds_y[6], m.st_mask + 6 * 4096));
+  add(b, bstep(L_FC2_0 + 0, 16, 0, m.ds_y[5], m.st_mask + 5 * 4096));
+  add(b, bstep(L_SKIP, 16, 0, m.ds_y[4], m.st_mask + 4 * 4096));
+  add(b, bstep(L_FC0 + 3, 16, 0, m.ds_y[3], m.st_mask + 3 * 4096));
+  add(b, bstep(L_FC0 + 2, 16, 0, m.ds_y[2], m.st_mask + 2 * 4096));
+  add(b, bstep(L_FC0 + 1, 16, 0, m.ds_y[1], m.st_mask + 1 * 4096));
+  add(b, bstep(L_FC0 + 0, 16, EPI_LAST, m.ds_y[0], m.st_mask + 0 * 4096));
 
   // packed buffer
   const int fwd_bytes = f.image_bytes, bwd_bytes = b.image_bytes;
@@ -200,9 +203,10 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
     w.dy_off = dy_off; w.m_kcores = m_kcores; w.x_off = x_off; w.n = n; w.n_valid = n_valid;
     w.w_off = m.w_off[lin]; w.in_f = m.in_f[lin]; w.col0 = col0;
     w.b_off = owns_bias ? m.b_off[lin] : -1;
-    // cost ~ MMA cycles (m_halves * n/2 per k-step) vs. load bytes (both per 64 rows), whichever binds
-    const int mma = (m_kcores / 16) * n * 2;
-    const int ld = (m_kcores + n / 8) * 8;
+    // cost per 128-row tile in SM cycles: UMMA time (128xNx16 = N/2 cycles, 8 k-steps per M half) vs.
+    // the time to stream both operand blocks at one SM's share of HBM (~20 B/cycle), whichever binds
+    const int mma = (m_kcores / 16) * 4 * n;
+    const int ld = (m_kcores + n / 8) * (kKcoreBytes / 20);
     w.cost = mma > ld ? mma : ld;
     m.wg[m.n_wgrad++] = w;
   };

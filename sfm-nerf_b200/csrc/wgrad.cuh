@@ -3,7 +3,7 @@
 // blocked stash/dstash tiles ([k_core][row][8]); the fp32 accumulator (up to 256x256) lives in the
 // whole 512-column TMEM of one SM for the CTA's entire row range and is added into the flat
 // gradient vector once at the end (split-K over CTAs, red.global.add.f32).
-//   warp 0    : loader -- 64-row half tiles of dY and X, 1 KB bulk copies per k_core, 3-stage ring
+//   warp 0    : loader -- whole 128-row dY / X blocks, ONE bulk copy (<= 64 KB) each, ring of 3 slots
 //   warp 1    : MMA issuer (one thread)
 //   warps 2-5 : bias gradients (column sums of dY from the staged tile) + final TMEM -> HBM epilogue
 // Head gradients (density_layer, rgb_layer2: N < 16, not UMMA shapes) run on CUDA cores.
@@ -14,9 +14,9 @@
 
 namespace nerf {
 
-constexpr int kWgStages = 3;
-constexpr int kWgStageBytes = 65536;       // dY half tile (<= 32 KB) + X half tile (<= 32 KB)
-constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 128;
+constexpr int kWgSlots = 3;                // ring of operand slots: dY_t, X_t, dY_{t+1}, X_{t+1}, ...
+constexpr int kWgSlotBytes = 65536;        // one 128-row operand block (<= 256 channels)
+constexpr int kWgSmemBytes = kWgSlots * kWgSlotBytes + 128;
 
 struct WgradArgs {
   const uint8_t* stash;
@@ -31,13 +31,13 @@ struct WgradArgs {
 __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = tc::smem_u32(smem);
-  const uint32_t s_bar = s_base + kWgStages * kWgStageBytes;
+  const uint32_t s_bar = s_base + kWgSlots * kWgSlotBytes;
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 24, bar_acc = s_bar + 48;
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kWgStages * kWgStageBytes + 64);
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kWgSlots * kWgSlotBytes + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kWgStages; ++i) { tc::mbar_init(bar_full + 8 * i, 1); tc::mbar_init(bar_empty + 8 * i, 5); }
+    for (int i = 0; i < kWgSlots; ++i) { tc::mbar_init(bar_full + 8 * i, 1); tc::mbar_init(bar_empty + 8 * i, 5); }
     tc::mbar_init(bar_acc, 1);
     tc::fence_mbar_init();
   }
@@ -55,44 +55,48 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   const int split = (int)blockIdx.x - a.cta_begin[item];
   const int t0 = (int)(((int64_t)a.n_tiles * split) / splits);
   const int t1 = (int)(((int64_t)a.n_tiles * (split + 1)) / splits);
-  const int n_stages_total = (t1 - t0) * 2;
+  const int n_my_tiles = t1 - t0;
   const int m_halves = W.m_kcores / 16;
-  const int x_kcores = W.n / 8;
+  const uint32_t dy_bytes = (uint32_t)W.m_kcores * kKcoreBytes;
+  const uint32_t x_bytes = (uint32_t)(W.n / 8) * kKcoreBytes;
 
   if (warp == 0) {
-    // ===================== loader =====================
-    for (int s = 0; s < n_stages_total; ++s) {
-      const int tile = t0 + (s >> 1), half = s & 1;
-      const uint32_t slot = s % kWgStages, ph = (s / kWgStages) & 1u;
-      const uint32_t stage = s_base + slot * kWgStageBytes;
-      if (lane == 0) {
+    // ===================== loader: one bulk copy per operand block =====================
+    if (lane == 0) {
+      for (int L = 0; L < 2 * n_my_tiles; ++L) {
+        const int tile = t0 + (L >> 1);
+        const uint32_t slot = L % kWgSlots, ph = (L / kWgSlots) & 1u;
+        const bool is_dy = (L & 1) == 0;
+        const uint8_t* src = is_dy ? a.dstash + (size_t)tile * a.dstash_tile_bytes + W.dy_off
+                                   : a.stash + (size_t)tile * a.stash_tile_bytes + W.x_off;
+        const uint32_t bytes = is_dy ? dy_bytes : x_bytes;
         tc::mbar_wait(bar_empty + 8 * slot, ph ^ 1u);
-        tc::mbar_arrive_expect_tx(bar_full + 8 * slot, (uint32_t)(W.m_kcores + x_kcores) * 1024u);
+        tc::mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+        tc::bulk_g2s(s_base + slot * kWgSlotBytes, src, bytes, bar_full + 8 * slot);
       }
-      __syncwarp();
-      const uint8_t* dy = a.dstash + (size_t)tile * a.dstash_tile_bytes + W.dy_off + half * 1024;
-      const uint8_t* x = a.stash + (size_t)tile * a.stash_tile_bytes + W.x_off + half * 1024;
-      for (int c = lane; c < W.m_kcores; c += 32) tc::bulk_g2s(stage + c * 1024, dy + (size_t)c * kKcoreBytes, 1024, bar_full + 8 * slot);
-      for (int c = lane; c < x_kcores; c += 32) tc::bulk_g2s(stage + 32768 + c * 1024, x + (size_t)c * kKcoreBytes, 1024, bar_full + 8 * slot);
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = tc::umma_idesc_bf16(128, W.n, 1, 1);
-      for (int s = 0; s < n_stages_total; ++s) {
-        const uint32_t slot = s % kWgStages, ph = (s / kWgStages) & 1u;
-        const uint32_t stage = s_base + slot * kWgStageBytes;
-        tc::mbar_wait(bar_full + 8 * slot, ph);
+      for (int i = 0; i < n_my_tiles; ++i) {
+        const int La = 2 * i, Lb = 2 * i + 1;
+        const uint32_t slot_a = La % kWgSlots, slot_b = Lb % kWgSlots;
+        tc::mbar_wait(bar_full + 8 * slot_a, (La / kWgSlots) & 1u);
+        tc::mbar_wait(bar_full + 8 * slot_b, (Lb / kWgSlots) & 1u);
         tc::tc_fence_after();
+        const uint32_t sa = s_base + slot_a * kWgSlotBytes, sb = s_base + slot_b * kWgSlotBytes;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t bdesc = tc::umma_smem_desc(stage + 32768 + ks * 256, 128, 1024);
+        for (int ks = 0; ks < 8; ++ks) {               // 16 rows (the contraction axis) per UMMA
+          const uint64_t bdesc = tc::umma_smem_desc(sb + ks * 256, 128, kKcoreBytes);
           for (int mh = 0; mh < m_halves; ++mh) {
-            const uint64_t adesc = tc::umma_smem_desc(stage + mh * 16384 + ks * 256, 128, 1024);
-            tc::umma_bf16(tmem_base + mh * W.n, adesc, bdesc, idesc, (s > 0 || ks > 0) ? 1u : 0u);
+            const uint64_t adesc = tc::umma_smem_desc(sa + mh * 16 * kKcoreBytes + ks * 256, 128, kKcoreBytes);
+            tc::umma_bf16(tmem_base + mh * W.n, adesc, bdesc, idesc, (i > 0 || ks > 0) ? 1u : 0u);
           }
         }
-        tc::umma_commit(bar_empty + 8 * slot);
+        tc::umma_commit(bar_empty + 8 * slot_a);
+        tc::umma_commit(bar_empty + 8 * slot_b);
       }
       tc::umma_commit(bar_acc);
     }
@@ -105,20 +109,21 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-    for (int s = 0; s < n_stages_total; ++s) {
-      const uint32_t slot = s % kWgStages, ph = (s / kWgStages) & 1u;
-      const uint32_t stage = s_base + slot * kWgStageBytes;
-      tc::mbar_wait(bar_full + 8 * slot, ph);
+    for (int t = 0; t < n_my_tiles; ++t) {
+      const int La = 2 * t, Lb = 2 * t + 1;
+      const uint32_t slot_a = La % kWgSlots, slot_b = Lb % kWgSlots;
+      const uint32_t sa = s_base + slot_a * kWgSlotBytes;
+      tc::mbar_wait(bar_full + 8 * slot_a, (La / kWgSlots) & 1u);
       if (W.b_off >= 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (i * 4 < W.m_kcores) {
             const int kc = q + 4 * i;
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
+            for (int rr = 0; rr < 4; ++rr) {
               uint32_t u0, u1, u2, u3;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(stage + kc * 1024 + (lane + 32 * rr) * 16));
+                           : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(sa + kc * kKcoreBytes + (lane + 32 * rr) * 16));
               acc[i][0] += __uint_as_float(u0 << 16); acc[i][1] += __uint_as_float(u0 & 0xffff0000u);
               acc[i][2] += __uint_as_float(u1 << 16); acc[i][3] += __uint_as_float(u1 & 0xffff0000u);
               acc[i][4] += __uint_as_float(u2 << 16); acc[i][5] += __uint_as_float(u2 & 0xffff0000u);
@@ -128,7 +133,11 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         }
       }
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(bar_empty + 8 * slot);
+      if (lane == 0) tc::mbar_arrive(bar_empty + 8 * slot_a);
+      // the X slot is not read here, but its "empty" barrier counts this warp too: arrive only once it
+      // has been filled for THIS tile, so the arrival cannot land in an earlier phase
+      tc::mbar_wait(bar_full + 8 * slot_b, (Lb / kWgSlots) & 1u);
+      if (lane == 0) tc::mbar_arrive(bar_empty + 8 * slot_b);
     }
     if (W.b_off >= 0) {
 #pragma unroll
@@ -149,7 +158,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     tc::tc_fence_after();
     const int lq = warp & 3;                      // TMEM lane quarter this warp may read
     const int n_chunks = (W.n + 31) >> 5;
-    if (n_stages_total > 0) {
+    if (n_my_tiles > 0) {
       for (int mh = 0; mh < m_halves; ++mh) {
         const int o = mh * 128 + lq * 32 + lane;
         float* dst = a.grads + W.w_off + (int64_t)o * W.in_f + W.col0;

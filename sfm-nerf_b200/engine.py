@@ -255,6 +255,25 @@ class RenderFunction(torch.autograd.Function):
         return (None, None, None, None) + tuple(v.view(s) for v, s in zip(st.split(grads), ctx.shapes))
 
 
+class _timed:
+    """Brackets a launch with CUDA events on the current stream when a timers dict is given."""
+
+    def __init__(self, timers, name):
+        self.timers, self.name = timers, name
+
+    def __enter__(self):
+        if self.timers is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.timers is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.timers.setdefault(self.name, []).append((self.a, b))
+        return False
+
+
 # ------------------------------------------------------------------------------------------
 # Fused train step (train.py:447-465) over the flat buffers: one call = one optimisation step.
 # ------------------------------------------------------------------------------------------
@@ -298,9 +317,10 @@ class Trainer:
     def close(self):
         self.st.frozen = False
 
-    def step(self, rays=None):
+    def step(self, rays=None, timers=None):
         """One optimisation step.  ``rays`` = optional (rays_o, rays_d, target) device tensors (e.g. a
-        batch uploaded from the host like train.py:448); default draws the batch on the GPU."""
+        batch uploaded from the host like train.py:448); default draws the batch on the GPU.
+        ``timers`` = optional dict: CUDA-event pairs per kernel are appended to timers[name]."""
         st, S = self.st, self.n_sample
         W, H = int(self.cam["width"]), int(self.cam["height"])
         dev = st.device
@@ -315,16 +335,25 @@ class Trainer:
         n_rays = o.shape[0]
         z = sample_z(n_rays, S, self.near, self.far, dev, perturb=self.perturb, seed=self.seed ^ 0x5bd1e995,
                      offset=ctr * ((n_rays * S + 3) // 4))
-        sigma_rgb = mlp_forward_rays(st, o, d, z, self.stash)
-        rgb, _, _ = composite_forward(sigma_rgb, z, extras=False)
+        with _timed(timers, "mlp_fwd"):
+            sigma_rgb = mlp_forward_rays(st, o, d, z, self.stash)
+        with _timed(timers, "composite_fwd"):
+            rgb, _, _ = composite_forward(sigma_rgb, z, extras=False)
         # local mean over this rank's rays; the allreduce sum is scaled by 1/world inside Adam
         call("nerf_mse_loss", ptr(rgb), ptr(tgt), n_rays, 1.0, ptr(self.loss), ptr(self.g_rgb), stream_ptr())
-        dsr = composite_backward(sigma_rgb, z, self.g_rgb[:n_rays])
-        mlp_backward(st, self.stash, sigma_rgb, dsr, self.grads, self.dstash)
-        launches += 9                               # sample, mlp fwd, comp fwd, mse, comp bwd, memset, dgrad, wgrad, heads
+        with _timed(timers, "composite_bwd"):
+            dsr = composite_backward(sigma_rgb, z, self.g_rgb[:n_rays])
+        rows = n_rays * S
+        with _timed(timers, "mlp_dgrad"):
+            call("nerf_mlp_dgrad", ptr(st.packed), st.layout, ptr(self.stash), ptr(sigma_rgb), ptr(dsr), rows,
+                 ptr(self.dstash), stream_ptr())
+        with _timed(timers, "mlp_wgrad"):
+            call("nerf_mlp_wgrad", st.layout, ptr(self.stash), ptr(self.dstash), rows, ptr(self.grads), 0, stream_ptr())
+        launches += 8                               # sample, mlp fwd, comp fwd, mse, comp bwd, dgrad, wgrad, heads (+1 memset)
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.pg)
+            with _timed(timers, "allreduce"):
+                dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.pg)
         lr = self.lr()
         self.iteration += 1
         call("nerf_adam_step", ptr(st.flat), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), st.n_params,
