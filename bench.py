@@ -120,7 +120,6 @@ def cpu_train_steps(n_rays, steps, warmup):
     for it in range(warmup + steps):
         k = rng.integers(0, 8, n_rays); x = rng.integers(0, IMG, n_rays); y = rng.integers(0, IMG, n_rays)
         t0 = time.perf_counter()
-        rays = orc.rays_from_indices(images, poses, cam, k, x % 16, y % 16) if False else None
         # ray generation as the reference does it (per-ray Python, train.py:119-125) is timed too
         batch = np.empty((n_rays, 9), np.float32)
         for i in range(n_rays):
@@ -251,23 +250,24 @@ def run_ours(args):
 
     # ---- render throughput (inference, no stash) for the same metric family -----------------
     args_r = argparse.Namespace(n_sample=N_SAMPLE, perturb=True, chunk_size=32768, n_rays_batch=IMG * IMG, near=2.0, far=6.0)
-    per_rank = IMG * IMG // world
+    r_begin, r_end = s.parallel.shard_range(IMG * IMG, rank, world)
+    per_rank = r_end - r_begin
     with torch.no_grad():
         st = model.kernel_state()
         for _ in range(2):
-            o, d = E.raygen_image(poses, 0, cam, rank * per_rank, per_rank)
+            o, d = E.raygen_image(poses, 0, cam, r_begin, per_rank)
             s.render(model, o, d, args_r)
         barrier()
         ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_frames = 10
         ev4.record()
         for f in range(n_frames):
-            o, d = E.raygen_image(poses, f % len(poses_np), cam, rank * per_rank, per_rank)
+            o, d = E.raygen_image(poses, f % len(poses_np), cam, r_begin, per_rank)
             s.render(model, o, d, args_r)
         ev5.record()
         barrier()
     render_ms = max_over_ranks(ev4.elapsed_time(ev5))
-    render_rays_s = per_rank * world * n_frames / render_ms * 1e3
+    render_rays_s = IMG * IMG * n_frames / render_ms * 1e3
     trainer.close()
 
     if rank != 0:

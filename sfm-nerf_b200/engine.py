@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _lib, parallel
 from ._lib import call, ptr, stream_ptr
 
 
@@ -325,7 +325,7 @@ class Trainer:
         W, H = int(self.cam["width"]), int(self.cam["height"])
         dev = st.device
         launches = 0
-        ctr = (self.iteration * self.world + self.rank)
+        ctr = parallel.batch_counter(self.iteration, self.rank, self.world)
         if rays is None:
             k, x, y = draw_pixels(self.seed, ctr * self.n_rays, self.images.shape[0], W, H, self.n_rays, dev)
             o, d, tgt = raygen_batch(self.poses, self.cam, k, x, y, self.images)
@@ -351,13 +351,12 @@ class Trainer:
             call("nerf_mlp_wgrad", st.layout, ptr(self.stash), ptr(self.dstash), rows, ptr(self.grads), 0, stream_ptr())
         launches += 8                               # sample, mlp fwd, comp fwd, mse, comp bwd, dgrad, wgrad, heads (+1 memset)
         if self.world > 1:
-            import torch.distributed as dist
             with _timed(timers, "allreduce"):
-                dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.pg)
+                parallel.allreduce_sum_(self.grads, self.pg)
         lr = self.lr()
         self.iteration += 1
         call("nerf_adam_step", ptr(st.flat), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), st.n_params,
-             lr, self.betas[0], self.betas[1], self.eps, self.iteration, 1.0 / self.world, stream_ptr())
+             lr, self.betas[0], self.betas[1], self.eps, self.iteration, parallel.mean_scale(self.world), stream_ptr())
         st.pack()
         launches += 4
         self.launches_per_step = launches
