@@ -172,12 +172,12 @@ def model_forward(sd, pos, direction, embed_pos_L=10, embed_direction_L=4, pos_e
     post-activation tensors in layer order (used by per-layer parity tests).
 
     ``operand_dtype=torch.bfloat16`` restates the SAME network with the operand rounding of a
-    bf16-tensor-core evaluation (weights and inputs of the eleven 128/256-wide layers rounded to
-    bf16, fp32 accumulation, fp32 density / rgb heads).  It is NOT reference behaviour; tests use it
+    bf16-tensor-core evaluation (weights, biases and inputs of the eleven 128/256-wide layers rounded
+    to bf16, fp32 accumulation, fp32 density / rgb heads).  It is NOT reference behaviour; tests use it
     to separate "kernel is wrong" from "bf16 operands differ from fp32" when comparing gradients,
     whose element-wise error is dominated by ReLU masks flipping for near-zero pre-activations."""
     q = lambda x: _round_st(x, operand_dtype)
-    lin = lambda name, x: F.linear(x, q(sd[name + ".weight"]), sd[name + ".bias"])
+    lin = lambda name, x: F.linear(x, q(sd[name + ".weight"]), q(sd[name + ".bias"]))   # bias rides on the MMA too
     head = lambda name, x: F.linear(x, sd[name + ".weight"], sd[name + ".bias"])
     if pos_encoding:
         pe = position_encoding(pos, embed_pos_L)

@@ -79,8 +79,9 @@ int launch_forward(const void* packed, int layout, const float* pos, const float
   a.sigma_rgb = sigma_rgb;
   a.stash = static_cast<uint8_t*>(stash);
   a.prog = m->fwd;
-  const int grid = a.n_tiles < 2 * dev->sms ? a.n_tiles : 2 * dev->sms;
-  mlp_fused_kernel<MODE_FWD><<<grid, 192, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
+  const int n_pairs = (a.n_tiles + 1) / 2;               // one CTA per SM, two resident tiles each
+  const int grid = n_pairs < dev->sms ? n_pairs : dev->sms;
+  mlp_fused_kernel<MODE_FWD><<<grid, kMlpThreads, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
@@ -215,12 +216,9 @@ int nerf_mlp_pack_weights(const float* params, int layout, void* packed, void* s
   pack_images_kernel<<<dim3(64, m->bwd.n_steps), 256, 0, s>>>(params, m->bwd, static_cast<uint8_t*>(packed));
   NERF_LAUNCH_CHECK();
   PackSmallArgs p{};
-  p.n_bias = m->fwd.n_steps;
-  const int lin_of_step[11] = {L_FC1, L_FC0, L_FC0 + 1, L_FC0 + 2, L_FC0 + 3, L_SKIP, L_FC2_0, L_FC2_0 + 1, L_FC2_0 + 2, L_FEAT, L_RGB1};
-  for (int i = 0; i < 11; ++i) { p.b_src[i] = m->b_off[lin_of_step[i]]; p.b_n[i] = m->out_f[lin_of_step[i]]; }
   p.wd_src = m->w_off[L_DENS]; p.bd_src = m->b_off[L_DENS]; p.w2_src = m->w_off[L_RGB2]; p.b2_src = m->b_off[L_RGB2];
   p.sm_wd = m->sm_wd; p.sm_bd = m->sm_bd; p.sm_w2 = m->sm_w2; p.sm_b2 = m->sm_b2;
-  pack_small_kernel<<<blocks_for(11 * 256, 256), 256, 0, s>>>(params, p, reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + m->small_off));
+  pack_small_kernel<<<2, 256, 0, s>>>(params, p, reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + m->small_off));
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
@@ -269,8 +267,9 @@ int nerf_mlp_dgrad(const void* packed, int layout, const void* stash, const floa
   a.stash = static_cast<uint8_t*>(const_cast<void*>(stash));
   a.dstash = static_cast<uint8_t*>(dstash);
   a.prog = m->bwd;
-  const int grid = a.n_tiles < 2 * dev->sms ? a.n_tiles : 2 * dev->sms;
-  mlp_fused_kernel<MODE_BWD><<<grid, 192, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
+  const int n_pairs = (a.n_tiles + 1) / 2;
+  const int grid = n_pairs < dev->sms ? n_pairs : dev->sms;
+  mlp_fused_kernel<MODE_BWD><<<grid, kMlpThreads, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }

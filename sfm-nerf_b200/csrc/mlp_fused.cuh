@@ -1,15 +1,22 @@
-// mlp_fused.cuh -- K4: the fused NeRF MLP (NeRFModel.py:158-202) as ONE tcgen05 kernel, used for
+// mlp_fused.cuh -- K4: the fused NeRF MLP (NeRFModel.py:158-202) as ONE persistent tcgen05 kernel:
 //   MODE_FWD : positions/directions (or rays + depths) -> encoding -> 11 chained UMMA layers ->
 //              density/rgb heads; activations never leave the SM (training additionally bulk-stores
-//              a bf16 stash of every layer input for the weight-gradient kernel).
+//              a bf16 stash of every layer input + ReLU bit masks for the backward kernels).
 //   MODE_BWD : the data-gradient chain dY_l = (dY_{l+1} . W_{l+1}) * relu'(h_l), same machinery
 //              with transposed weight images; emits every dY_l to the dstash.
 //
-// One CTA = one 128-row tile in flight, 2 CTAs per SM (each owns 256 TMEM columns and ~105 KB of
-// shared memory) so one CTA's epilogue overlaps the other's MMAs.  Warp roles:
-//   warps 0-3 : epilogue (thread = row = TMEM lane): TMEM -> regs -> bias/ReLU -> bf16 -> next A tile
-//   warp  4   : weight loader, 1-D bulk copies (TMA engine) of 8 KB K=16 weight images into a ring
-//   warp  5   : MMA issuer (one thread), tcgen05.mma kind::f16 128xNx16, accumulator in TMEM
+// One CTA per SM keeps TWO 128-row tiles resident (2 x 64 KB activation tiles in shared memory,
+// 2 x 256 TMEM columns).  Weights stream from L2 through an 8-slot ring of K=16 slabs (8 KB); every
+// slab is consumed by BOTH tiles before its slot is recycled, so weight traffic per MMA is halved and
+// 64 KB of loads are always in flight.  Within a layer the MMA issuer alternates between the tiles in
+// groups of 8 k-steps (A: k0-7, B: k0-7, A: k8-15, B: k8-15): while one tile's epilogue runs on its
+// warpgroup, the tensor pipe works on the other tile.
+//   warps 0-3 / 4-7 : epilogue of tile slot 0 / 1 (thread = row = TMEM lane):
+//                     TMEM -> regs -> ReLU+bf16 pack (one cvt) -> next layer's A tile, in place
+//   warp 8          : weight loader (1-D bulk copies into the ring)
+//   warp 9          : MMA issuer (one thread), tcgen05.mma kind::f16 128xNx16, accumulators in TMEM
+// Biases ride on the MMA: channel 63 of the encoding tile is the constant 1.0 and the packed weight
+// image carries the bias in that K column, so the epilogue does no bias loads or adds.
 #pragma once
 #include "common.cuh"
 #include "mlp_layout.cuh"
@@ -19,10 +26,12 @@ namespace nerf {
 
 constexpr int MODE_FWD = 0;
 constexpr int MODE_BWD = 1;
+constexpr int kMlpThreads = 320;
+constexpr int kGroupKsteps = 8;     // k-steps issued for one tile before switching to the other
 
 struct MlpArgs {
   const uint8_t* packed;     // weight images
-  const float* small;        // biases + heads (fp32)
+  const float* small;        // heads (fp32)
   // forward inputs: per-row (pos, dir) or per-ray (rays_o, rays_d, z) with n_sample > 0
   const float* pos;
   const float* dir;
@@ -42,15 +51,14 @@ struct MlpArgs {
 };
 
 struct MlpSmem {
-  static constexpr int kAct = 0;
-  static constexpr int kEnc = kAct + kActBytes;
-  static constexpr int kRing = kEnc + kEncBytes;
+  static constexpr int kAct = 0;                                   // 2 x 64 KB
+  static constexpr int kEnc = kAct + 2 * kActBytes;                // 2 x 16 KB
+  static constexpr int kRing = kEnc + 2 * kEncBytes;               // 8 x 8 KB
   static constexpr int kBars = kRing + kRingSlots * kRingSlotBytes;
-  static constexpr int kTotal = kBars + 128;
+  // barriers (8 B each): full[8] @0, empty[8] @64, acc_full[2] @128, act_ready[2] @144; tmem ptr @160
+  static constexpr int kTotal = kBars + 256;
 };
-
-__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+static_assert(MlpSmem::kTotal <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
 // sin/cos positional encoding of one scalar for level `i` from the exact decomposition
 // a_i = 2^i * fl32(fl32(pi) * x) (NeRFModel.py:151-156): the angle is carried in
@@ -76,8 +84,9 @@ __device__ __forceinline__ void pe_sincos(const TurnsF& t, int level, float& s, 
 }
 
 // Encodes v[3] with L levels into bf16 channels [v, sin0(v), cos0(v), ...] padded with zeros to
-// 8*n_kcores channels, stored at enc + kcore*2048 + row*16.
-template <int L, int NKC>
+// 8*NKC channels, stored at enc + kcore*2048 + row*16.  ONE: the last channel is the constant 1.0
+// (the K column the packed weight images pair with the bias).
+template <int L, int NKC, bool ONE>
 __device__ __forceinline__ void write_encoding(uint32_t enc_smem, int row, const float v[3]) {
   float e[NKC * 8];
 #pragma unroll
@@ -98,6 +107,7 @@ __device__ __forceinline__ void write_encoding(uint32_t enc_smem, int row, const
       }
     }
   }
+  if (ONE) e[NKC * 8 - 1] = 1.0f;
 #pragma unroll
   for (int kc = 0; kc < NKC; ++kc) {
     tc::st_shared_v4(enc_smem + kc * kKcoreBytes + row * 16,
@@ -124,40 +134,37 @@ __device__ __forceinline__ float softplus_f(float x) {        // torch default b
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 template <int MODE>
-__global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant__ MlpArgs a) {
+__global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_constant__ MlpArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = tc::smem_u32(smem);
-  const uint32_t s_act = s_base + MlpSmem::kAct;
-  const uint32_t s_enc = s_base + MlpSmem::kEnc;
   const uint32_t s_ring = s_base + MlpSmem::kRing;
   const uint32_t s_bar = s_base + MlpSmem::kBars;
-  // barrier slots (8 B each): full[3] @0, empty[3] @24, acc_full @48, act_ready @56; tmem ptr @64
-  const uint32_t bar_full = s_bar, bar_empty = s_bar + 24, bar_acc = s_bar + 48, bar_act = s_bar + 56;
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kBars + 64);
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 64, bar_acc = s_bar + 128, bar_act = s_bar + 144;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kBars + 160);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingSlots; ++i) { tc::mbar_init(bar_full + 8 * i, 1); tc::mbar_init(bar_empty + 8 * i, 1); }
-    tc::mbar_init(bar_acc, 1);
-    tc::mbar_init(bar_act, 128);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(bar_acc + 8 * i, 1); tc::mbar_init(bar_act + 8 * i, 128); }
     tc::fence_mbar_init();
   }
-  if (warp == 4) tc::tmem_alloc(tc::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 256);
+  if (warp == 8) tc::tmem_alloc(tc::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const Program& P = a.prog;
+  const int n_pairs = (a.n_tiles + 1) >> 1;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== weight loader =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int si = 0; si < P.n_steps; ++si) {
           const Step& st = P.s[si];
           const uint32_t bytes = (uint32_t)st.n * 32u;
-          const int total = st.act_ksteps + st.enc_ksteps;
+          const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
           const uint8_t* src = a.packed + st.w_off;
           for (int k = 0; k < total; ++k, ++it) {
             const uint32_t slot = it % kRingSlots, ph = (it / kRingSlots) & 1u;
@@ -169,51 +176,68 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t it = 0, act_phase = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        for (int si = 0; si < P.n_steps; ++si) {
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int si = 0; si < P.n_steps; ++si, ++act_phase) {
           const Step& st = P.s[si];
-          const int total = st.act_ksteps + st.enc_ksteps;
+          const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
           const uint32_t idesc = tc::umma_idesc_bf16(128, st.n, 0, 0);
-          tc::mbar_wait(bar_act, act_phase & 1u); ++act_phase;
-          tc::tc_fence_after();
-          for (int k = 0; k < total; ++k, ++it) {
-            const uint32_t slot = it % kRingSlots, ph = (it / kRingSlots) & 1u;
-            tc::mbar_wait(bar_full + 8 * slot, ph);
-            tc::tc_fence_after();
-            const uint32_t a_addr = (k < st.act_ksteps) ? (s_act + k * 2 * kKcoreBytes)
-                                                        : (s_enc + (k - st.act_ksteps) * 2 * kKcoreBytes);
-            const uint64_t adesc = tc::umma_smem_desc(a_addr, kKcoreBytes, 128);
-            const uint64_t bdesc = tc::umma_smem_desc(s_ring + slot * kRingSlotBytes, (uint32_t)st.n * 16u, 128);
-            tc::umma_bf16(tmem_base, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
-            tc::umma_commit(bar_empty + 8 * slot);
+          for (int g0 = 0; g0 < total; g0 += kGroupKsteps) {
+            const int g1 = (g0 + kGroupKsteps < total) ? g0 + kGroupKsteps : total;
+            for (int slot = 0; slot < 2; ++slot) {
+              const uint32_t s_act = s_base + MlpSmem::kAct + slot * kActBytes;
+              const uint32_t s_enc = s_base + MlpSmem::kEnc + slot * kEncBytes;
+              if (g0 == 0) { tc::mbar_wait(bar_act + 8 * slot, act_phase & 1u); tc::tc_fence_after(); }
+              for (int k = g0; k < g1; ++k) {
+                const uint32_t j = it + (uint32_t)(k - g0);
+                const uint32_t rs = j % kRingSlots;
+                if (slot == 0) { tc::mbar_wait(bar_full + 8 * rs, (j / kRingSlots) & 1u); tc::tc_fence_after(); }
+                uint32_t a_addr;
+                if (k < st.act_ksteps) a_addr = s_act + k * 2 * kKcoreBytes;
+                else if (k < st.act_ksteps + st.enc_ksteps) a_addr = s_enc + (k - st.act_ksteps) * 2 * kKcoreBytes;
+                else a_addr = s_enc + 3 * 2 * kKcoreBytes;                     // the "ones" k-step (channel 63 == 1.0)
+                const uint64_t adesc = tc::umma_smem_desc(a_addr, kKcoreBytes, 128);
+                const uint64_t bdesc = tc::umma_smem_desc(s_ring + rs * kRingSlotBytes, (uint32_t)st.n * 16u, 128);
+                tc::umma_bf16(tmem_base + 256 * slot, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
+                if (slot == 1) tc::umma_commit(bar_empty + 8 * rs);            // both tiles have used this slab
+              }
+              if (g1 == total) tc::umma_commit(bar_acc + 8 * slot);
+            }
+            it += (uint32_t)(g1 - g0);
           }
-          tc::umma_commit(bar_acc);
         }
       }
     }
     __syncwarp();
   } else {
-    // ===================== epilogue warps (thread = row) =====================
-    const int row = threadIdx.x;                       // 0..127 == TMEM lane
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // ===================== epilogue warpgroups (thread = row) =====================
+    const int slot = warp >> 2;                        // tile slot of this warpgroup
+    const int row = threadIdx.x & 127;                 // 0..127 == TMEM lane
+    const uint32_t s_act = s_base + MlpSmem::kAct + slot * kActBytes;
+    const uint32_t s_enc = s_base + MlpSmem::kEnc + slot * kEncBytes;
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256 * slot;
+    const uint32_t my_acc = bar_acc + 8 * slot, my_act = bar_act + 8 * slot;
+    const uint32_t nb = 1 + slot;                      // named barrier of this warpgroup
     const bool train = (a.stash != nullptr);
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int tile = 2 * pair + slot;
+      const bool tile_ok = tile < a.n_tiles;           // odd tile count: the last pair's second slot is a phantom
       const int64_t grow = (int64_t)tile * 128 + row;
-      const bool valid = grow < a.n_rows;
-      uint8_t* stash_tile = train ? a.stash + (size_t)tile * a.stash_tile_bytes : nullptr;
-      uint8_t* dstash_tile = (MODE == MODE_BWD) ? a.dstash + (size_t)tile * a.dstash_tile_bytes : nullptr;
+      const bool valid = tile_ok && grow < a.n_rows;
+      uint8_t* stash_tile = (train && tile_ok) ? a.stash + (size_t)tile * a.stash_tile_bytes : nullptr;
+      uint8_t* dstash_tile = (MODE == MODE_BWD && tile_ok) ? a.dstash + (size_t)tile * a.dstash_tile_bytes : nullptr;
+      const bool store_out = tile_ok && ((MODE == MODE_BWD) || train);
       float dirv[3] = {0.f, 0.f, 0.f};
       float sigma_keep = 0.0f, dsp = 0.0f;
       (void)sigma_keep; (void)dsp;
 
-      if (MODE == MODE_FWD ? train : true) {           // previous tile's bulk stores must have read ACT/ENC
+      if ((MODE == MODE_BWD) || train) {               // previous tile's bulk stores must have read ACT/ENC
         if (row == 0) tc::bulk_wait_read0();
-        tc::named_bar_sync(1, 128);
+        tc::named_bar_sync(nb, 128);
       }
       // ---------------- prologue ----------------
       if (MODE == MODE_FWD) {
@@ -232,25 +256,26 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
             for (int k = 0; k < 3; ++k) { p[k] = a.pos[3 * grow + k]; dirv[k] = a.dir[3 * grow + k]; }
           }
         }
-        if (a.pos_L == 10) write_encoding<10, 8>(s_enc, row, p);
-        else write_encoding<0, 8>(s_enc, row, p);
+        if (a.pos_L == 10) write_encoding<10, 8, true>(s_enc, row, p);
+        else write_encoding<0, 8, true>(s_enc, row, p);
         tc::fence_proxy_async_smem();
-        if (train) {
-          tc::named_bar_sync(1, 128);
+        if (store_out) {
+          tc::named_bar_sync(nb, 128);
           if (row == 0) { tc::bulk_s2g(stash_tile + a.st_pe, s_enc, kEncBytes); tc::bulk_commit(); }
         }
       } else {
         // backward prologue: d(rgb2 pre-act), d(density pre-act), dR1 = d_rgb_pre . W2 masked by r1 > 0
         float4 d = make_float4(0.f, 0.f, 0.f, 0.f), o = make_float4(0.f, 0.5f, 0.5f, 0.5f);
+        uint4 r1m = make_uint4(0u, 0u, 0u, 0u);
         if (valid) {
           d = reinterpret_cast<const float4*>(a.d_sigma_rgb)[grow];
           o = reinterpret_cast<const float4*>(a.sigma_rgb)[grow];
         }
+        if (tile_ok) r1m = __ldg(reinterpret_cast<const uint4*>(stash_tile + a.st_mask + 10 * 4096) + row * 2);
         dsp = d.x * (1.0f - expf(-o.x));               // softplus'(x) = 1 - exp(-softplus(x))
         const float d0 = d.y * o.y * (1.0f - o.y), d1 = d.z * o.z * (1.0f - o.z), d2 = d.w * o.w * (1.0f - o.w);
-        reinterpret_cast<float4*>(dstash_tile + a.ds_sr)[row] = make_float4(dsp, d0, d1, d2);
+        if (tile_ok) reinterpret_cast<float4*>(dstash_tile + a.ds_sr)[row] = make_float4(dsp, d0, d1, d2);
         const float* w2 = a.small + a.sm_w2;
-        const uint4 r1m = __ldg(reinterpret_cast<const uint4*>(stash_tile + a.st_mask + 10 * 4096) + row * 2);
         const uint32_t r1w[4] = {r1m.x, r1m.y, r1m.z, r1m.w};
 #pragma unroll
         for (int kc = 0; kc < 16; ++kc) {
@@ -265,29 +290,29 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
                            tc::pack_bf16x2(g[2], g[3]), tc::pack_bf16x2(g[4], g[5]), tc::pack_bf16x2(g[6], g[7]));
         }
         tc::fence_proxy_async_smem();
-        tc::named_bar_sync(1, 128);
-        if (row == 0) { tc::bulk_s2g(dstash_tile + a.ds_y10, s_act, 16 * kKcoreBytes); tc::bulk_commit(); }
+        if ((MODE == MODE_BWD) || train) {
+          tc::named_bar_sync(nb, 128);
+          if (row == 0 && store_out) { tc::bulk_s2g(dstash_tile + a.ds_y10, s_act, 16 * kKcoreBytes); tc::bulk_commit(); }
+        }
       }
-      tc::mbar_arrive(bar_act);
+      tc::mbar_arrive(my_act);
 
       // ---------------- layer steps ----------------
       for (int si = 0; si < P.n_steps; ++si) {
         const Step& st = P.s[si];
         uint4 mk_a = make_uint4(0u, 0u, 0u, 0u), mk_b = make_uint4(0u, 0u, 0u, 0u);   // this row's ReLU mask words
-        if (MODE == MODE_BWD) {                        // fetched while the MMAs of this step still run
+        if (MODE == MODE_BWD && tile_ok) {             // fetched while the MMAs of this step still run
           const uint4* mp = reinterpret_cast<const uint4*>(stash_tile + st.mask_off) + row * 2;
           mk_a = __ldg(mp); mk_b = __ldg(mp + 1);
         }
-        tc::mbar_wait(bar_acc, acc_phase & 1u); ++acc_phase;
+        tc::mbar_wait(my_acc, acc_phase & 1u); ++acc_phase;
         tc::tc_fence_after();
-        const bool store_out = (MODE == MODE_BWD) || train;
-        if (store_out) {                               // an earlier bulk store may still be reading ACT/ENC
+        if ((MODE == MODE_BWD) || train) {             // an earlier bulk store may still be reading ACT/ENC
           if (row == 0) tc::bulk_wait_read0();
-          tc::named_bar_sync(1, 128);
+          tc::named_bar_sync(nb, 128);
         }
         const int n_chunks = st.n >> 5;
         if (MODE == MODE_FWD) {
-          const float* bias = a.small + st.bias_off;
           float dens = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
           const bool is_rgb = (st.flags & EPI_RGB) != 0;
           const bool is_dens = (st.flags & EPI_DENSITY) != 0;
@@ -295,51 +320,48 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
             uint32_t v[32];
             tc::tmem_ld32(t_lane + ch * 32, v);
             tc::tmem_wait_ld();
-            float y[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ch * 32 + j));
-              y[j + 0] = fmaxf(__uint_as_float(v[j + 0]) + b4.x, 0.0f);
-              y[j + 1] = fmaxf(__uint_as_float(v[j + 1]) + b4.y, 0.0f);
-              y[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + b4.z, 0.0f);
-              y[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + b4.w, 0.0f);
-            }
-            if (is_dens) {
+            if (is_dens) {                             // density head on the fp32 ReLU output (NeRFModel.py:192)
               const float* wd = a.small + a.sm_wd + ch * 32;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 w4 = __ldg(reinterpret_cast<const float4*>(wd + j));
-                dens = fmaf(y[j], w4.x, dens); dens = fmaf(y[j + 1], w4.y, dens);
-                dens = fmaf(y[j + 2], w4.z, dens); dens = fmaf(y[j + 3], w4.w, dens);
+                dens = fmaf(fmaxf(__uint_as_float(v[j]), 0.f), w4.x, dens);
+                dens = fmaf(fmaxf(__uint_as_float(v[j + 1]), 0.f), w4.y, dens);
+                dens = fmaf(fmaxf(__uint_as_float(v[j + 2]), 0.f), w4.z, dens);
+                dens = fmaf(fmaxf(__uint_as_float(v[j + 3]), 0.f), w4.w, dens);
               }
             }
-            if (is_rgb) {
+            if (is_rgb) {                              // rgb_layer2 on the fp32 ReLU output (NeRFModel.py:199-200)
               const float* w2 = a.small + a.sm_w2 + ch * 32;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 wa = __ldg(reinterpret_cast<const float4*>(w2 + j));
                 const float4 wb = __ldg(reinterpret_cast<const float4*>(w2 + 128 + j));
                 const float4 wc = __ldg(reinterpret_cast<const float4*>(w2 + 256 + j));
-                c0 = fmaf(y[j], wa.x, c0); c0 = fmaf(y[j + 1], wa.y, c0); c0 = fmaf(y[j + 2], wa.z, c0); c0 = fmaf(y[j + 3], wa.w, c0);
-                c1 = fmaf(y[j], wb.x, c1); c1 = fmaf(y[j + 1], wb.y, c1); c1 = fmaf(y[j + 2], wb.z, c1); c1 = fmaf(y[j + 3], wb.w, c1);
-                c2 = fmaf(y[j], wc.x, c2); c2 = fmaf(y[j + 1], wc.y, c2); c2 = fmaf(y[j + 2], wc.z, c2); c2 = fmaf(y[j + 3], wc.w, c2);
+                const float y0 = fmaxf(__uint_as_float(v[j]), 0.f), y1 = fmaxf(__uint_as_float(v[j + 1]), 0.f);
+                const float y2 = fmaxf(__uint_as_float(v[j + 2]), 0.f), y3 = fmaxf(__uint_as_float(v[j + 3]), 0.f);
+                c0 = fmaf(y0, wa.x, c0); c0 = fmaf(y1, wa.y, c0); c0 = fmaf(y2, wa.z, c0); c0 = fmaf(y3, wa.w, c0);
+                c1 = fmaf(y0, wb.x, c1); c1 = fmaf(y1, wb.y, c1); c1 = fmaf(y2, wb.z, c1); c1 = fmaf(y3, wb.w, c1);
+                c2 = fmaf(y0, wc.x, c2); c2 = fmaf(y1, wc.y, c2); c2 = fmaf(y2, wc.z, c2); c2 = fmaf(y3, wc.w, c2);
               }
             }
             if (train) {
               uint32_t word = 0u;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) word |= (y[j] > 0.0f) ? (1u << j) : 0u;
+              for (int j = 0; j < 32; ++j) word |= (__uint_as_float(v[j]) > 0.0f) ? (1u << j) : 0u;
               put8(mk_a, mk_b, ch, word);
             }
-            if (!is_rgb || train) {
+            if (!is_rgb || train) {                    // ReLU + bf16 pack in one cvt; the bias came through the MMA
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 tc::st_shared_v4(s_act + (ch * 4 + q) * kKcoreBytes + row * 16,
-                                 tc::pack_bf16x2(y[8 * q + 0], y[8 * q + 1]), tc::pack_bf16x2(y[8 * q + 2], y[8 * q + 3]),
-                                 tc::pack_bf16x2(y[8 * q + 4], y[8 * q + 5]), tc::pack_bf16x2(y[8 * q + 6], y[8 * q + 7]));
+                                 tc::pack_bf16x2_relu(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
+                                 tc::pack_bf16x2_relu(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+                                 tc::pack_bf16x2_relu(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
+                                 tc::pack_bf16x2_relu(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
             }
           }
-          if (train) {
+          if (store_out) {
             uint4* mp = reinterpret_cast<uint4*>(stash_tile + st.mask_off) + row * 2;
             mp[0] = mk_a; mp[1] = mk_b;
           }
@@ -350,8 +372,8 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
                 make_float4(sigma_keep, sigmoid_f(c0 + __ldg(b2)), sigmoid_f(c1 + __ldg(b2 + 1)), sigmoid_f(c2 + __ldg(b2 + 2)));
           }
           if (st.flags & EPI_WRITE_DIR) {
-            if (a.dir_L == 4) write_encoding<4, 4>(s_enc, row, dirv);
-            else write_encoding<0, 4>(s_enc, row, dirv);
+            if (a.dir_L == 4) write_encoding<4, 4, false>(s_enc, row, dirv);
+            else write_encoding<0, 4, false>(s_enc, row, dirv);
           }
         } else {
           const bool add_sigma = (st.flags & EPI_BWD_SIGMA) != 0;
@@ -383,23 +405,23 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
         }
         tc::tc_fence_before();                         // TMEM reads retired before the next MMA overwrites
         tc::fence_proxy_async_smem();                  // ACT/ENC writes visible to UMMA / bulk stores
-        if (store_out) {
-          tc::named_bar_sync(1, 128);
-          if (row == 0) {
+        if ((MODE == MODE_BWD) || train) {
+          tc::named_bar_sync(nb, 128);
+          if (row == 0 && store_out) {
             uint8_t* dst = (MODE == MODE_FWD ? stash_tile : dstash_tile) + st.stash_off;
             tc::bulk_s2g(dst, s_act, (uint32_t)st.n * 256u);          // n channels x 128 rows x 2 B
             if (MODE == MODE_FWD && (st.flags & EPI_WRITE_DIR)) tc::bulk_s2g(stash_tile + a.st_de, s_enc, 4 * kKcoreBytes);
             tc::bulk_commit();
           }
         }
-        if (!(st.flags & EPI_LAST)) tc::mbar_arrive(bar_act);
+        if (!(st.flags & EPI_LAST)) tc::mbar_arrive(my_act);
       }
     }
     if (row == 0) tc::bulk_wait0();
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem_base, 256);
+  if (warp == 8) tc::tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -407,7 +429,7 @@ __global__ void __launch_bounds__(192, 2) mlp_fused_kernel(const __grid_constant
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_images_kernel(const float* __restrict__ params, Program prog, uint8_t* __restrict__ packed) {
   const Step st = prog.s[blockIdx.y];
-  const int total_k = (st.act_ksteps + st.enc_ksteps) * 16;
+  const int total_k = (st.act_ksteps + st.enc_ksteps + st.bias_kstep) * 16;
   const int n_elems = total_k * st.n;
   __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(packed + st.w_off);
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_elems; idx += gridDim.x * blockDim.x) {
@@ -421,9 +443,15 @@ __global__ void pack_images_kernel(const float* __restrict__ params, Program pro
       if (st.p_transpose) {
         if (kk < st.act_cols) v = params[st.p_w + (int64_t)kk * st.p_in + n];
       } else {
-        const int act_k = st.act_ksteps * 16;
+        const int act_k = st.act_ksteps * 16, enc_k = st.enc_ksteps * 16;
         if (kk < act_k) { if (kk < st.act_cols) v = params[st.p_w + (int64_t)n * st.p_in + kk]; }
-        else { const int e = kk - act_k; if (e < st.enc_cols) v = params[st.p_w + (int64_t)n * st.p_in + st.enc_col0 + e]; }
+        else if (kk < act_k + enc_k) {
+          const int e = kk - act_k;
+          if (e < st.enc_cols) v = params[st.p_w + (int64_t)n * st.p_in + st.enc_col0 + e];
+          else if (st.bias_in_enc && e == 63) v = params[st.p_bias + n];       // pairs with the constant-1 channel
+        } else if ((kk - act_k - enc_k) == 15 && st.p_bias >= 0) {
+          v = params[st.p_bias + n];                                           // bias k-step: ENC channel 63
+        }
       }
     }
     img[idx] = __float2bfloat16_rn(v);
@@ -431,18 +459,11 @@ __global__ void pack_images_kernel(const float* __restrict__ params, Program pro
 }
 
 struct PackSmallArgs {
-  int32_t n_bias;                    // forward steps
-  int32_t b_src[kMaxSteps];          // float offsets of the step biases in the flat vector
-  int32_t b_n[kMaxSteps];
   int32_t wd_src, bd_src, w2_src, b2_src;
   int32_t sm_wd, sm_bd, sm_w2, sm_b2;
 };
 __global__ void pack_small_kernel(const float* __restrict__ params, PackSmallArgs p, float* __restrict__ small) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < p.n_bias * 256) {
-    const int s = i >> 8, c = i & 255;
-    small[i] = c < p.b_n[s] ? params[p.b_src[s] + c] : 0.0f;
-  }
   if (i < 256) small[p.sm_wd + i] = params[p.wd_src + i];
   if (i < 384) small[p.sm_w2 + i] = params[p.w2_src + i];
   if (i < 3) small[p.sm_b2 + i] = params[p.b2_src + i];

@@ -21,7 +21,7 @@ constexpr int kNumLinear = 13;          // fc1, fc_layers x4, skip, fc_layers2 x
 constexpr int kKcoreBytes = 2048;       // 128 rows x 16 B
 constexpr int kActBytes = 32 * kKcoreBytes;   // 256 channels = 64 KB
 constexpr int kEncBytes = 8 * kKcoreBytes;    // 64 channels  = 16 KB
-constexpr int kRingSlots = 3;
+constexpr int kRingSlots = 8;                 // = one half of a K=256 layer: both resident tiles share every slab
 constexpr int kRingSlotBytes = 256 * 32;      // one K=16 step of an N=256 layer = 8 KB
 
 // epilogue flags
@@ -50,7 +50,9 @@ struct Step {
   int32_t enc_col0;     // kk >= 16*act_ksteps maps to source column enc_col0 + (kk - 16*act_ksteps)
   int32_t enc_cols;     //   valid if (kk - 16*act_ksteps) < enc_cols
   int32_t p_rows;       // valid rows n
-  int32_t pad_;
+  int32_t p_bias;       // float offset of the bias in the flat vector (-1: none); it rides on the MMA:
+  int32_t bias_kstep;   //   1: one extra K=16 step reads ENC k-step 3, whose channel 63 is the constant 1.0
+  int32_t bias_in_enc;  //   1: the ENC k-steps of this step already cover channel 63 (PE layers)
 };
 
 struct Program {
@@ -87,7 +89,7 @@ struct ModelLayout {
   int32_t small_off;                 // byte offset of the fp32 table
   int32_t small_floats;
   int32_t packed_bytes;
-  // small table (float offsets): biases of the 11 MMA layers at 256*i, then heads
+  // small fp32 table (float offsets): the two heads that run on CUDA cores (layer biases ride on the MMA)
   int32_t sm_wd, sm_bd, sm_w2, sm_b2;
   // per-tile stash (bytes): PE, DE, H0..H9 (h0..h8, feature), R1, then 11 ReLU bit masks
   // ([row][8 x u32] = 4 KB each; bit c of a row = output channel c of that layer was > 0)
@@ -137,8 +139,8 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
 
   auto add = [](Program& p, Step st) {
     st.w_off = p.image_bytes;
-    p.image_bytes += (st.act_ksteps + st.enc_ksteps) * st.n * 32;
-    p.total_ksteps += st.act_ksteps + st.enc_ksteps;
+    p.image_bytes += (st.act_ksteps + st.enc_ksteps + st.bias_kstep) * st.n * 32;
+    p.total_ksteps += st.act_ksteps + st.enc_ksteps + st.bias_kstep;
     p.s[p.n_steps++] = st;
   };
   // ---- forward program ------------------------------------------------------------------
@@ -152,6 +154,9 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
     st.p_w = m.w_off[lin]; st.p_in = m.in_f[lin]; st.p_transpose = 0;
     st.act_cols = act_ks ? 256 : 0; st.enc_col0 = enc_col0; st.enc_cols = enc_cols;
     st.p_rows = m.out_f[lin];
+    st.p_bias = m.b_off[lin];
+    st.bias_in_enc = (enc_ks == 4 && enc_col0 + 63 >= st.p_in) ? 1 : 0;   // PE tile (64 ch): channel 63 is free
+    st.bias_kstep = st.bias_in_enc ? 0 : 1;
     return st;
   };
   Program& f = m.fwd;
@@ -172,6 +177,7 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
     st.p_w = m.w_off[lin]; st.p_in = m.in_f[lin]; st.p_transpose = 1;
     st.act_cols = m.out_f[lin]; st.enc_col0 = 0; st.enc_cols = 0;
     st.p_rows = 256;                    // only the first 256 input columns carry gradient
+    st.p_bias = -1; st.bias_kstep = 0; st.bias_in_enc = 0;
     return st;
   };
   Program& b = m.bwd;
@@ -191,7 +197,7 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
   // packed buffer
   const int fwd_bytes = f.image_bytes, bwd_bytes = b.image_bytes;
   for (int i = 0; i < b.n_steps; ++i) b.s[i].w_off += fwd_bytes;
-  m.sm_wd = 256 * 11; m.sm_bd = m.sm_wd + 256; m.sm_w2 = m.sm_bd + 4; m.sm_b2 = m.sm_w2 + 384;
+  m.sm_wd = 0; m.sm_bd = m.sm_wd + 256; m.sm_w2 = m.sm_bd + 4; m.sm_b2 = m.sm_w2 + 384;
   m.small_floats = m.sm_b2 + 4;
   m.small_off = fwd_bytes + bwd_bytes;
   m.packed_bytes = m.small_off + m.small_floats * 4;
