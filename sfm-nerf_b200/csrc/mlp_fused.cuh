@@ -8,13 +8,14 @@
 // One CTA per SM keeps TWO 128-row tiles resident (2 x 64 KB activation tiles in shared memory,
 // 2 x 256 TMEM columns).  Weights stream from L2 through an 8-slot ring of K=16 slabs (8 KB); every
 // slab is consumed by BOTH tiles before its slot is recycled, so weight traffic per MMA is halved and
-// 64 KB of loads are always in flight.  Within a layer the MMA issuer alternates between the tiles in
-// groups of 8 k-steps (A: k0-7, B: k0-7, A: k8-15, B: k8-15): while one tile's epilogue runs on its
-// warpgroup, the tensor pipe works on the other tile.
+// 64 KB of loads are always in flight.  Each tile has its own MMA-issuing warp; the two run at most
+// one ring depth (8 k-steps) apart, so while one tile's epilogue runs on its warpgroup the tensor
+// pipe works on the other tile.
 //   warps 0-3 / 4-7 : epilogue of tile slot 0 / 1 (thread = row = TMEM lane):
 //                     TMEM -> regs -> ReLU+bf16 pack (one cvt) -> next layer's A tile, in place
 //   warp 8          : weight loader (1-D bulk copies into the ring)
-//   warp 9          : MMA issuer (one thread), tcgen05.mma kind::f16 128xNx16, accumulators in TMEM
+//   warps 9 / 10    : MMA issuer of tile slot 0 / 1 (one elected lane), tcgen05.mma kind::f16
+//                     128xNx16, accumulators in TMEM
 // Biases ride on the MMA: channel 63 of the encoding tile is the constant 1.0 and the packed weight
 // image carries the bias in that K column, so the epilogue does no bias loads or adds.
 #pragma once
@@ -26,8 +27,7 @@ namespace nerf {
 
 constexpr int MODE_FWD = 0;
 constexpr int MODE_BWD = 1;
-constexpr int kMlpThreads = 320;
-constexpr int kGroupKsteps = 8;     // k-steps issued for one tile before switching to the other
+constexpr int kMlpThreads = 352;    // 8 epilogue warps + loader + 2 MMA issuers
 
 struct MlpArgs {
   const uint8_t* packed;     // weight images
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kRingSlots; ++i) { tc::mbar_init(bar_full + 8 * i, 1); tc::mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < kRingSlots; ++i) { tc::mbar_init(bar_full + 8 * i, 1); tc::mbar_init(bar_empty + 8 * i, 2); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(bar_acc + 8 * i, 1); tc::mbar_init(bar_act + 8 * i, 128); }
     tc::fence_mbar_init();
   }
@@ -176,42 +176,49 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t it = 0, act_phase = 0;
-      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        for (int si = 0; si < P.n_steps; ++si, ++act_phase) {
-          const Step& st = P.s[si];
-          const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
-          const uint32_t idesc = tc::umma_idesc_bf16(128, st.n, 0, 0);
-          for (int g0 = 0; g0 < total; g0 += kGroupKsteps) {
-            const int g1 = (g0 + kGroupKsteps < total) ? g0 + kGroupKsteps : total;
-            for (int slot = 0; slot < 2; ++slot) {
-              const uint32_t s_act = s_base + MlpSmem::kAct + slot * kActBytes;
-              const uint32_t s_enc = s_base + MlpSmem::kEnc + slot * kEncBytes;
-              if (g0 == 0) { tc::mbar_wait(bar_act + 8 * slot, act_phase & 1u); tc::tc_fence_after(); }
-              for (int k = g0; k < g1; ++k) {
-                const uint32_t j = it + (uint32_t)(k - g0);
-                const uint32_t rs = j % kRingSlots;
-                if (slot == 0) { tc::mbar_wait(bar_full + 8 * rs, (j / kRingSlots) & 1u); tc::tc_fence_after(); }
-                uint32_t a_addr;
-                if (k < st.act_ksteps) a_addr = s_act + k * 2 * kKcoreBytes;
-                else if (k < st.act_ksteps + st.enc_ksteps) a_addr = s_enc + (k - st.act_ksteps) * 2 * kKcoreBytes;
-                else a_addr = s_enc + 3 * 2 * kKcoreBytes;                     // the "ones" k-step (channel 63 == 1.0)
-                const uint64_t adesc = tc::umma_smem_desc(a_addr, kKcoreBytes, 128);
-                const uint64_t bdesc = tc::umma_smem_desc(s_ring + rs * kRingSlotBytes, (uint32_t)st.n * 16u, 128);
-                tc::umma_bf16(tmem_base + 256 * slot, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
-                if (slot == 1) tc::umma_commit(bar_empty + 8 * rs);            // both tiles have used this slab
-              }
-              if (g1 == total) tc::umma_commit(bar_acc + 8 * slot);
-            }
-            it += (uint32_t)(g1 - g0);
+  } else if (warp >= 9) {
+    // ===================== MMA issuers: warp 9 -> tile slot 0, warp 10 -> tile slot 1 =====================
+    // Each warp runs its loop with warp-uniform control flow (all lanes poll the barriers) and one
+    // elected lane issues the tcgen05 instructions.  The two warps share every weight slab: a ring
+    // slot is recycled once BOTH have committed their MMA on it (empty barriers count 2), which also
+    // bounds the skew between the two tiles to the ring depth.
+    const int slot = warp - 9;
+    const uint32_t s_act = s_base + MlpSmem::kAct + slot * kActBytes;
+    const uint32_t s_enc = s_base + MlpSmem::kEnc + slot * kEncBytes;
+    const uint32_t d_tmem = tmem_base + 256 * slot;
+    const uint32_t my_acc = bar_acc + 8 * slot, my_act = bar_act + 8 * slot;
+    const uint64_t desc_hi = (uint64_t)(((128u >> 4) & 0x3FFFu) | (1u << 14)) << 32;      // SBO = 128 B, version 1
+    const uint32_t a_lbo = ((uint32_t)kKcoreBytes >> 4) << 16;                              // LBO = 2048 B
+    const uint32_t act_lo = a_lbo | ((s_act & 0x3FFFFu) >> 4), enc_lo = a_lbo | ((s_enc & 0x3FFFFu) >> 4);
+    const uint32_t ring_lo = (s_ring & 0x3FFFFu) >> 4;
+    uint32_t it = 0, act_phase = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (int si = 0; si < P.n_steps; ++si, ++act_phase) {
+        const int n = P.s[si].n, act_ks = P.s[si].act_ksteps, enc_ks = P.s[si].enc_ksteps;
+        const int total = act_ks + enc_ks + P.s[si].bias_kstep;
+        const uint32_t idesc = tc::umma_idesc_bf16(128, n, 0, 0);
+        const uint32_t b_lo = ((((uint32_t)n * 16u) >> 4) << 16) | ring_lo;
+        tc::mbar_wait(my_act, act_phase & 1u);
+        tc::tc_fence_after();
+        for (int k = 0; k < total; ++k) {
+          const uint32_t j = it + (uint32_t)k;
+          const uint32_t rs = j & (kRingSlots - 1);
+          tc::mbar_wait(bar_full + 8 * rs, (j >> 3) & 1u);
+          tc::tc_fence_after();
+          const int e = k - act_ks;                                           // >= enc_ks: the "ones" k-step (ENC k-step 3)
+          const uint32_t a_lo = (e < 0) ? act_lo + (uint32_t)k * ((2 * kKcoreBytes) >> 4)
+                                        : enc_lo + (uint32_t)(e < enc_ks ? e : 3) * ((2 * kKcoreBytes) >> 4);
+          if (tc::elect_one()) {
+            tc::umma_bf16(d_tmem, desc_hi | a_lo, desc_hi | (b_lo + rs * (kRingSlotBytes >> 4)), idesc, k > 0 ? 1u : 0u);
+            tc::umma_commit(bar_empty + 8 * rs);
           }
+          __syncwarp();
         }
+        if (tc::elect_one()) tc::umma_commit(my_acc);
+        __syncwarp();
+        it += (uint32_t)total;
       }
     }
-    __syncwarp();
   } else {
     // ===================== epilogue warpgroups (thread = row) =====================
     const int slot = warp >> 2;                        // tile slot of this warpgroup

@@ -178,7 +178,7 @@ def test_mlp_forward_hidden_activations(pkg, orc, model_pe, sd_pe256, golden):
         report.append(("pe_raw", float((pe[:, :3].cpu() - pe_ref[rows][:, :3]).abs().max())))
         report.append(("pe", float((pe[:, 3:63].cpu() - pe_ref[rows][:, 3:]).abs().max())))
         report.append(("de", float((de[:, :27].cpu() - de_ref[rows]).abs().max())))
-        assert float(pe[:, 63].abs().max()) == 0.0
+        assert float((pe[:, 63] - 1.0).abs().max()) == 0.0          # the constant-1 channel that carries the biases
         for i in range(10):
             h = _decode_block(blob[off:off + 65536], 256)[:nrow]; off += 65536
             ref = hidden[i][rows]
