@@ -158,6 +158,10 @@ int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
  * Diagnostics only: synchronises the device and is the one entry point that allocates.
  * ------------------------------------------------------------------------------------- */
 int nerf_selftest_umma(int variant, float* result_host);
+/* Diagnostics: when device_buffer != NULL, CTA 0 of the fused MLP kernels writes clock64 stamps
+ * [pair][step 0..11][tile slot 0..1][4] = (MMA issue start, MMA issue end, accumulator ready seen by
+ * the epilogue, next-layer release) into it (int64; 8 pairs fit in 8*12*2*4 entries).  NULL disables. */
+int nerf_debug_trace(void* device_buffer);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "nerf_mse_loss": (_I, [_P, _P, _L, _F, _P, _P, _P]),
     "nerf_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
     "nerf_selftest_umma": (_I, [_I, _P]),
+    "nerf_debug_trace": (_I, [_P]),
 }
 
 _lib = None

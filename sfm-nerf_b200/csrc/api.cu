@@ -2,6 +2,7 @@
 // geometry and nothing else: every entry point enqueues sm_100a kernels on the caller's stream.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "composite.cuh"
@@ -17,6 +18,7 @@ namespace {
 
 struct DeviceInfo { int device = -1; int sms = 0; int cc_major = 0; bool attrs_set = false; };
 thread_local DeviceInfo g_dev;
+long long* g_trace = nullptr;      // diagnostics only (nerf_debug_trace)
 
 int device_info(DeviceInfo** out) {
   int dev = 0;
@@ -59,6 +61,8 @@ void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t
   a.n_rows = n_rows;
   a.n_tiles = (int)((n_rows + 127) / 128);
   a.stash_tile_bytes = m.stash_tile_bytes; a.dstash_tile_bytes = m.dstash_tile_bytes;
+  a.trace = g_trace;
+  { const char* e = getenv("NERF_EXP"); a.exp_flags = e ? atoi(e) : 0; }
   a.st_pe = m.st_pe; a.st_de = m.st_de; a.st_r1 = m.st_r1; a.st_mask = m.st_mask; a.ds_y10 = m.ds_y[10]; a.ds_sr = m.ds_sr;
 }
 
@@ -383,6 +387,12 @@ int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
   adam_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                     eps, (float)bc1, (float)sqrt(bc2), grad_scale);
   NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+// ------------------------------------------------------------------------------------ diagnostics
+int nerf_debug_trace(void* device_buffer) {
+  g_trace = static_cast<long long*>(device_buffer);
   return NERF_OK;
 }
 

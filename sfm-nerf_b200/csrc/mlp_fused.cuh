@@ -47,6 +47,8 @@ struct MlpArgs {
   uint8_t* dstash;           // bwd: written
   int32_t stash_tile_bytes, dstash_tile_bytes;
   int32_t st_pe, st_de, st_r1, st_mask, ds_y10, ds_sr;
+  int32_t exp_flags;         // diagnostics (NERF_EXP env): 1 = skip stash bulk stores, 2 = skip mask generation
+  long long* trace;          // diagnostics: per-(pair,step,slot) clock64 stamps of CTA 0 (or null)
   Program prog;
 };
 
@@ -55,8 +57,10 @@ struct MlpSmem {
   static constexpr int kEnc = kAct + 2 * kActBytes;                // 2 x 16 KB
   static constexpr int kRing = kEnc + 2 * kEncBytes;               // 8 x 8 KB
   static constexpr int kBars = kRing + kRingSlots * kRingSlotBytes;
-  // barriers (8 B each): full[8] @0, empty[8] @64, acc_full[2] @128, act_ready[2] @144; tmem ptr @160
-  static constexpr int kTotal = kBars + 256;
+  // barriers (8 B each): full[8] @0, empty[8] @64, acc_full[2] @128, act_ready[2] @144, skew @160; tmem ptr @176
+  static constexpr int kHead = kBars + 256;                        // fp32 head tables (w_d, b_d, W2, b2): 648 floats
+  static constexpr int kHeadFloats = 648;
+  static constexpr int kTotal = kHead + kHeadFloats * 4;
 };
 static_assert(MlpSmem::kTotal <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
@@ -87,7 +91,7 @@ __device__ __forceinline__ void pe_sincos(const TurnsF& t, int level, float& s, 
 // 8*NKC channels, stored at enc + kcore*2048 + row*16.  ONE: the last channel is the constant 1.0
 // (the K column the packed weight images pair with the bias).
 template <int L, int NKC, bool ONE>
-__device__ __forceinline__ void write_encoding(uint32_t enc_smem, int row, const float v[3]) {
+__device__ __forceinline__ void write_encoding(uint32_t enc_smem, int row, const float v[3], uint8_t* gdst) {
   float e[NKC * 8];
 #pragma unroll
   for (int i = 0; i < NKC * 8; ++i) e[i] = 0.0f;
@@ -110,9 +114,10 @@ __device__ __forceinline__ void write_encoding(uint32_t enc_smem, int row, const
   if (ONE) e[NKC * 8 - 1] = 1.0f;
 #pragma unroll
   for (int kc = 0; kc < NKC; ++kc) {
-    tc::st_shared_v4(enc_smem + kc * kKcoreBytes + row * 16,
-                     tc::pack_bf16x2(e[8 * kc + 0], e[8 * kc + 1]), tc::pack_bf16x2(e[8 * kc + 2], e[8 * kc + 3]),
-                     tc::pack_bf16x2(e[8 * kc + 4], e[8 * kc + 5]), tc::pack_bf16x2(e[8 * kc + 6], e[8 * kc + 7]));
+    const uint4 p = make_uint4(tc::pack_bf16x2(e[8 * kc + 0], e[8 * kc + 1]), tc::pack_bf16x2(e[8 * kc + 2], e[8 * kc + 3]),
+                               tc::pack_bf16x2(e[8 * kc + 4], e[8 * kc + 5]), tc::pack_bf16x2(e[8 * kc + 6], e[8 * kc + 7]));
+    tc::st_shared_v4(enc_smem + kc * kKcoreBytes + row * 16, p.x, p.y, p.z, p.w);
+    if (gdst != nullptr) reinterpret_cast<uint4*>(gdst + kc * kKcoreBytes)[row] = p;   // training stash copy
   }
 }
 
@@ -140,12 +145,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
   const uint32_t s_ring = s_base + MlpSmem::kRing;
   const uint32_t s_bar = s_base + MlpSmem::kBars;
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 64, bar_acc = s_bar + 128, bar_act = s_bar + 144;
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kBars + 160);
+  const uint32_t bar_skew = s_bar + 160;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kBars + 176);
+  // head weights live in shared memory: with 224 KB of it carved out there is no L1 left to cache them
+  float* sm = reinterpret_cast<float*>(smem + MlpSmem::kHead);
+  for (int i = threadIdx.x; i < MlpSmem::kHeadFloats; i += blockDim.x) sm[i] = a.small[i];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingSlots; ++i) { tc::mbar_init(bar_full + 8 * i, 1); tc::mbar_init(bar_empty + 8 * i, 2); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(bar_acc + 8 * i, 1); tc::mbar_init(bar_act + 8 * i, 128); }
+    tc::mbar_init(bar_skew, 1);
     tc::fence_mbar_init();
   }
   if (warp == 8) tc::tmem_alloc(tc::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
@@ -191,8 +201,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
     const uint32_t a_lbo = ((uint32_t)kKcoreBytes >> 4) << 16;                              // LBO = 2048 B
     const uint32_t act_lo = a_lbo | ((s_act & 0x3FFFFu) >> 4), enc_lo = a_lbo | ((s_enc & 0x3FFFFu) >> 4);
     const uint32_t ring_lo = (s_ring & 0x3FFFFu) >> 4;
-    uint32_t it = 0, act_phase = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    uint32_t it = 0, act_phase = 0, pair_phase = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pair_phase) {
       for (int si = 0; si < P.n_steps; ++si, ++act_phase) {
         const int n = P.s[si].n, act_ks = P.s[si].act_ksteps, enc_ks = P.s[si].enc_ksteps;
         const int total = act_ks + enc_ks + P.s[si].bias_kstep;
@@ -200,6 +210,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
         const uint32_t b_lo = ((((uint32_t)n * 16u) >> 4) << 16) | ring_lo;
         tc::mbar_wait(my_act, act_phase & 1u);
         tc::tc_fence_after();
+        long long* tr = (a.trace != nullptr && blockIdx.x == 0 && lane == 0)
+                            ? a.trace + ((size_t)((pair / gridDim.x) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
+        if (tr) tr[0] = clock64();
+        // De-synchronise the two tiles: tile 1 enters the first deep layer only when tile 0 is one ring
+        // depth (8 k-steps) into it.  The offset then persists (the shared ring bounds it from above), so
+        // one tile's epilogue runs under the other tile's MMAs instead of both idling the tensor pipe.
+        if (si == 1 && slot == 1) tc::mbar_wait(bar_skew, pair_phase & 1u);
         for (int k = 0; k < total; ++k) {
           const uint32_t j = it + (uint32_t)k;
           const uint32_t rs = j & (kRingSlots - 1);
@@ -211,11 +228,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
           if (tc::elect_one()) {
             tc::umma_bf16(d_tmem, desc_hi | a_lo, desc_hi | (b_lo + rs * (kRingSlotBytes >> 4)), idesc, k > 0 ? 1u : 0u);
             tc::umma_commit(bar_empty + 8 * rs);
+            if (si == 1 && slot == 0 && k == kRingSlots - 1) tc::mbar_arrive(bar_skew);
           }
           __syncwarp();
         }
         if (tc::elect_one()) tc::umma_commit(my_acc);
         __syncwarp();
+        if (tr) tr[1] = clock64();
         it += (uint32_t)total;
       }
     }
@@ -227,7 +246,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
     const uint32_t s_enc = s_base + MlpSmem::kEnc + slot * kEncBytes;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256 * slot;
     const uint32_t my_acc = bar_acc + 8 * slot, my_act = bar_act + 8 * slot;
-    const uint32_t nb = 1 + slot;                      // named barrier of this warpgroup
     const bool train = (a.stash != nullptr);
     uint32_t acc_phase = 0;
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -242,10 +260,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
       float sigma_keep = 0.0f, dsp = 0.0f;
       (void)sigma_keep; (void)dsp;
 
-      if ((MODE == MODE_BWD) || train) {               // previous tile's bulk stores must have read ACT/ENC
-        if (row == 0) tc::bulk_wait_read0();
-        tc::named_bar_sync(nb, 128);
-      }
       // ---------------- prologue ----------------
       if (MODE == MODE_FWD) {
         float p[3] = {0.f, 0.f, 0.f};
@@ -263,13 +277,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
             for (int k = 0; k < 3; ++k) { p[k] = a.pos[3 * grow + k]; dirv[k] = a.dir[3 * grow + k]; }
           }
         }
-        if (a.pos_L == 10) write_encoding<10, 8, true>(s_enc, row, p);
-        else write_encoding<0, 8, true>(s_enc, row, p);
-        tc::fence_proxy_async_smem();
-        if (store_out) {
-          tc::named_bar_sync(nb, 128);
-          if (row == 0) { tc::bulk_s2g(stash_tile + a.st_pe, s_enc, kEncBytes); tc::bulk_commit(); }
-        }
+        uint8_t* g_pe = store_out ? stash_tile + a.st_pe : nullptr;
+        if (a.pos_L == 10) write_encoding<10, 8, true>(s_enc, row, p, g_pe);
+        else write_encoding<0, 8, true>(s_enc, row, p, g_pe);
       } else {
         // backward prologue: d(rgb2 pre-act), d(density pre-act), dR1 = d_rgb_pre . W2 masked by r1 > 0
         float4 d = make_float4(0.f, 0.f, 0.f, 0.f), o = make_float4(0.f, 0.5f, 0.5f, 0.5f);
@@ -282,7 +292,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
         dsp = d.x * (1.0f - expf(-o.x));               // softplus'(x) = 1 - exp(-softplus(x))
         const float d0 = d.y * o.y * (1.0f - o.y), d1 = d.z * o.z * (1.0f - o.z), d2 = d.w * o.w * (1.0f - o.w);
         if (tile_ok) reinterpret_cast<float4*>(dstash_tile + a.ds_sr)[row] = make_float4(dsp, d0, d1, d2);
-        const float* w2 = a.small + a.sm_w2;
+        const float* w2 = sm + a.sm_w2;
         const uint32_t r1w[4] = {r1m.x, r1m.y, r1m.z, r1m.w};
 #pragma unroll
         for (int kc = 0; kc < 16; ++kc) {
@@ -290,18 +300,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int c = kc * 8 + j;
-            const float v = d0 * __ldg(w2 + c) + d1 * __ldg(w2 + 128 + c) + d2 * __ldg(w2 + 256 + c);
-            g[j] = ((r1w[kc >> 2] >> ((kc & 3) * 8 + j)) & 1u) ? v : 0.0f;
+            const float v = d0 * w2[c] + d1 * w2[128 + c] + d2 * w2[256 + c];
+            g[j] = ((r1w[kc >> 2] >> (((((kc & 3) * 8 + j)) >> 1) + 16 * (j & 1))) & 1u) ? v : 0.0f;
           }
-          tc::st_shared_v4(s_act + kc * kKcoreBytes + row * 16, tc::pack_bf16x2(g[0], g[1]),
-                           tc::pack_bf16x2(g[2], g[3]), tc::pack_bf16x2(g[4], g[5]), tc::pack_bf16x2(g[6], g[7]));
-        }
-        tc::fence_proxy_async_smem();
-        if ((MODE == MODE_BWD) || train) {
-          tc::named_bar_sync(nb, 128);
-          if (row == 0 && store_out) { tc::bulk_s2g(dstash_tile + a.ds_y10, s_act, 16 * kKcoreBytes); tc::bulk_commit(); }
+          const uint4 pk = make_uint4(tc::pack_bf16x2(g[0], g[1]), tc::pack_bf16x2(g[2], g[3]),
+                                      tc::pack_bf16x2(g[4], g[5]), tc::pack_bf16x2(g[6], g[7]));
+          tc::st_shared_v4(s_act + kc * kKcoreBytes + row * 16, pk.x, pk.y, pk.z, pk.w);
+          if (store_out) reinterpret_cast<uint4*>(dstash_tile + a.ds_y10 + kc * kKcoreBytes)[row] = pk;
         }
       }
+      tc::fence_proxy_async_smem();
       tc::mbar_arrive(my_act);
 
       // ---------------- layer steps ----------------
@@ -314,117 +322,147 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
         }
         tc::mbar_wait(my_acc, acc_phase & 1u); ++acc_phase;
         tc::tc_fence_after();
-        if ((MODE == MODE_BWD) || train) {             // an earlier bulk store may still be reading ACT/ENC
-          if (row == 0) tc::bulk_wait_read0();
-          tc::named_bar_sync(nb, 128);
-        }
-        const int n_chunks = st.n >> 5;
-        if (MODE == MODE_FWD) {
-          float dens = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
-          const bool is_rgb = (st.flags & EPI_RGB) != 0;
-          const bool is_dens = (st.flags & EPI_DENSITY) != 0;
-          for (int ch = 0; ch < n_chunks; ++ch) {
-            uint32_t v[32];
-            tc::tmem_ld32(t_lane + ch * 32, v);
-            tc::tmem_wait_ld();
+        long long* tr = (a.trace != nullptr && blockIdx.x == 0 && row == 0)
+                            ? a.trace + ((size_t)((pair / gridDim.x) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
+        if (tr) tr[2] = clock64();
+        const int n_units = st.n >> 6;                 // 64 accumulator columns per TMEM load (4 or 2 units, even)
+        const bool is_rgb = (MODE == MODE_FWD) && (st.flags & EPI_RGB) != 0;
+        const bool is_dens = (MODE == MODE_FWD) && (st.flags & EPI_DENSITY) != 0;
+        const bool add_sigma = (MODE == MODE_BWD) && (st.flags & EPI_BWD_SIGMA) != 0;
+        const bool write_act = (MODE == MODE_BWD) || !is_rgb || train;
+        float dn[4] = {0.f, 0.f, 0.f, 0.f}, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+
+        // one 64-column unit: heads (rare steps), activation / mask, bf16 pack, store as the next A tile
+        auto process = [&](uint32_t (&v)[64], int u) {
+          if (MODE == MODE_FWD) {
             if (is_dens) {                             // density head on the fp32 ReLU output (NeRFModel.py:192)
-              const float* wd = a.small + a.sm_wd + ch * 32;
+              const float4* wd = reinterpret_cast<const float4*>(sm + a.sm_wd + u * 64);
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(wd + j));
-                dens = fmaf(fmaxf(__uint_as_float(v[j]), 0.f), w4.x, dens);
-                dens = fmaf(fmaxf(__uint_as_float(v[j + 1]), 0.f), w4.y, dens);
-                dens = fmaf(fmaxf(__uint_as_float(v[j + 2]), 0.f), w4.z, dens);
-                dens = fmaf(fmaxf(__uint_as_float(v[j + 3]), 0.f), w4.w, dens);
+              for (int j = 0; j < 64; j += 4) {
+                const float4 w4 = wd[j >> 2];
+                dn[0] = fmaf(fmaxf(__uint_as_float(v[j]), 0.f), w4.x, dn[0]);
+                dn[1] = fmaf(fmaxf(__uint_as_float(v[j + 1]), 0.f), w4.y, dn[1]);
+                dn[2] = fmaf(fmaxf(__uint_as_float(v[j + 2]), 0.f), w4.z, dn[2]);
+                dn[3] = fmaf(fmaxf(__uint_as_float(v[j + 3]), 0.f), w4.w, dn[3]);
               }
             }
             if (is_rgb) {                              // rgb_layer2 on the fp32 ReLU output (NeRFModel.py:199-200)
-              const float* w2 = a.small + a.sm_w2 + ch * 32;
+              const float4* w2 = reinterpret_cast<const float4*>(sm + a.sm_w2 + u * 64);
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 wa = __ldg(reinterpret_cast<const float4*>(w2 + j));
-                const float4 wb = __ldg(reinterpret_cast<const float4*>(w2 + 128 + j));
-                const float4 wc = __ldg(reinterpret_cast<const float4*>(w2 + 256 + j));
+              for (int j = 0; j < 64; j += 4) {
+                const float4 wa = w2[j >> 2], wb = w2[32 + (j >> 2)], wc = w2[64 + (j >> 2)];
                 const float y0 = fmaxf(__uint_as_float(v[j]), 0.f), y1 = fmaxf(__uint_as_float(v[j + 1]), 0.f);
                 const float y2 = fmaxf(__uint_as_float(v[j + 2]), 0.f), y3 = fmaxf(__uint_as_float(v[j + 3]), 0.f);
-                c0 = fmaf(y0, wa.x, c0); c0 = fmaf(y1, wa.y, c0); c0 = fmaf(y2, wa.z, c0); c0 = fmaf(y3, wa.w, c0);
-                c1 = fmaf(y0, wb.x, c1); c1 = fmaf(y1, wb.y, c1); c1 = fmaf(y2, wb.z, c1); c1 = fmaf(y3, wb.w, c1);
-                c2 = fmaf(y0, wc.x, c2); c2 = fmaf(y1, wc.y, c2); c2 = fmaf(y2, wc.z, c2); c2 = fmaf(y3, wc.w, c2);
+                c0 = fmaf(y0, wa.x, c0); c1 = fmaf(y0, wb.x, c1); c2 = fmaf(y0, wc.x, c2);
+                c0 = fmaf(y1, wa.y, c0); c1 = fmaf(y1, wb.y, c1); c2 = fmaf(y1, wc.y, c2);
+                c0 = fmaf(y2, wa.z, c0); c1 = fmaf(y2, wb.z, c1); c2 = fmaf(y2, wc.z, c2);
+                c0 = fmaf(y3, wa.w, c0); c1 = fmaf(y3, wb.w, c1); c2 = fmaf(y3, wc.w, c2);
               }
             }
-            if (train) {
-              uint32_t word = 0u;
+            if (write_act) {                           // ReLU + bf16 pack in one cvt; the bias came through the MMA
 #pragma unroll
-              for (int j = 0; j < 32; ++j) word |= (__uint_as_float(v[j]) > 0.0f) ? (1u << j) : 0u;
-              put8(mk_a, mk_b, ch, word);
-            }
-            if (!is_rgb || train) {                    // ReLU + bf16 pack in one cvt; the bias came through the MMA
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                tc::st_shared_v4(s_act + (ch * 4 + q) * kKcoreBytes + row * 16,
+              for (int q = 0; q < 8; ++q)
+                tc::st_shared_v4(s_act + (u * 8 + q) * kKcoreBytes + row * 16,
                                  tc::pack_bf16x2_relu(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
                                  tc::pack_bf16x2_relu(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
                                  tc::pack_bf16x2_relu(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
                                  tc::pack_bf16x2_relu(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
             }
-          }
-          if (store_out) {
-            uint4* mp = reinterpret_cast<uint4*>(stash_tile + st.mask_off) + row * 2;
-            mp[0] = mk_a; mp[1] = mk_b;
-          }
-          if (is_dens) sigma_keep = softplus_f(dens + __ldg(a.small + a.sm_bd));
-          if (is_rgb && valid) {
-            const float* b2 = a.small + a.sm_b2;
-            reinterpret_cast<float4*>(a.sigma_rgb)[grow] =
-                make_float4(sigma_keep, sigmoid_f(c0 + __ldg(b2)), sigmoid_f(c1 + __ldg(b2 + 1)), sigmoid_f(c2 + __ldg(b2 + 2)));
-          }
-          if (st.flags & EPI_WRITE_DIR) {
-            if (a.dir_L == 4) write_encoding<4, 4, false>(s_enc, row, dirv);
-            else write_encoding<0, 4, false>(s_enc, row, dirv);
-          }
-        } else {
-          const bool add_sigma = (st.flags & EPI_BWD_SIGMA) != 0;
-          for (int ch = 0; ch < n_chunks; ++ch) {
-            const uint32_t word = pick8(mk_a, mk_b, ch);
-            uint32_t v[32];
-            tc::tmem_ld32(t_lane + ch * 32, v);
-            tc::tmem_wait_ld();
-            float y[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
+          } else {
+            const uint32_t w_lo = pick8(mk_a, mk_b, 2 * u), w_hi = pick8(mk_a, mk_b, 2 * u + 1);
             if (add_sigma) {                           // density head: d h8 += d_sigma_pre * w_d
-              const float* wd = a.small + a.sm_wd + ch * 32;
+              const float4* wd = reinterpret_cast<const float4*>(sm + a.sm_wd + u * 64);
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(wd + j));
-                y[j] = fmaf(dsp, w4.x, y[j]); y[j + 1] = fmaf(dsp, w4.y, y[j + 1]);
-                y[j + 2] = fmaf(dsp, w4.z, y[j + 2]); y[j + 3] = fmaf(dsp, w4.w, y[j + 3]);
+              for (int j = 0; j < 64; j += 4) {
+                const float4 w4 = wd[j >> 2];
+                v[j] = __float_as_uint(fmaf(dsp, w4.x, __uint_as_float(v[j])));
+                v[j + 1] = __float_as_uint(fmaf(dsp, w4.y, __uint_as_float(v[j + 1])));
+                v[j + 2] = __float_as_uint(fmaf(dsp, w4.z, __uint_as_float(v[j + 2])));
+                v[j + 3] = __float_as_uint(fmaf(dsp, w4.w, __uint_as_float(v[j + 3])));
               }
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = ((word >> j) & 1u) ? y[j] : 0.0f;     // relu'(h)
+            for (int j = 0; j < 64; ++j) {             // relu'(h): mask bit of column c sits at (c>>1) + 16*(c&1)
+              const uint32_t w = (j < 32) ? w_lo : w_hi;
+              v[j] = ((w >> (((j & 31) >> 1) + 16 * (j & 1))) & 1u) ? v[j] : 0u;
+            }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              tc::st_shared_v4(s_act + (ch * 4 + q) * kKcoreBytes + row * 16,
-                               tc::pack_bf16x2(y[8 * q + 0], y[8 * q + 1]), tc::pack_bf16x2(y[8 * q + 2], y[8 * q + 3]),
-                               tc::pack_bf16x2(y[8 * q + 4], y[8 * q + 5]), tc::pack_bf16x2(y[8 * q + 6], y[8 * q + 7]));
+            for (int q = 0; q < 8; ++q)
+              tc::st_shared_v4(s_act + (u * 8 + q) * kKcoreBytes + row * 16,
+                               tc::pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
+                               tc::pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+                               tc::pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
+                               tc::pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+          }
+        };
+
+        {   // double-buffered accumulator read-out: the next unit's TMEM load flies while this one is packed
+          uint32_t va[64], vb[64];
+          tc::tmem_ld64(t_lane, va);
+          tc::tmem_wait_ld();
+          for (int u = 0; u < n_units; u += 2) {
+            tc::tmem_ld64(t_lane + (u + 1) * 64, vb);
+            process(va, u);
+            tc::tmem_wait_ld();
+            if (u + 2 < n_units) tc::tmem_ld64(t_lane + (u + 2) * 64, va);
+            process(vb, u + 1);
+            tc::tmem_wait_ld();
           }
         }
         tc::tc_fence_before();                         // TMEM reads retired before the next MMA overwrites
-        tc::fence_proxy_async_smem();                  // ACT/ENC writes visible to UMMA / bulk stores
-        if ((MODE == MODE_BWD) || train) {
-          tc::named_bar_sync(nb, 128);
-          if (row == 0 && store_out) {
-            uint8_t* dst = (MODE == MODE_FWD ? stash_tile : dstash_tile) + st.stash_off;
-            tc::bulk_s2g(dst, s_act, (uint32_t)st.n * 256u);          // n channels x 128 rows x 2 B
-            if (MODE == MODE_FWD && (st.flags & EPI_WRITE_DIR)) tc::bulk_s2g(stash_tile + a.st_de, s_enc, 4 * kKcoreBytes);
-            tc::bulk_commit();
+        tc::fence_proxy_async_smem();                  // ACT writes visible to UMMA
+        if (!(st.flags & EPI_LAST)) tc::mbar_arrive(my_act);   // the next layer's MMAs may start NOW
+        if (tr) tr[3] = clock64();
+
+        // ---- everything below is off the MMA -> epilogue -> MMA critical path ----
+        if (MODE == MODE_FWD) {
+          if (st.flags & EPI_WRITE_DIR) {              // ENC k-cores 0-3 <- direction encoding (used by rgb_layer1)
+            uint8_t* g_de = store_out ? stash_tile + a.st_de : nullptr;
+            if (a.dir_L == 4) write_encoding<4, 4, false>(s_enc, row, dirv, g_de);
+            else write_encoding<0, 4, false>(s_enc, row, dirv, g_de);
+            tc::fence_proxy_async_smem();
+          }
+          if (is_dens) sigma_keep = softplus_f((dn[0] + dn[1]) + (dn[2] + dn[3]) + sm[a.sm_bd]);
+          if (is_rgb && valid) {
+            const float* b2 = sm + a.sm_b2;
+            reinterpret_cast<float4*>(a.sigma_rgb)[grow] =
+                make_float4(sigma_keep, sigmoid_f(c0 + b2[0]), sigmoid_f(c1 + b2[1]), sigmoid_f(c2 + b2[2]));
           }
         }
-        if (!(st.flags & EPI_LAST)) tc::mbar_arrive(my_act);
+        if (store_out && !(a.exp_flags & 1)) {
+          // Training stash: this thread reads back the 16-byte pieces of ITS OWN row of the bf16 tile it
+          // just wrote and streams them to HBM (a warp writes 512 contiguous bytes per instruction), and
+          // (forward) folds them into the ReLU bit masks (bit of column c in a 32-column chunk:
+          // (c>>1) + 16*(c&1)).  This runs under the next layer's MMAs.  A bulk (TMA) store of the tile
+          // would be one instruction, but its shared-memory reads halve the UMMA issue rate (measured).
+          uint4* gdst = reinterpret_cast<uint4*>((MODE == MODE_FWD ? stash_tile : dstash_tile) + st.stash_off) + row;
+          uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            if (ch * 32 < st.n) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 pk;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "r"(s_act + (ch * 4 + q) * kKcoreBytes + row * 16));
+                gdst[(ch * 4 + q) * 128] = pk;
+                if (MODE == MODE_FWD) {
+                  mw[ch] |= ((pk.x + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 0));
+                  mw[ch] |= ((pk.y + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 1));
+                  mw[ch] |= ((pk.z + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 2));
+                  mw[ch] |= ((pk.w + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 3));
+                }
+              }
+            }
+          }
+          if (MODE == MODE_FWD) {
+            uint4* mp = reinterpret_cast<uint4*>(stash_tile + st.mask_off) + row * 2;
+            mp[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+            mp[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+          }
+        }
       }
     }
-    if (row == 0) tc::bulk_wait0();
   }
   tc::tc_fence_before();
   __syncthreads();
