@@ -3,7 +3,7 @@
 // blocked stash/dstash tiles ([k_core][row][8]); the fp32 accumulator (up to 256x256) lives in the
 // whole 512-column TMEM of one SM for the CTA's entire row range and is added into the flat
 // gradient vector once at the end (split-K over CTAs, red.global.add.f32).
-//   warp 0    : loader -- whole 128-row dY / X blocks, ONE bulk copy (<= 64 KB) each, ring of 3 slots
+//   warp 0    : loader -- 128-row x 128-channel sub-blocks of dY / X, ONE bulk copy (<= 32 KB) each, ring of 6 slots
 //   warp 1    : MMA issuer (one thread)
 //   warps 2-5 : bias gradients (column sums of dY from the staged tile) + final TMEM -> HBM epilogue
 // Head gradients (density_layer, rgb_layer2: N < 16, not UMMA shapes) run on CUDA cores.
@@ -14,8 +14,8 @@
 
 namespace nerf {
 
-constexpr int kWgSlots = 3;                // ring of operand slots: dY_t, X_t, dY_{t+1}, X_{t+1}, ...
-constexpr int kWgSlotBytes = 65536;        // one 128-row operand block (<= 256 channels)
+constexpr int kWgSlots = 6;                // ring of operand sub-blocks
+constexpr int kWgSlotBytes = 32768;        // one 128-row block of 128 channels (dY M-half or X N-half)
 constexpr int kWgSmemBytes = kWgSlots * kWgSlotBytes + 128;
 
 struct WgradArgs {
@@ -28,12 +28,35 @@ struct WgradArgs {
   WgradItem items[kMaxWgradItems];
 };
 
+// Per 128-row tile an item streams its operands as sub-blocks in the order dY0, X0, [X1], [dY1]
+// (dY_i = M-half i of dY, 16 k-cores; X_j = N-part j of the layer input, <= 16 k-cores) and issues the
+// UMMA groups (dY0,X0) (dY0,X1) (dY1,X0) (dY1,X1).  Each sub-block's ring slot is released right after
+// the last group that reads it, so the loader always has 2-3 sub-blocks (64-96 KB) in flight.
+struct WgPlan {
+  int m_halves, x_parts, n_loads;
+  int dy_load[2], x_load[2];               // position of each sub-block in the per-tile load order
+  uint32_t dy_bytes, x_bytes[2];
+  int x_n[2];                              // UMMA N of each X part
+};
+__device__ __forceinline__ WgPlan make_plan(const WgradItem& W) {
+  WgPlan p;
+  p.m_halves = W.m_kcores / 16;
+  p.x_parts = W.n > 128 ? 2 : 1;
+  p.dy_bytes = 16 * kKcoreBytes;
+  p.x_n[0] = W.n > 128 ? 128 : W.n; p.x_n[1] = W.n - p.x_n[0];
+  p.x_bytes[0] = (uint32_t)(p.x_n[0] / 8) * kKcoreBytes; p.x_bytes[1] = (uint32_t)(p.x_n[1] / 8) * kKcoreBytes;
+  p.dy_load[0] = 0; p.x_load[0] = 1; p.x_load[1] = 2;
+  p.dy_load[1] = 1 + p.x_parts;
+  p.n_loads = p.m_halves + p.x_parts;
+  return p;
+}
+
 __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = tc::smem_u32(smem);
   const uint32_t s_bar = s_base + kWgSlots * kWgSlotBytes;
-  const uint32_t bar_full = s_bar, bar_empty = s_bar + 24, bar_acc = s_bar + 48;
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kWgSlots * kWgSlotBytes + 64);
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 48, bar_acc = s_bar + 96;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kWgSlots * kWgSlotBytes + 104);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -56,99 +79,113 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   const int t0 = (int)(((int64_t)a.n_tiles * split) / splits);
   const int t1 = (int)(((int64_t)a.n_tiles * (split + 1)) / splits);
   const int n_my_tiles = t1 - t0;
-  const int m_halves = W.m_kcores / 16;
-  const uint32_t dy_bytes = (uint32_t)W.m_kcores * kKcoreBytes;
-  const uint32_t x_bytes = (uint32_t)(W.n / 8) * kKcoreBytes;
+  const WgPlan pl = make_plan(W);
+  const int m_halves = pl.m_halves;
 
   if (warp == 0) {
-    // ===================== loader: one bulk copy per operand block =====================
+    // ===================== loader: one bulk copy per operand sub-block =====================
     if (lane == 0) {
-      for (int L = 0; L < 2 * n_my_tiles; ++L) {
-        const int tile = t0 + (L >> 1);
-        const uint32_t slot = L % kWgSlots, ph = (L / kWgSlots) & 1u;
-        const bool is_dy = (L & 1) == 0;
-        const uint8_t* src = is_dy ? a.dstash + (size_t)tile * a.dstash_tile_bytes + W.dy_off
-                                   : a.stash + (size_t)tile * a.stash_tile_bytes + W.x_off;
-        const uint32_t bytes = is_dy ? dy_bytes : x_bytes;
-        tc::mbar_wait(bar_empty + 8 * slot, ph ^ 1u);
-        tc::mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
-        tc::bulk_g2s(s_base + slot * kWgSlotBytes, src, bytes, bar_full + 8 * slot);
+      uint32_t L = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        const uint8_t* dy = a.dstash + (size_t)(t0 + t) * a.dstash_tile_bytes + W.dy_off;
+        const uint8_t* x = a.stash + (size_t)(t0 + t) * a.stash_tile_bytes + W.x_off;
+        for (int l = 0; l < pl.n_loads; ++l, ++L) {
+          const uint8_t* src; uint32_t bytes;
+          if (l == 0) { src = dy; bytes = pl.dy_bytes; }
+          else if (l <= pl.x_parts) { src = x + (size_t)(l - 1) * 16 * kKcoreBytes; bytes = pl.x_bytes[l - 1]; }
+          else { src = dy + 16 * kKcoreBytes; bytes = pl.dy_bytes; }
+          const uint32_t slot = L % kWgSlots, ph = (L / kWgSlots) & 1u;
+          tc::mbar_wait(bar_empty + 8 * slot, ph ^ 1u);
+          tc::mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+          tc::bulk_g2s(s_base + slot * kWgSlotBytes, src, bytes, bar_full + 8 * slot);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = tc::umma_idesc_bf16(128, W.n, 1, 1);
-      for (int i = 0; i < n_my_tiles; ++i) {
-        const int La = 2 * i, Lb = 2 * i + 1;
-        const uint32_t slot_a = La % kWgSlots, slot_b = Lb % kWgSlots;
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    uint32_t L0 = 0;                                   // index of this tile's first load
+    for (int t = 0; t < n_my_tiles; ++t, L0 += (uint32_t)pl.n_loads) {
+      for (int i = 0; i < m_halves; ++i) {
+        const uint32_t La = L0 + (uint32_t)pl.dy_load[i];
+        const uint32_t slot_a = La % kWgSlots;
         tc::mbar_wait(bar_full + 8 * slot_a, (La / kWgSlots) & 1u);
-        tc::mbar_wait(bar_full + 8 * slot_b, (Lb / kWgSlots) & 1u);
-        tc::tc_fence_after();
-        const uint32_t sa = s_base + slot_a * kWgSlotBytes, sb = s_base + slot_b * kWgSlotBytes;
+        for (int j = 0; j < pl.x_parts; ++j) {
+          const uint32_t Lb = L0 + (uint32_t)pl.x_load[j];
+          const uint32_t slot_b = Lb % kWgSlots;
+          tc::mbar_wait(bar_full + 8 * slot_b, (Lb / kWgSlots) & 1u);
+          tc::tc_fence_after();
+          const uint32_t sa = s_base + slot_a * kWgSlotBytes, sb = s_base + slot_b * kWgSlotBytes;
+          const uint32_t idesc = tc::umma_idesc_bf16(128, pl.x_n[j], 1, 1);
+          const uint32_t d_col = tmem_base + (uint32_t)(i * W.n + j * 128);
+          if (tc::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {               // 16 rows (the contraction axis) per UMMA
-          const uint64_t bdesc = tc::umma_smem_desc(sb + ks * 256, 128, kKcoreBytes);
-          for (int mh = 0; mh < m_halves; ++mh) {
-            const uint64_t adesc = tc::umma_smem_desc(sa + mh * 16 * kKcoreBytes + ks * 256, 128, kKcoreBytes);
-            tc::umma_bf16(tmem_base + mh * W.n, adesc, bdesc, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < 8; ++ks)               // 16 rows (the contraction axis) per UMMA
+              tc::umma_bf16(d_col, tc::umma_smem_desc(sa + ks * 256, 128, kKcoreBytes),
+                            tc::umma_smem_desc(sb + ks * 256, 128, kKcoreBytes), idesc, (t > 0 || ks > 0) ? 1u : 0u);
+            if (i == m_halves - 1) tc::umma_commit(bar_empty + 8 * slot_b);   // last reader of X_j
+            if (j == pl.x_parts - 1) tc::umma_commit(bar_empty + 8 * slot_a); // last reader of dY_i
           }
+          __syncwarp();
         }
-        tc::umma_commit(bar_empty + 8 * slot_a);
-        tc::umma_commit(bar_empty + 8 * slot_b);
       }
-      tc::umma_commit(bar_acc);
     }
+    if (tc::elect_one()) tc::umma_commit(bar_acc);
     __syncwarp();
   } else {
     // ===================== bias sums + epilogue =====================
-    const int q = warp - 2;                       // k_cores q, q+4, ...
+    const int q = warp - 2;                       // k_cores q, q+4, q+8, q+12 of each dY half
     float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-    for (int t = 0; t < n_my_tiles; ++t) {
-      const int La = 2 * t, Lb = 2 * t + 1;
-      const uint32_t slot_a = La % kWgSlots, slot_b = Lb % kWgSlots;
-      const uint32_t sa = s_base + slot_a * kWgSlotBytes;
-      tc::mbar_wait(bar_full + 8 * slot_a, (La / kWgSlots) & 1u);
-      if (W.b_off >= 0) {
+    uint32_t L0 = 0;
+    for (int t = 0; t < n_my_tiles; ++t, L0 += (uint32_t)pl.n_loads) {
+      for (int l = 0; l < pl.n_loads; ++l) {
+        const uint32_t L = L0 + (uint32_t)l;
+        const uint32_t slot = L % kWgSlots;
+        tc::mbar_wait(bar_full + 8 * slot, (L / kWgSlots) & 1u);
+        const bool is_dy = (l == 0) || (l > pl.x_parts);
+        if (is_dy && W.b_off >= 0) {
+          const uint32_t sa = s_base + slot * kWgSlotBytes;
+          const int half = (l == 0) ? 0 : 1;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i * 4 < W.m_kcores) {
-            const int kc = q + 4 * i;
+          for (int ii = 0; ii < 4; ++ii) {
+            const int kc = q + 4 * ii;
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
               uint32_t u0, u1, u2, u3;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(sa + kc * kKcoreBytes + (lane + 32 * rr) * 16));
-              acc[i][0] += __uint_as_float(u0 << 16); acc[i][1] += __uint_as_float(u0 & 0xffff0000u);
-              acc[i][2] += __uint_as_float(u1 << 16); acc[i][3] += __uint_as_float(u1 & 0xffff0000u);
-              acc[i][4] += __uint_as_float(u2 << 16); acc[i][5] += __uint_as_float(u2 & 0xffff0000u);
-              acc[i][6] += __uint_as_float(u3 << 16); acc[i][7] += __uint_as_float(u3 & 0xffff0000u);
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                if (hh == half) {                    // compile-time accumulator index, runtime half
+                  acc[hh * 4 + ii][0] += __uint_as_float(u0 << 16); acc[hh * 4 + ii][1] += __uint_as_float(u0 & 0xffff0000u);
+                  acc[hh * 4 + ii][2] += __uint_as_float(u1 << 16); acc[hh * 4 + ii][3] += __uint_as_float(u1 & 0xffff0000u);
+                  acc[hh * 4 + ii][4] += __uint_as_float(u2 << 16); acc[hh * 4 + ii][5] += __uint_as_float(u2 & 0xffff0000u);
+                  acc[hh * 4 + ii][6] += __uint_as_float(u3 << 16); acc[hh * 4 + ii][7] += __uint_as_float(u3 & 0xffff0000u);
+                }
+              }
             }
           }
         }
+        __syncwarp();
+        // every slot's "empty" barrier counts this warp: arrive only after the slot has been filled for
+        // THIS load, so the arrival cannot land in an earlier phase
+        if (lane == 0) tc::mbar_arrive(bar_empty + 8 * slot);
       }
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(bar_empty + 8 * slot_a);
-      // the X slot is not read here, but its "empty" barrier counts this warp too: arrive only once it
-      // has been filled for THIS tile, so the arrival cannot land in an earlier phase
-      tc::mbar_wait(bar_full + 8 * slot_b, (Lb / kWgSlots) & 1u);
-      if (lane == 0) tc::mbar_arrive(bar_empty + 8 * slot_b);
     }
     if (W.b_off >= 0) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (i * 4 < W.m_kcores) {
+        if ((i >> 2) < m_halves) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float v = acc[i][j];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) atomicAdd(a.grads + W.b_off + (q + 4 * i) * 8 + j, v);
+            if (lane == 0) atomicAdd(a.grads + W.b_off + ((i >> 2) * 16 + q + 4 * (i & 3)) * 8 + j, v);
           }
         }
       }
