@@ -32,6 +32,18 @@ FLOP_DGRAD = 2 * 623232
 FLOP_WGRAD = 2 * 658944
 BYTES_COMPOSITE_FWD = 20         # sigma 4 + rgb 12 + z 4 per sample (jittered)
 BYTES_COMPOSITE_BWD = 36
+# algorithmic HBM bytes per sample of the training kernels (DESIGN.md "Data layout"): bf16 stash blocks
+# [PE 128 | DE 64 | h0..h8, feature 10 x 512 | r1 256] + 11 ReLU bit masks x 32 B; dY stash 10 x 512 + 256 + 16
+BYTES_FWD_TRAIN = 128 + 64 + 10 * 512 + 256 + 11 * 32 + 16 + 4
+BYTES_DGRAD = 11 * 32 + 16 + 16 + 10 * 512 + 256 + 16
+BYTES_WGRAD = (11 * 512 + 2 * 256) + (2 * 128 + 10 * 512 + 64) + (512 + 256 + 16)
+
+
+def workload_config(n_rays, world):
+    return {"workload": f"lego-shaped synthetic scene {IMG}x{IMG} (20 views), train step {n_rays} rays x {N_SAMPLE} samples per GPU, "
+                        "live PE model 661,636 params, Adam",
+            "samples_per_ray": N_SAMPLE, "parallelism": f"dp{world}" if world > 1 else "single",
+            "l2": "working set (stash+dstash ~2.8 GB/step) >> 126 MB L2; no explicit flush"}
 
 
 def parse():
@@ -153,8 +165,7 @@ def run_reference(args):
         "metric": "train_step_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"lego-shaped synthetic scene {IMG}x{IMG}, train step {args.rays} rays x {N_SAMPLE} samples, live PE model, Adam",
-                   "samples_per_ray": N_SAMPLE},
+        "config": workload_config(args.rays, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port",
                          "sample": f"{len(times)} train steps of {n_rays} rays x {N_SAMPLE} samples (oracle port of train.py:447-465, "
                                    f"torch CPU, {threads} threads; per-ray Python ray generation included as in the reference)"},
@@ -218,7 +229,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = (trainer.launches_per_step - 1) * args.steps      # my kernels only (the memset is the driver's)
+    launches = trainer.launches_per_step * args.steps            # this repo's kernels only (the gradient memset is the driver's)
     final_loss = float(trainer.loss.item())
 
     # ---- end to end through the public API with host buffers --------------------------------
@@ -267,6 +278,19 @@ def run_ours(args):
         ev5.record()
         barrier()
     render_ms = max_over_ranks(ev4.elapsed_time(ev5))
+    # the fused MLP inference kernel alone on this rank's slice of the frame (tensor-pipe fraction)
+    with torch.no_grad():
+        o, d = E.raygen_image(poses, 0, cam, r_begin, per_rank)
+        zr = E.sample_z(per_rank, N_SAMPLE, 2.0, 6.0, dev, perturb=True, seed=5)
+        for _ in range(2):
+            E.mlp_forward_rays(st, o, d, zr, None)
+        ev6, ev7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev6.record()
+        for _ in range(5):
+            E.mlp_forward_rays(st, o, d, zr, None)
+        ev7.record()
+        torch.cuda.synchronize()
+    mlp_infer_ms = ev6.elapsed_time(ev7) / 5
     render_rays_s = IMG * IMG * n_frames / render_ms * 1e3
     trainer.close()
 
@@ -279,26 +303,33 @@ def run_ours(args):
     peaks = measured_peaks()
     rows = n_rays * N_SAMPLE
     work = {"mlp_fwd": rows * FLOP_FWD, "mlp_dgrad": rows * FLOP_DGRAD, "mlp_wgrad": rows * FLOP_WGRAD}
+    traffic_alg = {"mlp_fwd": rows * BYTES_FWD_TRAIN, "mlp_dgrad": rows * BYTES_DGRAD, "mlp_wgrad": rows * BYTES_WGRAD,
+                   "composite_fwd": rows * BYTES_COMPOSITE_FWD, "composite_bwd": rows * BYTES_COMPOSITE_BWD}
     kern = {}
     for name, pairs in timers.items():
         ms = sum(a.elapsed_time(b) for a, b in pairs) / len(pairs)
         kern[name] = {"ms": round(ms, 4)}
         if name in work:
             kern[name]["tflops"] = round(work[name] / ms / 1e9, 1)
-            kern[name]["frac_of_peak"] = round(work[name] / ms / 1e9 / peaks["tflops"], 4)
-        elif name == "composite_fwd":
-            kern[name]["gbs"] = round(rows * BYTES_COMPOSITE_FWD / ms / 1e6, 1)
-        elif name == "composite_bwd":
-            kern[name]["gbs"] = round(rows * BYTES_COMPOSITE_BWD / ms / 1e6, 1)
+            kern[name]["tensor_frac"] = round(work[name] / ms / 1e9 / peaks["tflops"], 4)
+        if name in traffic_alg:
+            kern[name]["gbs"] = round(traffic_alg[name] / ms / 1e6, 1)
+            kern[name]["hbm_frac"] = round(traffic_alg[name] / ms / 1e6 / peaks["hbm"], 4)
     dom = max(work, key=lambda k: kern[k]["ms"])
-    traffic = None
+    measured = {}
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
-    roofline = {"bound": "tensor", "kernel": dom, "achieved": kern[dom]["tflops"], "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": kern[dom]["frac_of_peak"], "traffic": traffic, "peak_source": peaks["src"],
-                "flop_per_sample": {"mlp_fwd": FLOP_FWD, "mlp_dgrad": FLOP_DGRAD, "mlp_wgrad": FLOP_WGRAD}[dom],
-                "step_tflops": round(rows * (FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD) * args.steps / ms_total / 1e9, 1)}
+        measured = json.load(open(tpath))
+    k = kern[dom]
+    if k["hbm_frac"] >= k["tensor_frac"]:
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": k["gbs"], "peak": peaks["hbm"], "unit": "GB/s", "frac": k["hbm_frac"],
+                    "bytes_per_sample": traffic_alg[dom] // rows}
+    else:
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": k["tflops"], "peak": peaks["tflops"], "unit": "TFLOP/s",
+                    "frac": k["tensor_frac"], "flop_per_sample": work[dom] // rows}
+    roofline.update({"traffic": measured.get(dom), "peak_source": peaks["src"], "tensor_frac": k["tensor_frac"], "hbm_frac": k["hbm_frac"],
+                     "step_tflops": round(rows * (FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD) * args.steps / ms_total / 1e9, 1),
+                     "step_tensor_frac": round(rows * (FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD) * args.steps / ms_total / 1e9 / peaks["tflops"], 4)})
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -313,13 +344,14 @@ def run_ours(args):
         "metric": "train_step_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"lego-shaped synthetic scene {IMG}x{IMG} (20 views), train step {n_rays} rays x {N_SAMPLE} samples per GPU, "
-                               "live PE model 661,636 params, Adam; rays drawn on-GPU",
-                   "samples_per_ray": N_SAMPLE, "parallelism": f"dp{world}" if world > 1 else "single",
-                   "l2": "working set (stash+dstash ~2.8 GB/step) >> 126 MB L2; no explicit flush"},
+        "config": workload_config(n_rays, world),
         "samples_per_s": value * N_SAMPLE,
         "render": {"rays_per_s": render_rays_s, "samples_per_s": render_rays_s * N_SAMPLE,
-                   "workload": f"{IMG}x{IMG} frame x {N_SAMPLE} samples, rays sharded over {world} GPU(s), ray-gen included"},
+                   "workload": f"{IMG}x{IMG} frame x {N_SAMPLE} samples, rays sharded over {world} GPU(s), ray-gen + sampling + MLP + compositing",
+                   "mlp_kernel": {"ms": round(mlp_infer_ms, 4), "rows": per_rank * N_SAMPLE,
+                                  "tflops": round(per_rank * N_SAMPLE * FLOP_FWD / mlp_infer_ms / 1e9, 1),
+                                  "tensor_frac": round(per_rank * N_SAMPLE * FLOP_FWD / mlp_infer_ms / 1e9 / measured_peaks()["tflops"], 4),
+                                  "samples_per_s": per_rank * N_SAMPLE / mlp_infer_ms * 1e3}},
         "e2e": {"value": n_rays * world * e2e_steps / e2e_ms * 1e3, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 9 * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": launches,
