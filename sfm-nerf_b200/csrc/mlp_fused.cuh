@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
   float* sm = reinterpret_cast<float*>(smem + MlpSmem::kHead);
   for (int i = threadIdx.x; i < MlpSmem::kHeadFloats; i += blockDim.x) sm[i] = a.small[i];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops
+  // (barrier addresses, descriptors, counters) on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingSlots; ++i) { tc::mbar_init(bar_full + 8 * i, 1); tc::mbar_init(bar_empty + 8 * i, 2); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(bar_acc + 8 * i, 1); tc::mbar_init(bar_act + 8 * i, 128); }
@@ -201,8 +203,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
     const uint32_t a_lbo = ((uint32_t)kKcoreBytes >> 4) << 16;                              // LBO = 2048 B
     const uint32_t act_lo = a_lbo | ((s_act & 0x3FFFFu) >> 4), enc_lo = a_lbo | ((s_enc & 0x3FFFFu) >> 4);
     const uint32_t ring_lo = (s_ring & 0x3FFFFu) >> 4;
-    uint32_t it = 0, act_phase = 0, pair_phase = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pair_phase) {
+    uint32_t it = 0, act_phase = 0, skew_phase = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       for (int si = 0; si < P.n_steps; ++si, ++act_phase) {
         const int n = P.s[si].n, act_ks = P.s[si].act_ksteps, enc_ks = P.s[si].enc_ksteps;
         const int total = act_ks + enc_ks + P.s[si].bias_kstep;
@@ -213,10 +215,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
         long long* tr = (a.trace != nullptr && blockIdx.x == 0 && lane == 0)
                             ? a.trace + ((size_t)((pair / gridDim.x) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
         if (tr) tr[0] = clock64();
-        // De-synchronise the two tiles: tile 1 enters the first deep layer only when tile 0 is one ring
-        // depth (8 k-steps) into it.  The offset then persists (the shared ring bounds it from above), so
-        // one tile's epilogue runs under the other tile's MMAs instead of both idling the tensor pipe.
-        if (si == 1 && slot == 1) tc::mbar_wait(bar_skew, pair_phase & 1u);
+        // De-synchronise the two tiles: tile 1 enters a deep layer only when tile 0 is one ring depth
+        // (8 k-steps) into it, and the shared ring keeps tile 0 at most that far ahead -- so one tile's
+        // epilogue runs under the other tile's MMAs instead of both idling the tensor pipe together.
+        const bool deep = total > kRingSlots;           // every layer except fc1 (K=64) / the first dgrad step (K=128)
+        if (deep && slot == 1) { tc::mbar_wait(bar_skew, skew_phase & 1u); }
+        if (deep) ++skew_phase;
         for (int k = 0; k < total; ++k) {
           const uint32_t j = it + (uint32_t)k;
           const uint32_t rs = j & (kRingSlots - 1);
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
           if (tc::elect_one()) {
             tc::umma_bf16(d_tmem, desc_hi | a_lo, desc_hi | (b_lo + rs * (kRingSlotBytes >> 4)), idesc, k > 0 ? 1u : 0u);
             tc::umma_commit(bar_empty + 8 * rs);
-            if (si == 1 && slot == 0 && k == kRingSlots - 1) tc::mbar_arrive(bar_skew);
+            if (deep && slot == 0 && k == kRingSlots - 1) tc::mbar_arrive(bar_skew);
           }
           __syncwarp();
         }

@@ -55,7 +55,17 @@ def lego_field(pts):
     return sigma, rgb
 
 
-def render_lego_images(poses, camera_info, n_sample=256, near=2.0, far=6.0, device="cpu", rays_per_chunk=65536):
+def dense_field(pts):
+    """A frame-filling test scene (box of half-size 1.2 with smoothly varying colour): unlike the mostly
+    black lego views it has signal in every ray, so short trainings do not collapse to the black solution."""
+    inside = (pts.abs() < 1.2).all(dim=-1)
+    sigma = torch.where(inside, torch.full_like(pts[..., 0], 30.0), torch.zeros_like(pts[..., 0]))
+    phase = torch.tensor([0.0, 1.0, 2.0], dtype=pts.dtype, device=pts.device)
+    rgb = (0.5 + 0.4 * torch.sin(3.0 * pts + phase)) * inside.unsqueeze(-1)
+    return sigma, rgb
+
+
+def render_lego_images(poses, camera_info, n_sample=256, near=2.0, far=6.0, device="cpu", rays_per_chunk=65536, field=None):
     """Ground-truth images [n,H,W,3] float32 of the analytic scene, composited with the reference's
     formula (train.py:248-269) in fp64 on ``device`` (plain torch: dataset generation, not hot path)."""
     W, H = camera_info["width"], camera_info["height"]
@@ -75,7 +85,7 @@ def render_lego_images(poses, camera_info, n_sample=256, near=2.0, far=6.0, devi
         for i in range(0, H * W, rays_per_chunk):
             dd = d[i:i + rays_per_chunk]
             pts = o + dd[:, None, :] * zv[None, :, None]
-            sigma, rgb = lego_field(pts)
+            sigma, rgb = (field or lego_field)(pts)
             alpha = 1.0 - torch.exp(-sigma * dists)
             T = torch.cumprod(1.0 - alpha + 1e-10, dim=1)
             T = torch.cat([torch.ones_like(T[:, :1]), T[:, :-1]], dim=1)
