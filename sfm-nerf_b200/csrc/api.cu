@@ -16,7 +16,7 @@ using namespace nerf;
 
 namespace {
 
-struct DeviceInfo { int device = -1; int sms = 0; int cc_major = 0; bool attrs_set = false; };
+struct DeviceInfo { int device = -1; int sms = 0; int cc_major = 0; int mlp_clusters = 0; bool attrs_set = false; };
 thread_local DeviceInfo g_dev;
 long long* g_trace = nullptr;      // diagnostics only (nerf_debug_trace)
 
@@ -36,10 +36,29 @@ int device_info(DeviceInfo** out) {
     NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
     NERF_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     NERF_CUDA_TRY(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+    NERF_CUDA_TRY(cudaFuncSetAttribute(selftest_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+    // how many CTA pairs of the fused MLP kernel the device can hold at once (one CTA per SM, pairs share a TPC)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(g_dev.sms & ~1); cfg.blockDim = dim3(kMlpThreads); cfg.dynamicSmemBytes = MlpSmem::kTotal;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, mlp_fused_kernel<MODE_FWD>, &cfg) != cudaSuccess || n_clusters < 1) {
+      (void)cudaGetLastError();
+      n_clusters = g_dev.sms / 2;
+    }
+    g_dev.mlp_clusters = n_clusters;
     g_dev.attrs_set = true;
   }
   *out = &g_dev;
   return NERF_OK;
+}
+
+// persistent grid of the fused MLP kernels: CTA pairs, each iteration of a pair covers 4 tiles
+inline int mlp_grid(const DeviceInfo& dev, int n_tiles) {
+  const int n_quads = (n_tiles + 3) / 4;
+  return 2 * (n_quads < dev.mlp_clusters ? n_quads : dev.mlp_clusters);
 }
 
 inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
@@ -63,6 +82,7 @@ void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t
   a.stash_tile_bytes = m.stash_tile_bytes; a.dstash_tile_bytes = m.dstash_tile_bytes;
   a.trace = g_trace;
   { const char* e = getenv("NERF_EXP"); a.exp_flags = e ? atoi(e) : 0; }
+  { const char* e = getenv("NERF_SKEW"); a.skew = e ? atoi(e) : kSkew; if (a.skew < 1 || a.skew >= kRingSlots) a.skew = kSkew; }
   a.st_pe = m.st_pe; a.st_de = m.st_de; a.st_r1 = m.st_r1; a.st_mask = m.st_mask; a.ds_y10 = m.ds_y[10]; a.ds_sr = m.ds_sr;
 }
 
@@ -83,8 +103,7 @@ int launch_forward(const void* packed, int layout, const float* pos, const float
   a.sigma_rgb = sigma_rgb;
   a.stash = static_cast<uint8_t*>(stash);
   a.prog = m->fwd;
-  const int n_pairs = (a.n_tiles + 1) / 2;               // one CTA per SM, two resident tiles each
-  const int grid = n_pairs < dev->sms ? n_pairs : dev->sms;
+  const int grid = mlp_grid(*dev, a.n_tiles);
   mlp_fused_kernel<MODE_FWD><<<grid, kMlpThreads, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
@@ -271,8 +290,7 @@ int nerf_mlp_dgrad(const void* packed, int layout, const void* stash, const floa
   a.stash = static_cast<uint8_t*>(const_cast<void*>(stash));
   a.dstash = static_cast<uint8_t*>(dstash);
   a.prog = m->bwd;
-  const int n_pairs = (a.n_tiles + 1) / 2;
-  const int grid = n_pairs < dev->sms ? n_pairs : dev->sms;
+  const int grid = mlp_grid(*dev, a.n_tiles);
   mlp_fused_kernel<MODE_BWD><<<grid, kMlpThreads, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
@@ -401,11 +419,12 @@ int nerf_selftest_umma(int variant, float* result_host) {
   DeviceInfo* dev;
   int rc = device_info(&dev);
   if (rc != NERF_OK) return rc;
-  if (variant < 0 || variant > 1 || !result_host) return NERF_ERR_ARG;
+  if (variant < 0 || variant > 2 || !result_host) return NERF_ERR_ARG;
   float* d = nullptr;                        // diagnostics only: the one entry point that allocates
   NERF_CUDA_TRY(cudaMalloc(&d, 4 * sizeof(float)));
   cudaMemset(d, 0, 4 * sizeof(float));
-  selftest_umma_kernel<<<1, 128, 32768>>>(variant, d);
+  if (variant == 2) selftest_umma_pair_kernel<<<2, 128, 32768>>>(d);
+  else selftest_umma_kernel<<<1, 128, 32768>>>(variant, d);
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(result_host, d, 4 * sizeof(float), cudaMemcpyDeviceToHost);
   cudaFree(d);

@@ -1,21 +1,23 @@
 // mlp_fused.cuh -- K4: the fused NeRF MLP (NeRFModel.py:158-202) as ONE persistent tcgen05 kernel:
 //   MODE_FWD : positions/directions (or rays + depths) -> encoding -> 11 chained UMMA layers ->
-//              density/rgb heads; activations never leave the SM (training additionally bulk-stores
+//              density/rgb heads; activations never leave the SM (training additionally streams
 //              a bf16 stash of every layer input + ReLU bit masks for the backward kernels).
 //   MODE_BWD : the data-gradient chain dY_l = (dY_{l+1} . W_{l+1}) * relu'(h_l), same machinery
 //              with transposed weight images; emits every dY_l to the dstash.
 //
-// One CTA per SM keeps TWO 128-row tiles resident (2 x 64 KB activation tiles in shared memory,
-// 2 x 256 TMEM columns).  Weights stream from L2 through an 8-slot ring of K=16 slabs (8 KB); every
-// slab is consumed by BOTH tiles before its slot is recycled, so weight traffic per MMA is halved and
-// 64 KB of loads are always in flight.  Each tile has its own MMA-issuing warp; the two run at most
-// one ring depth (8 k-steps) apart, so while one tile's epilogue runs on its warpgroup the tensor
-// pipe works on the other tile.
-//   warps 0-3 / 4-7 : epilogue of tile slot 0 / 1 (thread = row = TMEM lane):
+// CTA PAIR (cluster of 2 = the two SMs of a TPC, tcgen05 cta_group::2).  Every CTA keeps TWO 128-row
+// tiles resident (2 x 64 KB activation tiles in shared memory, 2 x 256 TMEM columns); tile slot s of
+// the leader (rank 0) and of the peer (rank 1) form one M = 256 UMMA, so a weight slab (one K=16 step)
+// is split between the two CTAs: each loads and holds only its N/2 rows (4 KB).  Per SM that halves
+// the B-operand shared-memory reads and the L2 weight traffic, and the same 64 KB of ring now holds
+// 16 k-steps instead of 8 -- deep enough to keep tile slot 1 a steady ~9 k-steps behind slot 0, so one
+// slot's epilogue runs under the other slot's MMAs instead of both idling the tensor pipe together.
+//   warps 0-3 / 4-7 : epilogue of tile slot 0 / 1 (thread = row = TMEM lane), both CTAs:
 //                     TMEM -> regs -> ReLU+bf16 pack (one cvt) -> next layer's A tile, in place
-//   warp 8          : weight loader (1-D bulk copies into the ring)
-//   warps 9 / 10    : MMA issuer of tile slot 0 / 1 (one elected lane), tcgen05.mma kind::f16
-//                     128xNx16, accumulators in TMEM
+//   warp 8          : weight loader (1-D bulk copies of this CTA's half slabs into the ring), both CTAs
+//   warps 9 / 10    : leader: MMA issuer of tile slot 0 / 1 (one elected lane), tcgen05.mma
+//                     cta_group::2 kind::f16 256xNx16, completion multicast to both CTAs' barriers;
+//                     peer: warp 9 relays "my half slab has landed" to the leader's full barriers
 // Biases ride on the MMA: channel 63 of the encoding tile is the constant 1.0 and the packed weight
 // image carries the bias in that K column, so the epilogue does no bias loads or adds.
 #pragma once
@@ -47,7 +49,8 @@ struct MlpArgs {
   uint8_t* dstash;           // bwd: written
   int32_t stash_tile_bytes, dstash_tile_bytes;
   int32_t st_pe, st_de, st_r1, st_mask, ds_y10, ds_sr;
-  int32_t exp_flags;         // diagnostics (NERF_EXP env): 1 = skip stash bulk stores, 2 = skip mask generation
+  int32_t exp_flags;         // diagnostics (NERF_EXP env): 1 = skip stash stores
+  int32_t skew;              // k-steps tile slot 1 stays behind slot 0 inside a layer (NERF_SKEW env, default kSkew)
   long long* trace;          // diagnostics: per-(pair,step,slot) clock64 stamps of CTA 0 (or null)
   Program prog;
 };
@@ -55,10 +58,10 @@ struct MlpArgs {
 struct MlpSmem {
   static constexpr int kAct = 0;                                   // 2 x 64 KB
   static constexpr int kEnc = kAct + 2 * kActBytes;                // 2 x 16 KB
-  static constexpr int kRing = kEnc + 2 * kEncBytes;               // 8 x 8 KB
+  static constexpr int kRing = kEnc + 2 * kEncBytes;               // 16 x 4 KB (this CTA's half of every slab)
   static constexpr int kBars = kRing + kRingSlots * kRingSlotBytes;
-  // barriers (8 B each): full[8] @0, empty[8] @64, acc_full[2] @128, act_ready[2] @144, skew @160; tmem ptr @176
-  static constexpr int kHead = kBars + 256;                        // fp32 head tables (w_d, b_d, W2, b2): 648 floats
+  // barriers (8 B each): full[16] @0, empty[16] @128, acc_full[2] @256, act_ready[2] @272, skew @288; tmem ptr @304
+  static constexpr int kHead = kBars + 320;                        // fp32 head tables (w_d, b_d, W2, b2): 648 floats
   static constexpr int kHeadFloats = 648;
   static constexpr int kTotal = kHead + kHeadFloats * 4;
 };
@@ -139,14 +142,15 @@ __device__ __forceinline__ float softplus_f(float x) {        // torch default b
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 template <int MODE>
-__global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_constant__ MlpArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_constant__ MlpArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = tc::smem_u32(smem);
   const uint32_t s_ring = s_base + MlpSmem::kRing;
   const uint32_t s_bar = s_base + MlpSmem::kBars;
-  const uint32_t bar_full = s_bar, bar_empty = s_bar + 64, bar_acc = s_bar + 128, bar_act = s_bar + 144;
-  const uint32_t bar_skew = s_bar + 160;
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kBars + 176);
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 128, bar_acc = s_bar + 256, bar_act = s_bar + 272;
+  const uint32_t bar_skew = s_bar + 288;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kBars + 304);
+  const uint32_t rank = tc::cluster_ctarank();         // 0 = leader (issues the pair MMAs), 1 = peer
   // head weights live in shared memory: with 224 KB of it carved out there is no L1 left to cache them
   float* sm = reinterpret_cast<float*>(smem + MlpSmem::kHead);
   for (int i = threadIdx.x; i < MlpSmem::kHeadFloats; i += blockDim.x) sm[i] = a.small[i];
@@ -155,45 +159,67 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
   // (barrier addresses, descriptors, counters) on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kRingSlots; ++i) { tc::mbar_init(bar_full + 8 * i, 1); tc::mbar_init(bar_empty + 8 * i, 2); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(bar_acc + 8 * i, 1); tc::mbar_init(bar_act + 8 * i, 128); }
+    // leader full[i]: its own expect_tx arrival + the peer's relayed arrival; peer full[i]: its own only
+    for (int i = 0; i < kRingSlots; ++i) { tc::mbar_init(bar_full + 8 * i, rank == 0 ? 2 : 1); tc::mbar_init(bar_empty + 8 * i, 2); }
+    // act_ready lives in the leader: 128 epilogue threads of each CTA arrive on it
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(bar_acc + 8 * i, 1); tc::mbar_init(bar_act + 8 * i, 256); }
     tc::mbar_init(bar_skew, 1);
     tc::fence_mbar_init();
   }
-  if (warp == 8) tc::tmem_alloc(tc::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+  if (warp == 8) tc::tmem_alloc_pair(tc::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
   tc::tc_fence_before();
-  __syncthreads();
+  tc::cluster_sync();                                  // both CTAs' barriers exist before any remote arrive / multicast commit
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const Program& P = a.prog;
-  const int n_pairs = (a.n_tiles + 1) >> 1;
+  const int n_quads = (a.n_tiles + 3) >> 2;            // 4 tiles per cluster iteration: tile = 4*quad + 2*slot + rank
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
   if (warp == 8) {
-    // ===================== weight loader =====================
+    // ===================== weight loader (both CTAs: this CTA's N/2 rows of every slab) =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
         for (int si = 0; si < P.n_steps; ++si) {
           const Step& st = P.s[si];
-          const uint32_t bytes = (uint32_t)st.n * 32u;
+          const uint32_t bytes = (uint32_t)st.n * 16u;
           const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
-          const uint8_t* src = a.packed + st.w_off;
+          const uint8_t* src = a.packed + st.w_off + rank * bytes;
           for (int k = 0; k < total; ++k, ++it) {
             const uint32_t slot = it % kRingSlots, ph = (it / kRingSlots) & 1u;
             tc::mbar_wait(bar_empty + 8 * slot, ph ^ 1u);
             tc::mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
-            tc::bulk_g2s(s_ring + slot * kRingSlotBytes, src + (size_t)k * bytes, bytes, bar_full + 8 * slot);
+            tc::bulk_g2s(s_ring + slot * kRingSlotBytes, src + (size_t)k * (2u * bytes), bytes, bar_full + 8 * slot);
+          }
+        }
+      }
+      // tail: every slab consumed (all multicast commits onto this CTA's empty barriers have landed) before exit
+      for (int t = 0; t < kRingSlots; ++t, ++it) tc::mbar_wait(bar_empty + 8 * (it % kRingSlots), ((it / kRingSlots) & 1u) ^ 1u);
+    }
+    __syncwarp();
+  } else if (warp >= 9 && rank != 0) {
+    // ===================== peer: relay "my half of slab j has landed" to the leader's full barrier =====================
+    if (warp == 9 && lane == 0) {
+      const uint32_t leader_full = tc::mapa(bar_full, 0);
+      uint32_t it = 0;
+      for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
+        for (int si = 0; si < P.n_steps; ++si) {
+          const int total = P.s[si].act_ksteps + P.s[si].enc_ksteps + P.s[si].bias_kstep;
+          for (int k = 0; k < total; ++k, ++it) {
+            const uint32_t slot = it % kRingSlots;
+            tc::mbar_wait(bar_full + 8 * slot, (it / kRingSlots) & 1u);
+            tc::mbar_arrive_cluster(leader_full + 8 * slot);
           }
         }
       }
     }
     __syncwarp();
   } else if (warp >= 9) {
-    // ===================== MMA issuers: warp 9 -> tile slot 0, warp 10 -> tile slot 1 =====================
+    // ===================== leader MMA issuers: warp 9 -> tile slot 0, warp 10 -> tile slot 1 =====================
     // Each warp runs its loop with warp-uniform control flow (all lanes poll the barriers) and one
-    // elected lane issues the tcgen05 instructions.  The two warps share every weight slab: a ring
-    // slot is recycled once BOTH have committed their MMA on it (empty barriers count 2), which also
-    // bounds the skew between the two tiles to the ring depth.
+    // elected lane issues the cta_group::2 instructions (M = 256: this CTA's tile + the peer's tile of the
+    // same slot).  The two warps share every weight slab: a ring slot is recycled once BOTH have
+    // committed their MMA on it (empty barriers count 2, commit multicast to both CTAs).
     const int slot = warp - 9;
     const uint32_t s_act = s_base + MlpSmem::kAct + slot * kActBytes;
     const uint32_t s_enc = s_base + MlpSmem::kEnc + slot * kEncBytes;
@@ -203,40 +229,41 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
     const uint32_t a_lbo = ((uint32_t)kKcoreBytes >> 4) << 16;                              // LBO = 2048 B
     const uint32_t act_lo = a_lbo | ((s_act & 0x3FFFFu) >> 4), enc_lo = a_lbo | ((s_enc & 0x3FFFFu) >> 4);
     const uint32_t ring_lo = (s_ring & 0x3FFFFu) >> 4;
+    const int skew = a.skew;
     uint32_t it = 0, act_phase = 0, skew_phase = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
       for (int si = 0; si < P.n_steps; ++si, ++act_phase) {
         const int n = P.s[si].n, act_ks = P.s[si].act_ksteps, enc_ks = P.s[si].enc_ksteps;
         const int total = act_ks + enc_ks + P.s[si].bias_kstep;
-        const uint32_t idesc = tc::umma_idesc_bf16(128, n, 0, 0);
-        const uint32_t b_lo = ((((uint32_t)n * 16u) >> 4) << 16) | ring_lo;
-        tc::mbar_wait(my_act, act_phase & 1u);
+        const uint32_t idesc = tc::umma_idesc_bf16(256, n, 0, 0);
+        const uint32_t b_lo = ((((uint32_t)n * 8u) >> 4) << 16) | ring_lo;      // LBO = (N/2 rows) * 16 B
+        tc::mbar_wait_cluster(my_act, act_phase & 1u);
         tc::tc_fence_after();
         long long* tr = (a.trace != nullptr && blockIdx.x == 0 && lane == 0)
-                            ? a.trace + ((size_t)((pair / gridDim.x) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
+                            ? a.trace + ((size_t)((quad / n_clusters) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
         if (tr) tr[0] = clock64();
-        // De-synchronise the two tiles: tile 1 enters a deep layer only when tile 0 is one ring depth
-        // (8 k-steps) into it, and the shared ring keeps tile 0 at most that far ahead -- so one tile's
-        // epilogue runs under the other tile's MMAs instead of both idling the tensor pipe together.
-        const bool deep = total > kRingSlots;           // every layer except fc1 (K=64) / the first dgrad step (K=128)
+        // De-synchronise the two tile slots: slot 1 enters a deep layer only when slot 0 is `skew` k-steps
+        // into it; the 16-slot ring (slabs stay until BOTH slots consumed them) lets slot 0 keep that lead
+        // with slabs to spare for the load latency -- so one slot's epilogue runs under the other's MMAs.
+        const bool deep = total > skew;                 // every layer except fc1 (K=64) / the first dgrad step (K=128)
         if (deep && slot == 1) { tc::mbar_wait(bar_skew, skew_phase & 1u); }
         if (deep) ++skew_phase;
         for (int k = 0; k < total; ++k) {
           const uint32_t j = it + (uint32_t)k;
           const uint32_t rs = j & (kRingSlots - 1);
-          tc::mbar_wait(bar_full + 8 * rs, (j >> 3) & 1u);
+          tc::mbar_wait_cluster(bar_full + 8 * rs, (j / kRingSlots) & 1u);
           tc::tc_fence_after();
           const int e = k - act_ks;                                           // >= enc_ks: the "ones" k-step (ENC k-step 3)
           const uint32_t a_lo = (e < 0) ? act_lo + (uint32_t)k * ((2 * kKcoreBytes) >> 4)
                                         : enc_lo + (uint32_t)(e < enc_ks ? e : 3) * ((2 * kKcoreBytes) >> 4);
           if (tc::elect_one()) {
-            tc::umma_bf16(d_tmem, desc_hi | a_lo, desc_hi | (b_lo + rs * (kRingSlotBytes >> 4)), idesc, k > 0 ? 1u : 0u);
-            tc::umma_commit(bar_empty + 8 * rs);
-            if (deep && slot == 0 && k == kRingSlots - 1) tc::mbar_arrive(bar_skew);
+            tc::umma_bf16_pair(d_tmem, desc_hi | a_lo, desc_hi | (b_lo + rs * (kRingSlotBytes >> 4)), idesc, k > 0 ? 1u : 0u);
+            tc::umma_commit_pair(bar_empty + 8 * rs, 3);
+            if (deep && slot == 0 && k == skew - 1) tc::mbar_arrive(bar_skew);
           }
           __syncwarp();
         }
-        if (tc::elect_one()) tc::umma_commit(my_acc);
+        if (tc::elect_one()) tc::umma_commit_pair(my_acc, 3);
         __syncwarp();
         if (tr) tr[1] = clock64();
         it += (uint32_t)total;
@@ -249,12 +276,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
     const uint32_t s_act = s_base + MlpSmem::kAct + slot * kActBytes;
     const uint32_t s_enc = s_base + MlpSmem::kEnc + slot * kEncBytes;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256 * slot;
-    const uint32_t my_acc = bar_acc + 8 * slot, my_act = bar_act + 8 * slot;
+    const uint32_t my_acc = bar_acc + 8 * slot;
+    const uint32_t leader_act = tc::mapa(bar_act + 8 * slot, 0);   // "A tile of this slot is ready" lives in the leader
     const bool train = (a.stash != nullptr);
     uint32_t acc_phase = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int tile = 2 * pair + slot;
-      const bool tile_ok = tile < a.n_tiles;           // odd tile count: the last pair's second slot is a phantom
+    for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
+      const int tile = 4 * quad + 2 * slot + (int)rank;
+      const bool tile_ok = tile < a.n_tiles;           // tile count not a multiple of 4: the last quad has phantom tiles
       const int64_t grow = (int64_t)tile * 128 + row;
       const bool valid = tile_ok && grow < a.n_rows;
       uint8_t* stash_tile = (train && tile_ok) ? a.stash + (size_t)tile * a.stash_tile_bytes : nullptr;
@@ -314,7 +342,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
         }
       }
       tc::fence_proxy_async_smem();
-      tc::mbar_arrive(my_act);
+      if (rank == 0) tc::mbar_arrive(bar_act + 8 * slot); else tc::mbar_arrive_cluster(leader_act);
 
       // ---------------- layer steps ----------------
       for (int si = 0; si < P.n_steps; ++si) {
@@ -327,7 +355,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
         tc::mbar_wait(my_acc, acc_phase & 1u); ++acc_phase;
         tc::tc_fence_after();
         long long* tr = (a.trace != nullptr && blockIdx.x == 0 && row == 0)
-                            ? a.trace + ((size_t)((pair / gridDim.x) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
+                            ? a.trace + ((size_t)((quad / n_clusters) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
         if (tr) tr[2] = clock64();
         const int n_units = st.n >> 6;                 // 64 accumulator columns per TMEM load (4 or 2 units, even)
         const bool is_rgb = (MODE == MODE_FWD) && (st.flags & EPI_RGB) != 0;
@@ -415,7 +443,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
         }
         tc::tc_fence_before();                         // TMEM reads retired before the next MMA overwrites
         tc::fence_proxy_async_smem();                  // ACT writes visible to UMMA
-        if (!(st.flags & EPI_LAST)) tc::mbar_arrive(my_act);   // the next layer's MMAs may start NOW
+        if (!(st.flags & EPI_LAST)) {                  // the next layer's MMAs may start NOW
+          if (rank == 0) tc::mbar_arrive(bar_act + 8 * slot); else tc::mbar_arrive_cluster(leader_act);
+        }
         if (tr) tr[3] = clock64();
 
         // ---- everything below is off the MMA -> epilogue -> MMA critical path ----
@@ -469,8 +499,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_
     }
   }
   tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem_base, 512);
+  tc::cluster_sync();                                  // no remote arrive / multicast commit may target a CTA that has exited
+  if (warp == 8) tc::tmem_dealloc_pair(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -482,11 +512,13 @@ __global__ void pack_images_kernel(const float* __restrict__ params, Program pro
   const int n_elems = total_k * st.n;
   __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(packed + st.w_off);
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_elems; idx += gridDim.x * blockDim.x) {
-    // idx enumerates the destination linearly: [kstep][kc][n][8]
+    // idx enumerates the destination linearly: [kstep][half][kc][n_local][8] (half h = rows h*N/2.. of CTA rank h)
     const int j = idx & 7;
-    const int n = (idx >> 3) % st.n;
-    const int kc_lin = (idx >> 3) / st.n;              // = kstep*2 + kc
-    const int kk = kc_lin * 8 + j;
+    const int nh = st.n >> 1;
+    const int nl = (idx >> 3) % nh;
+    const int r2 = (idx >> 3) / nh;                    // = (kstep*2 + half)*2 + kc
+    const int n = ((r2 >> 1) & 1) * nh + nl;
+    const int kk = ((r2 >> 2) * 2 + (r2 & 1)) * 8 + j;
     float v = 0.0f;
     if (n < st.p_rows) {
       if (st.p_transpose) {

@@ -9,8 +9,9 @@
 //   * the no-swizzle MN-major canonical layout (LBO = 128 B, SBO = row_count*16 B) when the row
 //     (sample) axis is the contraction axis (wgrad operands),
 // so tiles move between SMEM and HBM with plain 1-D bulk copies and no re-tiling.
-// Packed weights use the same form with rows = output features, one image per K=16 step:
-//     [k_step][k_core 0..1][n][8]   (n*32 B per k-step).
+// Packed weights use the same form with rows = output features, one image per K=16 step, split
+// into the halves the two CTAs of a pair hold:
+//     [k_step][half 0..1][k_core 0..1][n_local 0..N/2-1][8]   (N*32 B per k-step, N*16 B per CTA).
 #pragma once
 #include <stdint.h>
 
@@ -21,8 +22,9 @@ constexpr int kNumLinear = 13;          // fc1, fc_layers x4, skip, fc_layers2 x
 constexpr int kKcoreBytes = 2048;       // 128 rows x 16 B
 constexpr int kActBytes = 32 * kKcoreBytes;   // 256 channels = 64 KB
 constexpr int kEncBytes = 8 * kKcoreBytes;    // 64 channels  = 16 KB
-constexpr int kRingSlots = 8;                 // = one half of a K=256 layer: both resident tiles share every slab
-constexpr int kRingSlotBytes = 256 * 32;      // one K=16 step of an N=256 layer = 8 KB
+constexpr int kRingSlots = 16;                // one K=256 layer: both resident tile slots share every slab
+constexpr int kRingSlotBytes = 128 * 32;      // one CTA's half (N/2 = 128 rows) of a K=16 step of an N=256 layer = 4 KB
+constexpr int kSkew = 9;                      // k-steps tile slot 1 runs behind slot 0 (~ one epilogue of MMA time)
 
 // epilogue flags
 enum : int32_t {

@@ -73,4 +73,54 @@ __global__ void __launch_bounds__(128) selftest_umma_kernel(int variant, float* 
   if (warp == 0) tc::tmem_dealloc(tmem, 64);
 }
 
+// variant 2: CTA-pair form (cta_group::2), K-major operands: D[256x64] = A[256x32] . B[64x32]^T with rows
+// 128r..128r+127 of A and B rows 32r..32r+31 in CTA r; the leader issues, the commit is multicast to both.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) selftest_umma_pair_kernel(float* result) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t s_a = tc::smem_u32(smem), s_b = s_a + 16384;
+  const int t = threadIdx.x, warp = t >> 5;
+  const int rank = (int)tc::cluster_ctarank();
+  __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(smem + 16384);
+  for (int i = t; i < 128 * 32; i += 128) { const int m = i / 32, k = i % 32; A[(k / 8) * 1024 + m * 8 + (k % 8)] = __float2bfloat16(st_val(rank * 128 + m, k, 1)); }
+  for (int i = t; i < 32 * 32; i += 128) { const int n = i / 32, k = i % 32; B[(k / 8) * 256 + n * 8 + (k % 8)] = __float2bfloat16(st_val(rank * 32 + n, k, 2)); }
+  if (t == 0) { tc::mbar_init(tc::smem_u32(&bar), 1); tc::fence_mbar_init(); }
+  if (warp == 0) tc::tmem_alloc_pair(tc::smem_u32(&tmem_slot), 64);
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  tc::cluster_sync();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (rank == 0 && t == 0) {
+    const uint32_t idesc = tc::umma_idesc_bf16(256, 64, 0, 0);
+    for (int ks = 0; ks < 2; ++ks)
+      tc::umma_bf16_pair(tmem, tc::umma_smem_desc(s_a + ks * 4096, 2048, 128), tc::umma_smem_desc(s_b + ks * 1024, 512, 128), idesc, ks > 0);
+    tc::umma_commit_pair(tc::smem_u32(&bar), 3);
+  }
+  tc::mbar_wait(tc::smem_u32(&bar), 0);
+  tc::tc_fence_after();
+  float max_err = 0.0f, checksum = 0.0f;
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t v[32];
+    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ch * 32, v);
+    tc::tmem_wait_ld();
+    for (int j = 0; j < 32; ++j) {
+      const int n = ch * 32 + j;
+      float ref = 0.0f;
+      for (int k = 0; k < 32; ++k) ref += st_val(rank * 128 + t, k, 1) * st_val(n, k, 2);
+      float e = fabsf(ref - __uint_as_float(v[j]));
+      if (!(e < 1e30f)) e = 1e30f;
+      max_err = fmaxf(max_err, e);
+      checksum += fabsf(ref);
+    }
+  }
+  atomicMax(reinterpret_cast<int*>(result), __float_as_int(max_err));
+  atomicAdd(result + 1, checksum);
+  tc::tc_fence_before();
+  tc::cluster_sync();
+  if (warp == 0) tc::tmem_dealloc_pair(tmem, 64);
+}
+
 }  // namespace nerf

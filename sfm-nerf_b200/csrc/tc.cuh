@@ -47,6 +47,51 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- CTA pair (cluster of 2) --
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {        // every thread of both CTAs
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> the same offset in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier of another CTA of the cluster (address from mapa).  Default semantics (release at CTA
+// scope), as CUTLASS's ClusterBarrier does: the .release.cluster form carries a cluster-wide fence that costs
+// ~600 cycles per arrive (measured: it throttled the slab relay to one k-step per 635 cycles).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// wait on a local mbarrier that CTAs of the whole cluster arrive on (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0 && (clock64() - t0) > 4000000000LL) {
+      printf("nerf_b200: cluster mbarrier timeout block %d thread %d bar %u parity %u\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- bulk async copies --------
 // global -> shared, completion signalled on an mbarrier (complete_tx::bytes).  16 B aligned.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
@@ -89,6 +134,14 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t n_cols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t n_cols) {    // same warp
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(n_cols) : "memory");
+}
+// CTA-pair allocation: one warp of EACH CTA of the pair executes it (and later the dealloc)
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t n_cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(n_cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t n_cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(n_cols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -147,6 +200,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// CTA-pair forms (issued by ONE thread of the leader CTA, rank 0): D[256 x N] = A[256 x 16] . B[N x 16]^T with
+// rows 0-127 of A and D in the leader, rows 128-255 in the peer, B rows 0..N/2-1 in the leader's shared memory
+// and N/2..N-1 in the peer's -- all at the SAME shared-memory / TMEM offsets in both CTAs.
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of `cta_mask` once all previously issued pair MMAs completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
 // ---------------------------------------------------------------- misc ---------------------

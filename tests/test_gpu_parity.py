@@ -53,7 +53,7 @@ def _decode_block(blob, n_ch):
 # ------------------------------------------------------------------------------------------
 def test_umma_descriptor_selftests(pkg):
     lib = pkg._lib.load()
-    for variant in (0, 1):
+    for variant in (0, 1, 2):       # 2 = CTA-pair (cta_group::2) form
         res = (ctypes.c_float * 4)()
         rc = lib.nerf_selftest_umma(variant, res)
         assert rc == 0, f"variant {variant}: rc={rc} ({pkg._lib.error_string(rc)}), max_err={res[0]}, checksum={res[1]}"
