@@ -162,6 +162,11 @@ int nerf_selftest_umma(int variant, float* result_host);
  * [pair][step 0..11][tile slot 0..1][4] = (MMA issue start, MMA issue end, accumulator ready seen by
  * the epilogue, next-layer release) into it (int64; 8 pairs fit in 8*12*2*4 entries).  NULL disables. */
 int nerf_debug_trace(void* device_buffer);
+/* Diagnostics: issue-rate microbenchmark of 128x256x16 UMMAs on one SM (variant: 0 one thread / one accumulator,
+ * 1 one thread / two accumulators, 2 two threads / one accumulator each, 3 one thread / N=128 halves,
+ * 4 two threads / same accumulator).  cycles_host[0] = SM cycles for n_mma MMAs, cycles_host[1] = n_mma.
+ * Synchronises the device and allocates; not part of the hot path. */
+int nerf_debug_umma_rate(int variant, int n_mma, long long* cycles_host);
 
 #ifdef __cplusplus
 }

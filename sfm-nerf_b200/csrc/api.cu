@@ -82,7 +82,6 @@ void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t
   a.stash_tile_bytes = m.stash_tile_bytes; a.dstash_tile_bytes = m.dstash_tile_bytes;
   a.trace = g_trace;
   { const char* e = getenv("NERF_EXP"); a.exp_flags = e ? atoi(e) : 0; }
-  { const char* e = getenv("NERF_SKEW"); a.skew = e ? atoi(e) : kSkew; if (a.skew < 1 || a.skew >= kRingSlots) a.skew = kSkew; }
   a.st_pe = m.st_pe; a.st_de = m.st_de; a.st_r1 = m.st_r1; a.st_mask = m.st_mask; a.ds_y10 = m.ds_y[10]; a.ds_sr = m.ds_sr;
 }
 
@@ -430,6 +429,27 @@ int nerf_selftest_umma(int variant, float* result_host) {
   cudaFree(d);
   if (e != cudaSuccess) return (int)e;
   return (result_host[0] == 0.0f && result_host[1] > 0.0f) ? NERF_OK : NERF_ERR_SELFTEST;
+}
+
+// diagnostics: UMMA issue-rate microbenchmark (selftest.cuh); cycles_host[0] = cycles, [1] = MMAs
+int nerf_debug_umma_rate(int variant, int n_mma, long long* cycles_host) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (variant < 0 || variant > 80 || n_mma < 2 || !cycles_host) return NERF_ERR_ARG;
+  long long* d = nullptr;
+  NERF_CUDA_TRY(cudaMalloc(&d, 2 * sizeof(long long)));
+  cudaMemset(d, 0, 2 * sizeof(long long));
+  cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 131072);
+  if (variant >= 5) {                                  // 5..9: CTA-pair variants 0..4; 10..25: 5 + loop-ingredient flags
+    cudaFuncSetAttribute(umma_pair_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 65536);
+    umma_pair_rate_kernel<<<2, 128, 65536 + 65536>>>(variant - 5, n_mma, d);
+  } else
+  umma_rate_kernel<<<1, 128, 65536 + 131072>>>(variant, n_mma, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? NERF_OK : (int)e;
 }
 
 }  // extern "C"

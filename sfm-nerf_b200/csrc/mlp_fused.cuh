@@ -8,16 +8,21 @@
 // CTA PAIR (cluster of 2 = the two SMs of a TPC, tcgen05 cta_group::2).  Every CTA keeps TWO 128-row
 // tiles resident (2 x 64 KB activation tiles in shared memory, 2 x 256 TMEM columns); tile slot s of
 // the leader (rank 0) and of the peer (rank 1) form one M = 256 UMMA, so a weight slab (one K=16 step)
-// is split between the two CTAs: each loads and holds only its N/2 rows (4 KB).  Per SM that halves
-// the B-operand shared-memory reads and the L2 weight traffic, and the same 64 KB of ring now holds
-// 16 k-steps instead of 8 -- deep enough to keep tile slot 1 a steady ~9 k-steps behind slot 0, so one
-// slot's epilogue runs under the other slot's MMAs instead of both idling the tensor pipe together.
+// is split between the two CTAs: each loads and holds only its N/2 rows (4 KB), which halves the
+// B-operand shared-memory reads per SM.
+// SCHEDULE: one warp issues every MMA of the pair in the fixed order
+//     slot 0 layer L (all k-steps) | slot 1 layer L | slot 0 layer L+1 | slot 1 layer L+1 | ...
+// and the tensor pipe executes in issue order, so slot 0's epilogue of layer L runs exactly under slot 1's MMAs of
+// layer L and vice versa: the pipe only idles if an epilogue takes longer than a layer of MMAs.  The loader streams the
+// slabs in that same order through one 16-slot ring (each layer's slabs twice, once per slot: 32 B/clk/SM from L2).
+// Sharing one pass of slabs between the slots was measured too: it ties the slots to within one ring of each other,
+// too close to hide an epilogue; a private 8-slot ring per slot covers less than the load latency.
 //   warps 0-3 / 4-7 : epilogue of tile slot 0 / 1 (thread = row = TMEM lane), both CTAs:
 //                     TMEM -> regs -> ReLU+bf16 pack (one cvt) -> next layer's A tile, in place
 //   warp 8          : weight loader (1-D bulk copies of this CTA's half slabs into the ring), both CTAs
-//   warps 9 / 10    : leader: MMA issuer of tile slot 0 / 1 (one elected lane), tcgen05.mma
-//                     cta_group::2 kind::f16 256xNx16, completion multicast to both CTAs' barriers;
-//                     peer: warp 9 relays "my half slab has landed" to the leader's full barriers
+//   warp 9          : leader: MMA issuer (one elected lane), tcgen05.mma cta_group::2 kind::f16 256xNx16,
+//                     completion multicast to both CTAs' barriers;
+//                     peer: relays "my half slab has landed" to the leader's full barriers
 // Biases ride on the MMA: channel 63 of the encoding tile is the constant 1.0 and the packed weight
 // image carries the bias in that K column, so the epilogue does no bias loads or adds.
 #pragma once
@@ -29,7 +34,11 @@ namespace nerf {
 
 constexpr int MODE_FWD = 0;
 constexpr int MODE_BWD = 1;
-constexpr int kMlpThreads = 352;    // 8 epilogue warps + loader + 2 MMA issuers
+// 8 epilogue warps + loader + MMA issuer (leader) / slab relay (peer) + 2 idle warps: the CTA must be a whole number of
+// 128-thread warpgroups.  tcgen05.ld lets warp w touch TMEM lanes 32*(w%4).., and only for warpgroup-aligned CTAs is a
+// warp's index in the CTA tied to the SM sub-partition it runs on: with 320 threads the epilogue warps were seen in
+// rotated hardware slots (cuda-gdb) and tcgen05.ld raised "misaligned address", depending on what ran on the SM before.
+constexpr int kMlpThreads = 384;
 
 struct MlpArgs {
   const uint8_t* packed;     // weight images
@@ -50,7 +59,6 @@ struct MlpArgs {
   int32_t stash_tile_bytes, dstash_tile_bytes;
   int32_t st_pe, st_de, st_r1, st_mask, ds_y10, ds_sr;
   int32_t exp_flags;         // diagnostics (NERF_EXP env): 1 = skip stash stores
-  int32_t skew;              // k-steps tile slot 1 stays behind slot 0 inside a layer (NERF_SKEW env, default kSkew)
   long long* trace;          // diagnostics: per-(pair,step,slot) clock64 stamps of CTA 0 (or null)
   Program prog;
 };
@@ -60,12 +68,14 @@ struct MlpSmem {
   static constexpr int kEnc = kAct + 2 * kActBytes;                // 2 x 16 KB
   static constexpr int kRing = kEnc + 2 * kEncBytes;               // 16 x 4 KB (this CTA's half of every slab)
   static constexpr int kBars = kRing + kRingSlots * kRingSlotBytes;
-  // barriers (8 B each): full[16] @0, empty[16] @128, acc_full[2] @256, act_ready[2] @272, skew @288; tmem ptr @304
-  static constexpr int kHead = kBars + 320;                        // fp32 head tables (w_d, b_d, W2, b2): 648 floats
+  // barriers (8 B each): full[16] @0, empty[16] @128, acc_full[2] @256, act_ready[2] @272, drain @288; tmem ptr @320
+  static constexpr int kTmemPtr = kBars + 320;
+  static constexpr int kHead = kBars + 384;                        // fp32 head tables (w_d, b_d, W2, b2): 648 floats
   static constexpr int kHeadFloats = 648;
   static constexpr int kTotal = kHead + kHeadFloats * 4;
 };
 static_assert(MlpSmem::kTotal <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+static_assert(MlpSmem::kBars + 296 <= MlpSmem::kTmemPtr && MlpSmem::kTmemPtr + 4 <= MlpSmem::kHead, "barriers / TMEM pointer / head tables overlap");
 
 // sin/cos positional encoding of one scalar for level `i` from the exact decomposition
 // a_i = 2^i * fl32(fl32(pi) * x) (NeRFModel.py:151-156): the angle is carried in
@@ -148,8 +158,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   const uint32_t s_ring = s_base + MlpSmem::kRing;
   const uint32_t s_bar = s_base + MlpSmem::kBars;
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 128, bar_acc = s_bar + 256, bar_act = s_bar + 272;
-  const uint32_t bar_skew = s_bar + 288;
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kBars + 304);
+  const uint32_t bar_drain = s_bar + 288;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kTmemPtr);
   const uint32_t rank = tc::cluster_ctarank();         // 0 = leader (issues the pair MMAs), 1 = peer
   // head weights live in shared memory: with 224 KB of it carved out there is no L1 left to cache them
   float* sm = reinterpret_cast<float*>(smem + MlpSmem::kHead);
@@ -160,10 +170,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     // leader full[i]: its own expect_tx arrival + the peer's relayed arrival; peer full[i]: its own only
-    for (int i = 0; i < kRingSlots; ++i) { tc::mbar_init(bar_full + 8 * i, rank == 0 ? 2 : 1); tc::mbar_init(bar_empty + 8 * i, 2); }
+    for (int i = 0; i < kRingSlots; ++i) { tc::mbar_init(bar_full + 8 * i, rank == 0 ? 2 : 1); tc::mbar_init(bar_empty + 8 * i, 1); }
     // act_ready lives in the leader: 128 epilogue threads of each CTA arrive on it
     for (int i = 0; i < 2; ++i) { tc::mbar_init(bar_acc + 8 * i, 1); tc::mbar_init(bar_act + 8 * i, 256); }
-    tc::mbar_init(bar_skew, 1);
+    tc::mbar_init(bar_drain, 1);                       // the MMA warp: "all my MMAs have completed" (multicast to both CTAs)
     tc::fence_mbar_init();
   }
   if (warp == 8) tc::tmem_alloc_pair(tc::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
@@ -176,100 +186,153 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
   if (warp == 8) {
-    // ===================== weight loader (both CTAs: this CTA's N/2 rows of every slab) =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
-        for (int si = 0; si < P.n_steps; ++si) {
-          const Step& st = P.s[si];
-          const uint32_t bytes = (uint32_t)st.n * 16u;
-          const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
-          const uint8_t* src = a.packed + st.w_off + rank * bytes;
-          for (int k = 0; k < total; ++k, ++it) {
-            const uint32_t slot = it % kRingSlots, ph = (it / kRingSlots) & 1u;
-            tc::mbar_wait(bar_empty + 8 * slot, ph ^ 1u);
-            tc::mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
-            tc::bulk_g2s(s_ring + slot * kRingSlotBytes, src + (size_t)k * (2u * bytes), bytes, bar_full + 8 * slot);
-          }
-        }
-      }
-      // tail: every slab consumed (all multicast commits onto this CTA's empty barriers have landed) before exit
-      for (int t = 0; t < kRingSlots; ++t, ++it) tc::mbar_wait(bar_empty + 8 * (it % kRingSlots), ((it / kRingSlots) & 1u) ^ 1u);
-    }
-    __syncwarp();
-  } else if (warp >= 9 && rank != 0) {
-    // ===================== peer: relay "my half of slab j has landed" to the leader's full barrier =====================
-    if (warp == 9 && lane == 0) {
-      const uint32_t leader_full = tc::mapa(bar_full, 0);
-      uint32_t it = 0;
-      for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
-        for (int si = 0; si < P.n_steps; ++si) {
-          const int total = P.s[si].act_ksteps + P.s[si].enc_ksteps + P.s[si].bias_kstep;
-          for (int k = 0; k < total; ++k, ++it) {
-            const uint32_t slot = it % kRingSlots;
-            tc::mbar_wait(bar_full + 8 * slot, (it / kRingSlots) & 1u);
-            tc::mbar_arrive_cluster(leader_full + 8 * slot);
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp >= 9) {
-    // ===================== leader MMA issuers: warp 9 -> tile slot 0, warp 10 -> tile slot 1 =====================
-    // Each warp runs its loop with warp-uniform control flow (all lanes poll the barriers) and one
-    // elected lane issues the cta_group::2 instructions (M = 256: this CTA's tile + the peer's tile of the
-    // same slot).  The two warps share every weight slab: a ring slot is recycled once BOTH have
-    // committed their MMA on it (empty barriers count 2, commit multicast to both CTAs).
-    const int slot = warp - 9;
-    const uint32_t s_act = s_base + MlpSmem::kAct + slot * kActBytes;
-    const uint32_t s_enc = s_base + MlpSmem::kEnc + slot * kEncBytes;
-    const uint32_t d_tmem = tmem_base + 256 * slot;
-    const uint32_t my_acc = bar_acc + 8 * slot, my_act = bar_act + 8 * slot;
-    const uint64_t desc_hi = (uint64_t)(((128u >> 4) & 0x3FFFu) | (1u << 14)) << 32;      // SBO = 128 B, version 1
-    const uint32_t a_lbo = ((uint32_t)kKcoreBytes >> 4) << 16;                              // LBO = 2048 B
-    const uint32_t act_lo = a_lbo | ((s_act & 0x3FFFFu) >> 4), enc_lo = a_lbo | ((s_enc & 0x3FFFFu) >> 4);
-    const uint32_t ring_lo = (s_ring & 0x3FFFFu) >> 4;
-    const int skew = a.skew;
-    uint32_t it = 0, act_phase = 0, skew_phase = 0;
+    // ===================== weight loader (both CTAs: this CTA's N/2 rows of every slab, every layer twice) ==========
+    // One slab per LANE, kLoadBatch slabs per trip: a single thread doing wait(empty) -> arrive.expect_tx -> bulk copy
+    // slab after slab is a chain of ~130-cycle barrier operations (~350 cycles per slab -- what limited every earlier
+    // variant of this kernel); across lanes the same operations issue together.
+    uint32_t it0 = 0;                                    // slabs issued before the current (layer, pass)
     for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
-      for (int si = 0; si < P.n_steps; ++si, ++act_phase) {
-        const int n = P.s[si].n, act_ks = P.s[si].act_ksteps, enc_ks = P.s[si].enc_ksteps;
-        const int total = act_ks + enc_ks + P.s[si].bias_kstep;
-        const uint32_t idesc = tc::umma_idesc_bf16(256, n, 0, 0);
-        const uint32_t b_lo = ((((uint32_t)n * 8u) >> 4) << 16) | ring_lo;      // LBO = (N/2 rows) * 16 B
-        tc::mbar_wait_cluster(my_act, act_phase & 1u);
-        tc::tc_fence_after();
-        long long* tr = (a.trace != nullptr && blockIdx.x == 0 && lane == 0)
-                            ? a.trace + ((size_t)((quad / n_clusters) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
-        if (tr) tr[0] = clock64();
-        // De-synchronise the two tile slots: slot 1 enters a deep layer only when slot 0 is `skew` k-steps
-        // into it; the 16-slot ring (slabs stay until BOTH slots consumed them) lets slot 0 keep that lead
-        // with slabs to spare for the load latency -- so one slot's epilogue runs under the other's MMAs.
-        const bool deep = total > skew;                 // every layer except fc1 (K=64) / the first dgrad step (K=128)
-        if (deep && slot == 1) { tc::mbar_wait(bar_skew, skew_phase & 1u); }
-        if (deep) ++skew_phase;
-        for (int k = 0; k < total; ++k) {
-          const uint32_t j = it + (uint32_t)k;
-          const uint32_t rs = j & (kRingSlots - 1);
-          tc::mbar_wait_cluster(bar_full + 8 * rs, (j / kRingSlots) & 1u);
-          tc::tc_fence_after();
-          const int e = k - act_ks;                                           // >= enc_ks: the "ones" k-step (ENC k-step 3)
-          const uint32_t a_lo = (e < 0) ? act_lo + (uint32_t)k * ((2 * kKcoreBytes) >> 4)
-                                        : enc_lo + (uint32_t)(e < enc_ks ? e : 3) * ((2 * kKcoreBytes) >> 4);
-          if (tc::elect_one()) {
-            tc::umma_bf16_pair(d_tmem, desc_hi | a_lo, desc_hi | (b_lo + rs * (kRingSlotBytes >> 4)), idesc, k > 0 ? 1u : 0u);
-            tc::umma_commit_pair(bar_empty + 8 * rs, 3);
-            if (deep && slot == 0 && k == skew - 1) tc::mbar_arrive(bar_skew);
+      for (int si = 0; si < P.n_steps; ++si) {
+        const Step& st = P.s[si];
+        const uint32_t bytes = (uint32_t)st.n * 16u;
+        const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
+        const uint8_t* src = a.packed + st.w_off + rank * bytes;
+        for (int pass = 0; pass < 2; ++pass) {           // slot 0's pass over the layer, then slot 1's
+          for (int k0 = 0; k0 < total; k0 += kLoadBatch) {
+            const int k = k0 + lane;
+            if (lane < kLoadBatch && k < total) {
+              const uint32_t it = it0 + (uint32_t)k;
+              const uint32_t rs = it % kRingSlots, ph = (it / kRingSlots) & 1u;
+              tc::mbar_wait(bar_empty + 8 * (rs | (uint32_t)(kCommitGroup - 1)), ph ^ 1u);   // slots are released in groups
+              tc::mbar_arrive_expect_tx(bar_full + 8 * rs, bytes);
+              tc::bulk_g2s(s_ring + rs * kRingSlotBytes, src + (size_t)k * (2u * bytes), bytes, bar_full + 8 * rs);
+            }
+            __syncwarp();
+          }
+          it0 += (uint32_t)total;
+        }
+      }
+    }
+    if (lane == 0) {
+      // tail: every multicast commit onto this CTA's barriers has landed before it may exit.  Complete groups are
+      // waited for like a further load would; a trailing partial group is covered by the drain barrier, which the MMA
+      // warp commits to last (a ring barrier must never complete a phase the loader has not waited for yet: a second
+      // completion would alias the parity wait).
+      const uint32_t n_slabs = it0;
+      uint32_t it = it0;
+      for (int t = 0; t < kRingSlots; ++t, ++it) {
+        const uint32_t group_last = (it - kRingSlots) | (uint32_t)(kCommitGroup - 1);      // of the slab this wait covers
+        if (it >= (uint32_t)kRingSlots && group_last < n_slabs)
+          tc::mbar_wait(bar_empty + 8 * (group_last % kRingSlots), ((it / kRingSlots) & 1u) ^ 1u);
+      }
+      tc::mbar_wait(bar_drain, 0);
+    }
+    __syncwarp();
+  } else if (warp == 9 && rank != 0) {
+    // ===================== peer: relay "my half of slab j has landed" to the leader's full barrier =====================
+    // (one slab per lane, like the loader)
+    const uint32_t leader_full = tc::mapa(bar_full, 0);
+    uint32_t it0 = 0;
+    for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
+      for (int si = 0; si < P.n_steps; ++si) {
+        const int total = 2 * (P.s[si].act_ksteps + P.s[si].enc_ksteps + P.s[si].bias_kstep);
+        for (int k0 = 0; k0 < total; k0 += kLoadBatch) {
+          const int k = k0 + lane;
+          if (lane < kLoadBatch && k < total) {
+            const uint32_t it = it0 + (uint32_t)k;
+            const uint32_t rs = it % kRingSlots;
+            tc::mbar_wait(bar_full + 8 * rs, (it / kRingSlots) & 1u);
+            tc::mbar_arrive_cluster(leader_full + 8 * rs);
           }
           __syncwarp();
         }
-        if (tc::elect_one()) tc::umma_commit_pair(my_acc, 3);
-        __syncwarp();
-        if (tr) tr[1] = clock64();
-        it += (uint32_t)total;
+        it0 += (uint32_t)total;
       }
     }
-  } else {
+  } else if (warp == 9) {
+    // ===================== leader MMA issuer =====================
+    // The warp runs with warp-uniform control flow (all lanes poll the barriers) and one elected lane issues the
+    // cta_group::2 instructions (M = 256: this CTA's tile + the peer's tile of the same slot).  What shaped this loop
+    // (all measured, tools/umma_rate.py + tools/trace_mlp.py):
+    //  * consecutive UTCHMMAs that reuse the same uniform registers for their descriptors serialise on the previous
+    //    one's scoreboard (~225 cycles per MMA): k-steps are issued four at a time from ONE asm block whose eight
+    //    descriptors are live inputs (tc::umma_bf16_pair_x4), the A descriptors advancing linearly inside three runs
+    //    (activation k-steps, encoding k-steps, the bias k-step);
+    //  * any mbarrier operation costs the warp ~130 cycles: the four full barriers of a group are probed back to back
+    //    (independent try_waits overlap) and blocked on one by one only when a slab has not landed yet;
+    //  * ring slots are released (tcgen05.commit, multicast to both CTAs) per kCommitGroup = 2 k-steps.
+    const uint64_t desc_hi = (uint64_t)(((128u >> 4) & 0x3FFFu) | (1u << 14)) << 32;      // SBO = 128 B, version 1
+    const uint32_t a_lbo = ((uint32_t)kKcoreBytes >> 4) << 16;                              // LBO = 2048 B
+    const uint32_t ring_lo = (s_ring & 0x3FFFFu) >> 4;
+    constexpr uint32_t kStepLo = (2 * kKcoreBytes) >> 4;                                    // A descriptor advance per k-step
+    constexpr uint32_t kSlabLo = kRingSlotBytes >> 4;
+    uint32_t rs = 0, par = 0, act_phase = 0;                       // ring slot / parity of the next slab
+
+    for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
+      for (int si = 0; si < P.n_steps; ++si, ++act_phase) {
+        const int n = P.s[si].n, act_ks = P.s[si].act_ksteps, enc_ks = P.s[si].enc_ksteps, bias_ks = P.s[si].bias_kstep;
+        const uint32_t idesc = tc::umma_idesc_bf16(256, n, 0, 0);
+        const uint32_t b_lo = ((((uint32_t)n * 8u) >> 4) << 16) | ring_lo;      // LBO = (N/2 rows) * 16 B
+#pragma unroll 1
+        for (int slot = 0; slot < 2; ++slot) {
+          const uint32_t act_lo = a_lbo | (((s_base + MlpSmem::kAct + slot * kActBytes) & 0x3FFFFu) >> 4);
+          const uint32_t enc_lo = a_lbo | (((s_base + MlpSmem::kEnc + slot * kEncBytes) & 0x3FFFFu) >> 4);
+          const uint32_t d_tmem = tmem_base + 256 * slot;
+          tc::mbar_wait_cluster(bar_act + 8 * slot, act_phase & 1u);       // this slot's A tile of the layer is ready
+          tc::tc_fence_after();
+          long long* tr = (a.trace != nullptr && blockIdx.x == 0 && lane == 0)
+                              ? a.trace + ((size_t)((quad / n_clusters) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
+          if (tr) tr[0] = clock64();
+          int k_done = 0;
+#pragma unroll 1
+          for (int seg = 0; seg < 3; ++seg) {
+            int cnt = (seg == 0) ? act_ks : (seg == 1) ? enc_ks : bias_ks;
+            uint32_t a_cur = (seg == 0) ? act_lo : (seg == 1) ? enc_lo : enc_lo + 3u * kStepLo;     // bias: ENC k-step 3
+#pragma unroll 1
+            while (cnt > 0) {
+              const int kn = cnt < kWaitGroup ? cnt : kWaitGroup;
+              uint32_t ready = 1u;
+#pragma unroll
+              for (int q = 0; q < kWaitGroup; ++q) {
+                if (q < kn) ready &= (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * ((rs + q) & (kRingSlots - 1)), par ^ ((rs + q) >> 4));
+              }
+              if (!ready) {
+                for (int q = 0; q < kn; ++q) tc::mbar_wait_cluster(bar_full + 8 * ((rs + q) & (kRingSlots - 1)), par ^ ((rs + q) >> 4));
+              }
+              if (tc::elect_one()) {
+                if (kn == kWaitGroup) {
+                  const uint32_t s0 = rs & (kRingSlots - 1), s1 = (rs + 1) & (kRingSlots - 1), s2 = (rs + 2) & (kRingSlots - 1),
+                                 s3 = (rs + 3) & (kRingSlots - 1);
+                  tc::umma_bf16_pair_x4(d_tmem, desc_hi | a_cur, desc_hi | (a_cur + kStepLo), desc_hi | (a_cur + 2 * kStepLo),
+                                        desc_hi | (a_cur + 3 * kStepLo), desc_hi | (b_lo + s0 * kSlabLo), desc_hi | (b_lo + s1 * kSlabLo),
+                                        desc_hi | (b_lo + s2 * kSlabLo), desc_hi | (b_lo + s3 * kSlabLo), idesc, k_done > 0 ? 1u : 0u);
+                  tc::umma_commit_pair(bar_empty + 8 * ((s0 & 1u) ? s0 : s1), 3);   // the odd slot's barrier stands for its pair
+                  tc::umma_commit_pair(bar_empty + 8 * ((s0 & 1u) ? s2 : s3), 3);
+                } else {
+                  for (int q = 0; q < kn; ++q) {
+                    const uint32_t sl = (rs + q) & (kRingSlots - 1);
+                    tc::umma_bf16_pair(d_tmem, desc_hi | (a_cur + (uint32_t)q * kStepLo), desc_hi | (b_lo + sl * kSlabLo), idesc, (k_done + q) > 0 ? 1u : 0u);
+                    if (sl & 1u) tc::umma_commit_pair(bar_empty + 8 * sl, 3);
+                  }
+                }
+              }
+              __syncwarp();
+              rs += (uint32_t)kn;
+              if (rs >= (uint32_t)kRingSlots) { rs -= kRingSlots; par ^= 1u; }
+              a_cur += (uint32_t)kn * kStepLo;
+              cnt -= kn; k_done += kn;
+            }
+          }
+          if (tc::elect_one()) tc::umma_commit_pair(bar_acc + 8 * slot, 3);
+          __syncwarp();
+          if (tr) tr[1] = clock64();
+        }
+      }
+    }
+    // a trailing odd slab has no commit of its own: the drain barrier covers it (and every earlier commit)
+    if (tc::elect_one()) tc::umma_commit_pair(bar_drain, 3);
+    __syncwarp();
+  } else if (warp < 8) {
     // ===================== epilogue warpgroups (thread = row) =====================
     const int slot = warp >> 2;                        // tile slot of this warpgroup
     const int row = threadIdx.x & 127;                 // 0..127 == TMEM lane

@@ -22,9 +22,11 @@ constexpr int kNumLinear = 13;          // fc1, fc_layers x4, skip, fc_layers2 x
 constexpr int kKcoreBytes = 2048;       // 128 rows x 16 B
 constexpr int kActBytes = 32 * kKcoreBytes;   // 256 channels = 64 KB
 constexpr int kEncBytes = 8 * kKcoreBytes;    // 64 channels  = 16 KB
-constexpr int kRingSlots = 16;                // one K=256 layer: both resident tile slots share every slab
+constexpr int kRingSlots = 16;                // slabs in flight (the two tile slots take turns, each streams its own pass of a layer's slabs)
 constexpr int kRingSlotBytes = 128 * 32;      // one CTA's half (N/2 = 128 rows) of a K=16 step of an N=256 layer = 4 KB
-constexpr int kSkew = 9;                      // k-steps tile slot 1 runs behind slot 0 (~ one epilogue of MMA time)
+constexpr int kCommitGroup = 2;               // ring slots are released (one tcgen05.commit) per this many k-steps (the odd slot's barrier)
+constexpr int kLoadBatch = 4;                 // slabs the loader / relay warps handle per trip (one per lane; <= kRingSlots / 2)
+constexpr int kWaitGroup = 4;                 // k-steps whose full barriers an MMA warp polls back to back before issuing them
 
 // epilogue flags
 enum : int32_t {

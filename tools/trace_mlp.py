@@ -13,7 +13,7 @@ z = E.sample_z(n_rays, S, 2.0, 6.0, "cuda", perturb=True, seed=1)
 mode = sys.argv[1] if len(sys.argv) > 1 else "infer"
 stash = E.alloc_stash(st, n_rays * S) if mode != "infer" else None
 for _ in range(3): E.mlp_forward_rays(st, o, d, z, stash)
-buf = torch.zeros(8 * 12 * 2 * 4, dtype=torch.int64, device="cuda")
+buf = torch.zeros(8 * 12 * 2 * 4 + 576 + 288, dtype=torch.int64, device="cuda")
 s._lib.call("nerf_debug_trace", s._lib.ptr(buf))
 sr = E.mlp_forward_rays(st, o, d, z, stash)
 if mode == "dgrad":
@@ -22,7 +22,8 @@ if mode == "dgrad":
     s._lib.call("nerf_mlp_dgrad", s._lib.ptr(st.packed), st.layout, s._lib.ptr(stash), s._lib.ptr(sr), s._lib.ptr(dsr), n_rays * S, s._lib.ptr(dst), s._lib.stream_ptr())
 torch.cuda.synchronize()
 s._lib.call("nerf_debug_trace", None)
-t = buf.cpu().reshape(8, 12, 2, 4)
+full = buf.cpu()
+t = full[:768].reshape(8, 12, 2, 4)
 t0 = int(t[t > 0].min())
 print("mode", mode, "(cycles relative to first stamp; per step: slot: issue_start issue_end acc_seen released | issue_len epi_len)")
 for pair in (0, 1, 3):
@@ -32,3 +33,8 @@ for pair in (0, 1, 3):
             a, b, c, e = (int(x) - t0 for x in t[pair, si, slot])
             row.append(f"s{slot}: {a:7d} {b:7d} {c:7d} {e:7d} | {b-a:5d} {e-c:5d}")
         print(f"p{pair} L{si:2d}  " + "   ".join(row))
+
+g = t[1]  # steady-state iteration
+import numpy as np
+starts = np.array([int(g[si, 0, 0]) for si in range(1, 9)])
+print("steady-state period per layer (cycles, slot 0 issue_start deltas):", np.diff(starts).tolist())
