@@ -16,13 +16,14 @@
 // layer L and vice versa: the pipe only idles if an epilogue takes longer than a layer of MMAs.  The loader streams the
 // slabs in that same order through one 16-slot ring (each layer's slabs twice, once per slot: 32 B/clk/SM from L2).
 // Sharing one pass of slabs between the slots was measured too: it ties the slots to within one ring of each other,
-// too close to hide an epilogue; a private 8-slot ring per slot covers less than the load latency.
+// too close to hide an epilogue (also with the lane-parallel loaders); a private 8-slot ring per slot covers less
+// than the load latency.
 //   warps 0-3 / 4-7 : epilogue of tile slot 0 / 1 (thread = row = TMEM lane), both CTAs:
 //                     TMEM -> regs -> ReLU+bf16 pack (one cvt) -> next layer's A tile, in place
-//   warp 8          : weight loader (1-D bulk copies of this CTA's half slabs into the ring), both CTAs
+//   warps 8, 10     : weight loaders (1-D bulk copies of this CTA's half slabs into the ring), both CTAs
 //   warp 9          : leader: MMA issuer (one elected lane), tcgen05.mma cta_group::2 kind::f16 256xNx16,
-//                     completion multicast to both CTAs' barriers;
-//                     peer: relays "my half slab has landed" to the leader's full barriers
+//                     completion multicast to both CTAs' barriers
+//   warps 9, 11     : peer: relay "my half slab has landed" to the leader's full barriers
 // Biases ride on the MMA: channel 63 of the encoding tile is the constant 1.0 and the packed weight
 // image carries the bias in that K column, so the epilogue does no bias loads or adds.
 #pragma once
@@ -34,7 +35,7 @@ namespace nerf {
 
 constexpr int MODE_FWD = 0;
 constexpr int MODE_BWD = 1;
-// 8 epilogue warps + loader + MMA issuer (leader) / slab relay (peer) + 2 idle warps: the CTA must be a whole number of
+// 8 epilogue warps + 2 loaders + MMA issuer (leader) / 2 slab relays (peer): the CTA must be a whole number of
 // 128-thread warpgroups.  tcgen05.ld lets warp w touch TMEM lanes 32*(w%4).., and only for warpgroup-aligned CTAs is a
 // warp's index in the CTA tied to the SM sub-partition it runs on: with 320 threads the epilogue warps were seen in
 // rotated hardware slots (cuda-gdb) and tcgen05.ld raised "misaligned address", depending on what ran on the SM before.
@@ -185,12 +186,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   const int n_quads = (a.n_tiles + 3) >> 2;            // 4 tiles per cluster iteration: tile = 4*quad + 2*slot + rank
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
-  if (warp == 8) {
-    // ===================== weight loader (both CTAs: this CTA's N/2 rows of every slab, every layer twice) ==========
-    // One slab per LANE, kLoadBatch slabs per trip: a single thread doing wait(empty) -> arrive.expect_tx -> bulk copy
-    // slab after slab is a chain of ~130-cycle barrier operations (~350 cycles per slab -- what limited every earlier
-    // variant of this kernel); across lanes the same operations issue together.
-    uint32_t it0 = 0;                                    // slabs issued before the current (layer, pass)
+  if (warp == 8 || warp == 10) {
+    // ===================== weight loaders (both CTAs: this CTA's N/2 rows of every slab, every layer twice) ==========
+    // One slab per LANE, kLoadBatch slabs per trip, the two loader warps taking alternate trips: a single thread doing
+    // wait(empty) -> bulk copy -> arrive.expect_tx slab after slab is a chain of ~130-cycle barrier operations (~350
+    // cycles per slab -- what limited every earlier variant of this kernel); across lanes the same operations issue
+    // together, and two warps overlap their trips.  The copy is issued before the expect_tx arrival (the phase cannot
+    // complete while that arrival is pending, so the order is free) to get it on its way ~130 cycles earlier.
+    const int which = (warp - 8) >> 1;
+    uint32_t it0 = 0, chunk = 0;                         // slabs issued before the current (layer, pass); trip counter
     for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
       for (int si = 0; si < P.n_steps; ++si) {
         const Step& st = P.s[si];
@@ -198,14 +202,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
         const uint8_t* src = a.packed + st.w_off + rank * bytes;
         for (int pass = 0; pass < 2; ++pass) {           // slot 0's pass over the layer, then slot 1's
-          for (int k0 = 0; k0 < total; k0 += kLoadBatch) {
+          for (int k0 = 0; k0 < total; k0 += kLoadBatch, ++chunk) {
+            if ((int)(chunk & 1u) != which) continue;
             const int k = k0 + lane;
             if (lane < kLoadBatch && k < total) {
               const uint32_t it = it0 + (uint32_t)k;
               const uint32_t rs = it % kRingSlots, ph = (it / kRingSlots) & 1u;
               tc::mbar_wait(bar_empty + 8 * (rs | (uint32_t)(kCommitGroup - 1)), ph ^ 1u);   // slots are released in groups
-              tc::mbar_arrive_expect_tx(bar_full + 8 * rs, bytes);
               tc::bulk_g2s(s_ring + rs * kRingSlotBytes, src + (size_t)k * (2u * bytes), bytes, bar_full + 8 * rs);
+              tc::mbar_arrive_expect_tx(bar_full + 8 * rs, bytes);
             }
             __syncwarp();
           }
@@ -213,7 +218,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         }
       }
     }
-    if (lane == 0) {
+    if (warp == 8 && lane == 0) {
       // tail: every multicast commit onto this CTA's barriers has landed before it may exit.  Complete groups are
       // waited for like a further load would; a trailing partial group is covered by the drain barrier, which the MMA
       // warp commits to last (a ring barrier must never complete a phase the loader has not waited for yet: a second
@@ -228,25 +233,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
       tc::mbar_wait(bar_drain, 0);
     }
     __syncwarp();
-  } else if (warp == 9 && rank != 0) {
+  } else if ((warp == 9 || warp == 11) && rank != 0) {
     // ===================== peer: relay "my half of slab j has landed" to the leader's full barrier =====================
-    // (one slab per lane, like the loader)
+    // (one slab per lane, alternate trips per warp, like the loaders)
+    const int which = (warp - 9) >> 1;
     const uint32_t leader_full = tc::mapa(bar_full, 0);
-    uint32_t it0 = 0;
+    uint32_t it0 = 0, chunk = 0;
     for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
       for (int si = 0; si < P.n_steps; ++si) {
-        const int total = 2 * (P.s[si].act_ksteps + P.s[si].enc_ksteps + P.s[si].bias_kstep);
-        for (int k0 = 0; k0 < total; k0 += kLoadBatch) {
-          const int k = k0 + lane;
-          if (lane < kLoadBatch && k < total) {
-            const uint32_t it = it0 + (uint32_t)k;
-            const uint32_t rs = it % kRingSlots;
-            tc::mbar_wait(bar_full + 8 * rs, (it / kRingSlots) & 1u);
-            tc::mbar_arrive_cluster(leader_full + 8 * rs);
+        const int total = P.s[si].act_ksteps + P.s[si].enc_ksteps + P.s[si].bias_kstep;
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int k0 = 0; k0 < total; k0 += kLoadBatch, ++chunk) {
+            if ((int)(chunk & 1u) != which) continue;
+            const int k = k0 + lane;
+            if (lane < kLoadBatch && k < total) {
+              const uint32_t it = it0 + (uint32_t)k;
+              const uint32_t rs = it % kRingSlots;
+              tc::mbar_wait(bar_full + 8 * rs, (it / kRingSlots) & 1u);
+              tc::mbar_arrive_cluster(leader_full + 8 * rs);
+            }
+            __syncwarp();
           }
-          __syncwarp();
+          it0 += (uint32_t)total;
         }
-        it0 += (uint32_t)total;
       }
     }
   } else if (warp == 9) {

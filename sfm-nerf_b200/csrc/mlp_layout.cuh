@@ -25,7 +25,7 @@ constexpr int kEncBytes = 8 * kKcoreBytes;    // 64 channels  = 16 KB
 constexpr int kRingSlots = 16;                // slabs in flight (the two tile slots take turns, each streams its own pass of a layer's slabs)
 constexpr int kRingSlotBytes = 128 * 32;      // one CTA's half (N/2 = 128 rows) of a K=16 step of an N=256 layer = 4 KB
 constexpr int kCommitGroup = 2;               // ring slots are released (one tcgen05.commit) per this many k-steps (the odd slot's barrier)
-constexpr int kLoadBatch = 4;                 // slabs the loader / relay warps handle per trip (one per lane; <= kRingSlots / 2)
+constexpr int kLoadBatch = 2;                 // slabs a loader / relay warp handles per trip (one per lane): finer trips = shorter supply latency
 constexpr int kWaitGroup = 4;                 // k-steps whose full barriers an MMA warp polls back to back before issuing them
 
 // epilogue flags
