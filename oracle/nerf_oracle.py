@@ -173,7 +173,7 @@ def model_forward(sd, pos, direction, embed_pos_L=10, embed_direction_L=4, pos_e
 
     ``operand_dtype=torch.bfloat16`` restates the SAME network with the operand rounding of a
     bf16-tensor-core evaluation (weights, biases and inputs of the eleven 128/256-wide layers rounded
-    to bf16, fp32 accumulation, fp32 density / rgb heads).  It is NOT reference behaviour; tests use it
+    to bf16, fp32 accumulation; the fp32 density / rgb heads read the bf16-rounded activations).  It is NOT reference behaviour; tests use it
     to separate "kernel is wrong" from "bf16 operands differ from fp32" when comparing gradients,
     whose element-wise error is dominated by ReLU masks flipping for near-zero pre-activations."""
     q = lambda x: _round_st(x, operand_dtype)
@@ -195,9 +195,9 @@ def model_forward(sd, pos, direction, embed_pos_L=10, embed_direction_L=4, pos_e
     for i in range(3):
         h_full = F.relu(lin(f"fc_layers2.{i}", h))
         h = q(h_full); hidden.append(h)
-    density = F.softplus(head("density_layer", h_full))        # head reads the unrounded activation
+    density = F.softplus(head("density_layer", h))             # head reads the (rounded) activation tile
     feature = q(F.relu(lin("feature_layer", h))); hidden.append(feature)
-    r = F.relu(lin("rgb_layer1", torch.cat([feature, de], dim=-1))); hidden.append(r)
+    r = q(F.relu(lin("rgb_layer1", torch.cat([feature, de], dim=-1)))); hidden.append(r)
     rgb = torch.sigmoid(head("rgb_layer2", r))
     if return_hidden:
         return density, rgb, hidden

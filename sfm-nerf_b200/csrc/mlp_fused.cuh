@@ -433,37 +433,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         const bool is_rgb = (MODE == MODE_FWD) && (st.flags & EPI_RGB) != 0;
         const bool is_dens = (MODE == MODE_FWD) && (st.flags & EPI_DENSITY) != 0;
         const bool add_sigma = (MODE == MODE_BWD) && (st.flags & EPI_BWD_SIGMA) != 0;
-        const bool write_act = (MODE == MODE_BWD) || !is_rgb || train;
-        float dn[4] = {0.f, 0.f, 0.f, 0.f}, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
 
         // one 64-column unit: heads (rare steps), activation / mask, bf16 pack, store as the next A tile
         auto process = [&](uint32_t (&v)[64], int u) {
           if (MODE == MODE_FWD) {
-            if (is_dens) {                             // density head on the fp32 ReLU output (NeRFModel.py:192)
-              const float4* wd = reinterpret_cast<const float4*>(sm + a.sm_wd + u * 64);
-#pragma unroll
-              for (int j = 0; j < 64; j += 4) {
-                const float4 w4 = wd[j >> 2];
-                dn[0] = fmaf(fmaxf(__uint_as_float(v[j]), 0.f), w4.x, dn[0]);
-                dn[1] = fmaf(fmaxf(__uint_as_float(v[j + 1]), 0.f), w4.y, dn[1]);
-                dn[2] = fmaf(fmaxf(__uint_as_float(v[j + 2]), 0.f), w4.z, dn[2]);
-                dn[3] = fmaf(fmaxf(__uint_as_float(v[j + 3]), 0.f), w4.w, dn[3]);
-              }
-            }
-            if (is_rgb) {                              // rgb_layer2 on the fp32 ReLU output (NeRFModel.py:199-200)
-              const float4* w2 = reinterpret_cast<const float4*>(sm + a.sm_w2 + u * 64);
-#pragma unroll
-              for (int j = 0; j < 64; j += 4) {
-                const float4 wa = w2[j >> 2], wb = w2[32 + (j >> 2)], wc = w2[64 + (j >> 2)];
-                const float y0 = fmaxf(__uint_as_float(v[j]), 0.f), y1 = fmaxf(__uint_as_float(v[j + 1]), 0.f);
-                const float y2 = fmaxf(__uint_as_float(v[j + 2]), 0.f), y3 = fmaxf(__uint_as_float(v[j + 3]), 0.f);
-                c0 = fmaf(y0, wa.x, c0); c1 = fmaf(y0, wb.x, c1); c2 = fmaf(y0, wc.x, c2);
-                c0 = fmaf(y1, wa.y, c0); c1 = fmaf(y1, wb.y, c1); c2 = fmaf(y1, wc.y, c2);
-                c0 = fmaf(y2, wa.z, c0); c1 = fmaf(y2, wb.z, c1); c2 = fmaf(y2, wc.z, c2);
-                c0 = fmaf(y3, wa.w, c0); c1 = fmaf(y3, wb.w, c1); c2 = fmaf(y3, wc.w, c2);
-              }
-            }
-            if (write_act) {                           // ReLU + bf16 pack in one cvt; the bias came through the MMA
+            {                                          // ReLU + bf16 pack in one cvt; the bias came through the MMA
 #pragma unroll
               for (int q = 0; q < 8; ++q)
                 tc::st_shared_v4(s_act + (u * 8 + q) * kKcoreBytes + row * 16,
@@ -528,11 +502,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             else write_encoding<0, 4, false>(s_enc, row, dirv, g_de);
             tc::fence_proxy_async_smem();
           }
-          if (is_dens) sigma_keep = softplus_f((dn[0] + dn[1]) + (dn[2] + dn[3]) + sm[a.sm_bd]);
-          if (is_rgb && valid) {
-            const float* b2 = sm + a.sm_b2;
-            reinterpret_cast<float4*>(a.sigma_rgb)[grow] =
-                make_float4(sigma_keep, sigmoid_f(c0 + b2[0]), sigmoid_f(c1 + b2[1]), sigmoid_f(c2 + b2[2]));
+          // The two CUDA-core heads read this thread's row of the bf16 tile it has just written, AFTER the layer loop:
+          // inside it the 128 accumulator registers of the double-buffered read-out leave no room to prefetch head
+          // weights, and the exposed shared-memory latency made these two epilogues 3x longer than a layer of MMAs.
+          if (is_dens) {                               // density_layer + softplus on h8 (NeRFModel.py:192)
+            const float4* wd = reinterpret_cast<const float4*>(sm + a.sm_wd);
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll 8
+            for (int kc = 0; kc < 32; ++kc) {
+              uint32_t x0, x1, x2, x3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(s_act + kc * kKcoreBytes + row * 16));
+              const float4 wa = wd[2 * kc], wb = wd[2 * kc + 1];
+              d0 = fmaf(__uint_as_float(x0 << 16), wa.x, d0); d1 = fmaf(__uint_as_float(x0 & 0xffff0000u), wa.y, d1);
+              d2 = fmaf(__uint_as_float(x1 << 16), wa.z, d2); d3 = fmaf(__uint_as_float(x1 & 0xffff0000u), wa.w, d3);
+              d0 = fmaf(__uint_as_float(x2 << 16), wb.x, d0); d1 = fmaf(__uint_as_float(x2 & 0xffff0000u), wb.y, d1);
+              d2 = fmaf(__uint_as_float(x3 << 16), wb.z, d2); d3 = fmaf(__uint_as_float(x3 & 0xffff0000u), wb.w, d3);
+            }
+            sigma_keep = softplus_f((d0 + d1) + (d2 + d3) + sm[a.sm_bd]);
+          }
+          if (is_rgb) {                                // rgb_layer2 + sigmoid on r1 (NeRFModel.py:199-200)
+            const float4* w2 = reinterpret_cast<const float4*>(sm + a.sm_w2);
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll 4
+            for (int kc = 0; kc < 16; ++kc) {
+              uint32_t x[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(s_act + kc * kKcoreBytes + row * 16));
+              float y[8];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { y[2 * q] = __uint_as_float(x[q] << 16); y[2 * q + 1] = __uint_as_float(x[q] & 0xffff0000u); }
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4 wa = w2[2 * kc + h], wb = w2[32 + 2 * kc + h], wc = w2[64 + 2 * kc + h];
+                c0 = fmaf(y[4 * h], wa.x, c0); c1 = fmaf(y[4 * h], wb.x, c1); c2 = fmaf(y[4 * h], wc.x, c2);
+                c0 = fmaf(y[4 * h + 1], wa.y, c0); c1 = fmaf(y[4 * h + 1], wb.y, c1); c2 = fmaf(y[4 * h + 1], wc.y, c2);
+                c0 = fmaf(y[4 * h + 2], wa.z, c0); c1 = fmaf(y[4 * h + 2], wb.z, c1); c2 = fmaf(y[4 * h + 2], wc.z, c2);
+                c0 = fmaf(y[4 * h + 3], wa.w, c0); c1 = fmaf(y[4 * h + 3], wb.w, c1); c2 = fmaf(y[4 * h + 3], wc.w, c2);
+              }
+            }
+            if (valid) {
+              const float* b2 = sm + a.sm_b2;
+              reinterpret_cast<float4*>(a.sigma_rgb)[grow] =
+                  make_float4(sigma_keep, sigmoid_f(c0 + b2[0]), sigmoid_f(c1 + b2[1]), sigmoid_f(c2 + b2[2]));
+            }
           }
         }
         if (store_out && !(a.exp_flags & 1)) {
