@@ -196,6 +196,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Eight consecutive contraction steps into one accumulator from ONE asm block (single-CTA form): the sixteen descriptors
+// are live inputs in distinct registers, so the UTCHMMAs do not serialise on each other's descriptor-register scoreboard
+// (see umma_bf16_pair_x4).  a[i] / b[i] are full 64-bit shared-memory descriptors.
+__device__ __forceinline__ void umma_bf16_x8(uint32_t d_tmem, const uint64_t (&a)[8], const uint64_t (&b)[8], uint32_t idesc,
+                                             uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, t;\n\t"
+      "setp.ne.b32 p, %18, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %9, %17, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %10, %17, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %11, %17, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %4, %12, %17, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %5, %13, %17, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %6, %14, %17, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %7, %15, %17, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %8, %16, %17, t;\n\t}"
+      ::"r"(d_tmem), "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(a[4]), "l"(a[5]), "l"(a[6]), "l"(a[7]),
+        "l"(b[0]), "l"(b[1]), "l"(b[2]), "l"(b[3]), "l"(b[4]), "l"(b[5]), "l"(b[6]), "l"(b[7]), "r"(idesc), "r"(accumulate_first) : "memory");
+}
 // mbarrier arrive when all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

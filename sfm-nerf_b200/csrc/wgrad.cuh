@@ -119,10 +119,17 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
           const uint32_t idesc = tc::umma_idesc_bf16(128, pl.x_n[j], 1, 1);
           const uint32_t d_col = tmem_base + (uint32_t)(i * W.n + j * 128);
           if (tc::elect_one()) {
+            // 16 rows (the contraction axis) per UMMA; the eight UMMAs of a 128-row block go out from one asm block with
+            // sixteen distinct descriptor registers: issued one by one they reuse the same uniform registers and each
+            // waits ~225 cycles on the previous one's scoreboard, which made this kernel issue-bound (232 cycles per MMA
+            // measured) instead of HBM-bound.
+            uint64_t da[8], db[8];
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)               // 16 rows (the contraction axis) per UMMA
-              tc::umma_bf16(d_col, tc::umma_smem_desc(sa + ks * 256, 128, kKcoreBytes),
-                            tc::umma_smem_desc(sb + ks * 256, 128, kKcoreBytes), idesc, (t > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < 8; ++ks) {
+              da[ks] = tc::umma_smem_desc(sa + ks * 256, 128, kKcoreBytes);
+              db[ks] = tc::umma_smem_desc(sb + ks * 256, 128, kKcoreBytes);
+            }
+            tc::umma_bf16_x8(d_col, da, db, idesc, t > 0 ? 1u : 0u);
             if (i == m_halves - 1) tc::umma_commit(bar_empty + 8 * slot_b);   // last reader of X_j
             if (j == pl.x_parts - 1) tc::umma_commit(bar_empty + 8 * slot_a); // last reader of dY_i
           }
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
 // Head gradients on CUDA cores (train: dL/d density_layer, dL/d rgb_layer2).
 //   d w_d[j]   = sum_rows dsp[row] * h8[row][j]      d b_d    = sum_rows dsp[row]
 //   d W2[c][j] = sum_rows drgb_pre[c][row] * r1[row][j]   d b2[c] = sum_rows drgb_pre[c][row]
-// Thread t < 256: density channel t; 256 <= t < 384: rgb1 channel t-256.
+// Threads 0-255: the 32 k-cores of h8 (density_layer); 256-383: the 16 k-cores of r1 (rgb_layer2).
 struct HeadGradArgs {
   const uint8_t* stash;
   const uint8_t* dstash;
@@ -227,41 +234,73 @@ struct HeadGradArgs {
   int32_t st_h8, st_r1, ds_sr;
   int32_t g_wd, g_bd, g_w2, g_b2;     // float offsets in the flat gradient vector
 };
+// Every thread owns one k-core (8 channels) and every 8th row of a tile: 16-byte loads, eight neighbouring threads read 128
+// contiguous bytes.  Partial sums are reduced over the 8 row-phases with shuffles at the end.
 __global__ void __launch_bounds__(384) head_grad_kernel(const HeadGradArgs a) {
   __shared__ float4 dsr[128];
   const int t = threadIdx.x;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accb = 0.f, accb1 = 0.f, accb2 = 0.f;
+  const bool dens = t < 256;
+  const int kc = dens ? (t >> 3) : ((t - 256) >> 3);       // k-core of h8 (32) / r1 (16)
+  const int rp = t & 7;                                     // row phase
+  float acc[3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+  float accb0 = 0.f, accb1 = 0.f, accb2 = 0.f, accbd = 0.f;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const uint8_t* st = a.stash + (size_t)tile * a.stash_tile_bytes;
     __syncthreads();
     if (t < 128) dsr[t] = reinterpret_cast<const float4*>(a.dstash + (size_t)tile * a.dstash_tile_bytes + a.ds_sr)[t];
     __syncthreads();
-    if (t < 256) {
-      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(st + a.st_h8) + (t >> 3) * 1024 + (t & 7);
-#pragma unroll 8
-      for (int r = 0; r < 128; ++r) acc0 = fmaf(dsr[r].x, __bfloat162float(h[r * 8]), acc0);
-      if (t == 0) for (int r = 0; r < 128; ++r) accb += dsr[r].x;
-    } else {
-      const int c = t - 256;
-      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(st + a.st_r1) + (c >> 3) * 1024 + (c & 7);
-#pragma unroll 8
-      for (int r = 0; r < 128; ++r) {
-        const float v = __bfloat162float(h[r * 8]);
-        const float4 d = dsr[r];
-        acc0 = fmaf(d.y, v, acc0); acc1 = fmaf(d.z, v, acc1); acc2 = fmaf(d.w, v, acc2);
+    const uint4* src = reinterpret_cast<const uint4*>(st + (dens ? a.st_h8 : a.st_r1) + kc * kKcoreBytes);
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int r = rp + 8 * i;
+      const uint4 u = __ldg(src + r);
+      const float4 d = dsr[r];
+      float v[8] = {__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u),
+                    __uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u), __uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u)};
+      if (dens) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[0][j] = fmaf(d.x, v[j], acc[0][j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[0][j] = fmaf(d.y, v[j], acc[0][j]); acc[1][j] = fmaf(d.z, v[j], acc[1][j]); acc[2][j] = fmaf(d.w, v[j], acc[2][j]); }
       }
-      if (c == 0) for (int r = 0; r < 128; ++r) { accb += dsr[r].y; accb1 += dsr[r].z; accb2 += dsr[r].w; }
+    }
+    if (t < 128) { const float4 d = dsr[t]; accbd += d.x; accb0 += d.y; accb1 += d.z; accb2 += d.w; }   // bias sums: thread = row
+  }
+  // reduce over the 8 row phases (lanes differing in bits 0-2)
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) acc[c][j] += __shfl_xor_sync(0xffffffffu, acc[c][j], o);
+  if (rp == 0) {
+    if (dens) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(a.grads + a.g_wd + kc * 8 + j, acc[0][j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(a.grads + a.g_w2 + kc * 8 + j, acc[0][j]);
+        atomicAdd(a.grads + a.g_w2 + 128 + kc * 8 + j, acc[1][j]);
+        atomicAdd(a.grads + a.g_w2 + 256 + kc * 8 + j, acc[2][j]);
+      }
     }
   }
-  if (t < 256) {
-    atomicAdd(a.grads + a.g_wd + t, acc0);
-    if (t == 0) atomicAdd(a.grads + a.g_bd, accb);
-  } else {
-    const int c = t - 256;
-    atomicAdd(a.grads + a.g_w2 + c, acc0);
-    atomicAdd(a.grads + a.g_w2 + 128 + c, acc1);
-    atomicAdd(a.grads + a.g_w2 + 256 + c, acc2);
-    if (c == 0) { atomicAdd(a.grads + a.g_b2, accb); atomicAdd(a.grads + a.g_b2 + 1, accb1); atomicAdd(a.grads + a.g_b2 + 2, accb2); }
+  if (t < 128) {                                            // bias gradients: warp sums, one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      accbd += __shfl_xor_sync(0xffffffffu, accbd, o); accb0 += __shfl_xor_sync(0xffffffffu, accb0, o);
+      accb1 += __shfl_xor_sync(0xffffffffu, accb1, o); accb2 += __shfl_xor_sync(0xffffffffu, accb2, o);
+    }
+    if ((t & 31) == 0) {
+      atomicAdd(a.grads + a.g_bd, accbd);
+      atomicAdd(a.grads + a.g_b2, accb0); atomicAdd(a.grads + a.g_b2 + 1, accb1); atomicAdd(a.grads + a.g_b2 + 2, accb2);
+    }
   }
 }
 
