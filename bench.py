@@ -278,6 +278,23 @@ def run_ours(args):
         ev5.record()
         barrier()
     render_ms = max_over_ranks(ev4.elapsed_time(ev5))
+    # BASELINE config 4: full-resolution 800x800 frame x 192 samples, rays sharded contiguously over the ranks
+    args_c4 = argparse.Namespace(n_sample=192, perturb=True, chunk_size=32768, n_rays_batch=800 * 800, near=2.0, far=6.0)
+    cam4 = s.synthetic.make_camera_info(800, 800)
+    b4, e4 = s.parallel.shard_range(800 * 800, rank, world)
+    with torch.no_grad():
+        for _ in range(2):
+            o, d = E.raygen_image(poses, 0, cam4, b4, e4 - b4)
+            s.render(model, o, d, args_c4)
+        barrier()
+        ev8, ev9 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev8.record()
+        for f in range(4):
+            o, d = E.raygen_image(poses, f % len(poses_np), cam4, b4, e4 - b4)
+            s.render(model, o, d, args_c4)
+        ev9.record()
+        barrier()
+    c4_ms = max_over_ranks(ev8.elapsed_time(ev9)) / 4
     # the fused MLP inference kernel alone on this rank's slice of the frame (tensor-pipe fraction)
     with torch.no_grad():
         o, d = E.raygen_image(poses, 0, cam, r_begin, per_rank)
@@ -352,6 +369,8 @@ def run_ours(args):
                                   "tflops": round(per_rank * N_SAMPLE * FLOP_FWD / mlp_infer_ms / 1e9, 1),
                                   "tensor_frac": round(per_rank * N_SAMPLE * FLOP_FWD / mlp_infer_ms / 1e9 / measured_peaks()["tflops"], 4),
                                   "samples_per_s": per_rank * N_SAMPLE / mlp_infer_ms * 1e3}},
+        "render_c4": {"workload": f"800x800 frame x 192 samples, rays sharded over {world} GPU(s)", "ms_per_frame": c4_ms,
+                      "rays_per_s": 800 * 800 / c4_ms * 1e3, "samples_per_s": 800 * 800 * 192 / c4_ms * 1e3},
         "e2e": {"value": n_rays * world * e2e_steps / e2e_ms * 1e3, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 9 * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": launches,

@@ -108,7 +108,7 @@ class NeRFmodel(nn.Module):
         p = pos.reshape(-1, 3).to(torch.float32).contiguous()
         d = direction.reshape(-1, 3).to(torch.float32).contiguous()
         params = self.ordered_parameters()
-        out = engine.MLPFunction.apply(st, p, d, *params)
+        out = engine.MLPFunction.apply(st, p, d, *params) if engine.wants_grad(params) else engine.mlp_inference(st, p, d)
         return out[:, 0:1].reshape(*lead, 1), out[:, 1:4].reshape(*lead, 3)
 
 

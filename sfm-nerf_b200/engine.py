@@ -202,6 +202,25 @@ def mlp_backward(st, stash, sigma_rgb, d_sigma_rgb, grads, dstash=None, accumula
     return grads
 
 
+def wants_grad(params):
+    """True when a backward pass can follow: grad mode is on and some parameter requires grad.  (Inside
+    autograd.Function.forward grad mode is always off and ctx.needs_input_grad ignores torch.no_grad(), so the callers decide:
+    without this the no_grad() render path would allocate and write the training stash.)"""
+    return torch.is_grad_enabled() and any(p.requires_grad for p in params)
+
+
+def mlp_inference(st, pos, dirs):
+    """NeRFmodel.forward without autograd: the inference kernel (no stash)."""
+    _need_cuda(pos, dirs)
+    return mlp_forward(st, pos, dirs, None)
+
+
+def render_inference(st, rays_o, rays_d, z):
+    """render without autograd: inference kernel + compositing -> (rgb, depth, acc)."""
+    _need_cuda(rays_o, rays_d, z)
+    return composite_forward(mlp_forward_rays(st, rays_o, rays_d, z, None), z, extras=True)
+
+
 class MLPFunction(torch.autograd.Function):
     """NeRFmodel.forward: (pos [n,3], dir [n,3]) -> sigma_rgb [n,4]; gradients reach the parameters."""
 

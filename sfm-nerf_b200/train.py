@@ -110,7 +110,10 @@ def render_full(model, rays_origin, rays_direction, args, near=2.0, far=6.0, t_r
         _jitter_counter[0] += (n_rays * S + 3) // 4
     z = engine.sample_z(n_rays, S, near, far, o.device, perturb=perturb or t_rand is not None, t_rand=t_rand,
                         seed=torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, offset=off)
-    return engine.RenderFunction.apply(st, o, d, z, *model.ordered_parameters())
+    params = model.ordered_parameters()
+    if not engine.wants_grad(params):
+        return engine.render_inference(st, o, d, z)
+    return engine.RenderFunction.apply(st, o, d, z, *params)
 
 
 def render(model, rays_origin, rays_direction, args, near=2.0, far=6.0):

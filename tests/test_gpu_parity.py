@@ -354,6 +354,46 @@ def test_ragged_and_empty_inputs(pkg, model_pe):
     assert bool(torch.isfinite(a).all())
 
 
+def test_tile_count_independence(pkg, model_pe):
+    """The fused MLP kernels work on quads of four 128-row tiles (two tile slots x two CTAs of a pair): every row count around
+    the tile / quad boundaries gives, row for row, the result of evaluating 128 rows at a time -- forward and training forward."""
+    st = model_pe.kernel_state()
+    gen = torch.Generator().manual_seed(11)
+    n_max = 9 * 128 + 77
+    pos = (torch.rand(n_max, 3, generator=gen) * 2 - 1).cuda()
+    dirs = torch.nn.functional.normalize(torch.randn(n_max, 3, generator=gen), dim=-1).cuda()
+    ref = torch.cat([pkg.engine.mlp_forward(st, pos[i:i + 128].contiguous(), dirs[i:i + 128].contiguous()) for i in range(0, n_max, 128)])
+    for n in (1, 127, 128, 129, 256, 300, 385, 512, 513, 640, 1025, n_max):
+        out = pkg.engine.mlp_forward(st, pos[:n].contiguous(), dirs[:n].contiguous())
+        assert torch.equal(out, ref[:n]), n
+        stash = pkg.engine.alloc_stash(st, n)
+        out_t = pkg.engine.mlp_forward(st, pos[:n].contiguous(), dirs[:n].contiguous(), stash)
+        assert torch.equal(out_t, ref[:n]), ("train", n)
+
+
+def test_full_resolution_frame_sharded(pkg, model_pe):
+    """BASELINE config 4 at full size: 800x800 rays x 192 samples.  The frame rendered as 8 contiguous ray shards (one per
+    GPU of a box) equals the same rows of ... the frame rendered as 3 uneven shards, bit for bit; values are finite and in [0, 1]."""
+    cam = pkg.synthetic.make_camera_info(800, 800)
+    poses = pkg.engine.poses_to_device(pkg.synthetic.look_at_pose(40.0, -25.0), "cuda")
+    args = _ns(n_sample=192, perturb=False)
+    n = 800 * 800
+
+    def shards(world):
+        parts = []
+        with torch.no_grad():
+            for r in range(world):
+                b, e = pkg.parallel.shard_range(n, r, world)
+                o, d = pkg.engine.raygen_image(poses, 0, cam, b, e - b)
+                parts.append(pkg.render(model_pe, o, d, args))
+        return torch.cat(parts)
+
+    a, b = shards(8), shards(3)
+    assert a.shape == (n, 3)
+    assert torch.equal(a, b)
+    assert bool(torch.isfinite(a).all()) and float(a.min()) >= 0.0 and float(a.max()) <= 1.0
+
+
 def test_large_batch_properties(pkg, model_pe):
     """C2-sized batch (4096 rays x 64): determinism and tile independence at full size."""
     o = torch.zeros(4096, 3, device="cuda"); o[:, 2] = -4.0
