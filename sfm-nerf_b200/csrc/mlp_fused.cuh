@@ -434,7 +434,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         const bool is_dens = (MODE == MODE_FWD) && (st.flags & EPI_DENSITY) != 0;
         const bool add_sigma = (MODE == MODE_BWD) && (st.flags & EPI_BWD_SIGMA) != 0;
 
-        // one 64-column unit: heads (rare steps), activation / mask, bf16 pack, store as the next A tile
+        uint4* g_out = (MODE == MODE_BWD && tile_ok) ? reinterpret_cast<uint4*>(dstash_tile + st.stash_off) + row : nullptr;
+        (void)g_out;
+        // one 64-column unit: activation / mask, bf16 pack, store as the next A tile
         auto process = [&](uint32_t (&v)[64], int u) {
           if (MODE == MODE_FWD) {
             {                                          // ReLU + bf16 pack in one cvt; the bias came through the MMA
@@ -459,18 +461,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
                 v[j + 3] = __float_as_uint(fmaf(dsp, w4.w, __uint_as_float(v[j + 3])));
               }
             }
+            // relu'(h) in the packed domain: the mask bits of columns 2i / 2i+1 of a 32-column chunk sit at i / i+16 of its
+            // mask word, so ((w >> i) & 0x00010001) * 0xFFFF is the AND mask of the bf16x2 word holding those two columns.
+            // The packed words go to the next A tile AND straight to the dstash from registers (a warp writes 512
+            // contiguous bytes per instruction): no shared-memory read-back after the layer is released.
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {             // relu'(h): mask bit of column c sits at (c>>1) + 16*(c&1)
-              const uint32_t w = (j < 32) ? w_lo : w_hi;
-              v[j] = ((w >> (((j & 31) >> 1) + 16 * (j & 1))) & 1u) ? v[j] : 0u;
+            for (int q = 0; q < 8; ++q) {
+              uint32_t p[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int i = 4 * q + t;
+                const uint32_t w = (i < 16) ? w_lo : w_hi;
+                p[t] = tc::pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & (((w >> (i & 15)) & 0x00010001u) * 0xFFFFu);
+              }
+              tc::st_shared_v4(s_act + (u * 8 + q) * kKcoreBytes + row * 16, p[0], p[1], p[2], p[3]);
+              if (g_out != nullptr) g_out[(u * 8 + q) * 128] = make_uint4(p[0], p[1], p[2], p[3]);
             }
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              tc::st_shared_v4(s_act + (u * 8 + q) * kKcoreBytes + row * 16,
-                               tc::pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
-                               tc::pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
-                               tc::pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
-                               tc::pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
           }
         };
 
@@ -546,13 +552,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             }
           }
         }
-        if (store_out && !(a.exp_flags & 1)) {
+        if (MODE == MODE_FWD && store_out && !(a.exp_flags & 1)) {
           // Training stash: this thread reads back the 16-byte pieces of ITS OWN row of the bf16 tile it
           // just wrote and streams them to HBM (a warp writes 512 contiguous bytes per instruction), and
-          // (forward) folds them into the ReLU bit masks (bit of column c in a 32-column chunk:
-          // (c>>1) + 16*(c&1)).  This runs under the next layer's MMAs.  A bulk (TMA) store of the tile
-          // would be one instruction, but its shared-memory reads halve the UMMA issue rate (measured).
-          uint4* gdst = reinterpret_cast<uint4*>((MODE == MODE_FWD ? stash_tile : dstash_tile) + st.stash_off) + row;
+          // folds them into the ReLU bit masks (bit of column c in a 32-column chunk: (c>>1) + 16*(c&1)).
+          // This runs under the other slot's MMAs.  (Storing from registers inside the read-out loop, as dgrad
+          // does, was measured too: no gain for training and a slower inference loop.)  A bulk (TMA) store of
+          // the tile would be one instruction, but its shared-memory reads halve the UMMA issue rate (measured).
+          uint4* gdst = reinterpret_cast<uint4*>(stash_tile + st.stash_off) + row;
           uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
@@ -563,20 +570,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "r"(s_act + (ch * 4 + q) * kKcoreBytes + row * 16));
                 gdst[(ch * 4 + q) * 128] = pk;
-                if (MODE == MODE_FWD) {
-                  mw[ch] |= ((pk.x + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 0));
-                  mw[ch] |= ((pk.y + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 1));
-                  mw[ch] |= ((pk.z + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 2));
-                  mw[ch] |= ((pk.w + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 3));
-                }
+                mw[ch] |= ((pk.x + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 0));
+                mw[ch] |= ((pk.y + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 1));
+                mw[ch] |= ((pk.z + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 2));
+                mw[ch] |= ((pk.w + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 3));
               }
             }
           }
-          if (MODE == MODE_FWD) {
-            uint4* mp = reinterpret_cast<uint4*>(stash_tile + st.mask_off) + row * 2;
-            mp[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-            mp[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
-          }
+          uint4* mp = reinterpret_cast<uint4*>(stash_tile + st.mask_off) + row * 2;
+          mp[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+          mp[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
         }
       }
     }
