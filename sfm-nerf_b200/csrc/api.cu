@@ -315,15 +315,25 @@ int nerf_mlp_wgrad(int layout, const void* stash, const void* dstash, int64_t n_
   w.stash = static_cast<const uint8_t*>(stash); w.dstash = static_cast<const uint8_t*>(dstash); w.grads = grads;
   w.stash_tile_bytes = m->stash_tile_bytes; w.dstash_tile_bytes = m->dstash_tile_bytes;
   w.n_tiles = n_tiles; w.n_items = m->n_wgrad;
-  int64_t total_cost = 0;
-  for (int i = 0; i < m->n_wgrad; ++i) { w.items[i] = m->wg[i]; total_cost += m->wg[i].cost; }
+  // Split the SMs over the items so that the LARGEST per-CTA share of an item's cost is as small as possible (the kernel
+  // ends with its slowest CTA): start from one CTA per item and keep giving a CTA to the item with the largest cost / CTAs.
+  int n_cta[kMaxWgradItems];
+  int used = 0;
+  for (int i = 0; i < m->n_wgrad; ++i) { w.items[i] = m->wg[i]; n_cta[i] = 1; ++used; }
+  while (used < dev->sms) {
+    int best = -1;
+    double worst = 0.0;
+    for (int i = 0; i < m->n_wgrad; ++i) {
+      const double per = (double)m->wg[i].cost / n_cta[i];
+      if (n_cta[i] < n_tiles && per > worst) { worst = per; best = i; }
+    }
+    if (best < 0) break;                         /* every item already has one CTA per tile */
+    ++n_cta[best]; ++used;
+  }
   int ctas = 0;
   for (int i = 0; i < m->n_wgrad; ++i) {
-    int c = (int)((int64_t)dev->sms * m->wg[i].cost / total_cost);
-    if (c < 1) c = 1;
-    if (c > n_tiles) c = n_tiles;
     w.cta_begin[i] = ctas;
-    ctas += c;
+    ctas += n_cta[i];
   }
   w.cta_begin[m->n_wgrad] = ctas;
   wgrad_kernel<<<ctas, 192, kWgSmemBytes, s>>>(w);

@@ -298,6 +298,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             int cnt = (seg == 0) ? act_ks : (seg == 1) ? enc_ks : bias_ks;
             uint32_t a_cur = (seg == 0) ? act_lo : (seg == 1) ? enc_lo : enc_lo + 3u * kStepLo;     // bias: ENC k-step 3
 #pragma unroll 1
+            // Two groups per trip while eight k-steps remain, all sixteen descriptors and parities derived up front: the
+            // second group goes out right behind the first one's commits (measured: 6200 -> 5570 cycles per layer pair).
+            // ptxas still stages both groups' descriptors through the same uniform registers (also when the second
+            // set is kept live across the first block), and one 8-MMA block needs all eight slabs landed (much slower).
+            while (cnt >= 2 * kWaitGroup) {
+              const uint32_t s0 = rs & (kRingSlots - 1), s1 = (rs + 1) & (kRingSlots - 1), s2 = (rs + 2) & (kRingSlots - 1),
+                             s3 = (rs + 3) & (kRingSlots - 1), s4 = (rs + 4) & (kRingSlots - 1), s5 = (rs + 5) & (kRingSlots - 1),
+                             s6 = (rs + 6) & (kRingSlots - 1), s7 = (rs + 7) & (kRingSlots - 1);
+              const uint64_t a0 = desc_hi | a_cur, a1 = desc_hi | (a_cur + kStepLo), a2 = desc_hi | (a_cur + 2 * kStepLo),
+                             a3 = desc_hi | (a_cur + 3 * kStepLo), a4 = desc_hi | (a_cur + 4 * kStepLo), a5 = desc_hi | (a_cur + 5 * kStepLo),
+                             a6 = desc_hi | (a_cur + 6 * kStepLo), a7 = desc_hi | (a_cur + 7 * kStepLo);
+              const uint64_t b0 = desc_hi | (b_lo + s0 * kSlabLo), b1 = desc_hi | (b_lo + s1 * kSlabLo), b2 = desc_hi | (b_lo + s2 * kSlabLo),
+                             b3 = desc_hi | (b_lo + s3 * kSlabLo), b4 = desc_hi | (b_lo + s4 * kSlabLo), b5 = desc_hi | (b_lo + s5 * kSlabLo),
+                             b6 = desc_hi | (b_lo + s6 * kSlabLo), b7 = desc_hi | (b_lo + s7 * kSlabLo);
+              const uint32_t p0 = par ^ (rs >> 4), p1 = par ^ ((rs + 1) >> 4), p2 = par ^ ((rs + 2) >> 4), p3 = par ^ ((rs + 3) >> 4),
+                             p4 = par ^ ((rs + 4) >> 4), p5 = par ^ ((rs + 5) >> 4), p6 = par ^ ((rs + 6) >> 4), p7 = par ^ ((rs + 7) >> 4);
+              uint32_t ready = (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s0, p0) & (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s1, p1) &
+                               (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s2, p2) & (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s3, p3);
+              if (!ready) {
+                tc::mbar_wait_cluster(bar_full + 8 * s0, p0); tc::mbar_wait_cluster(bar_full + 8 * s1, p1);
+                tc::mbar_wait_cluster(bar_full + 8 * s2, p2); tc::mbar_wait_cluster(bar_full + 8 * s3, p3);
+              }
+              if (tc::elect_one()) {
+                tc::umma_bf16_pair_x4(d_tmem, a0, a1, a2, a3, b0, b1, b2, b3, idesc, k_done > 0 ? 1u : 0u);
+                tc::umma_commit_pair(bar_empty + 8 * ((s0 & 1u) ? s0 : s1), 3);
+                tc::umma_commit_pair(bar_empty + 8 * ((s0 & 1u) ? s2 : s3), 3);
+              }
+              __syncwarp();
+              ready = (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s4, p4) & (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s5, p5) &
+                      (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s6, p6) & (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s7, p7);
+              if (!ready) {
+                tc::mbar_wait_cluster(bar_full + 8 * s4, p4); tc::mbar_wait_cluster(bar_full + 8 * s5, p5);
+                tc::mbar_wait_cluster(bar_full + 8 * s6, p6); tc::mbar_wait_cluster(bar_full + 8 * s7, p7);
+              }
+              if (tc::elect_one()) {
+                tc::umma_bf16_pair_x4(d_tmem, a4, a5, a6, a7, b4, b5, b6, b7, idesc, 1u);
+                tc::umma_commit_pair(bar_empty + 8 * ((s0 & 1u) ? s4 : s5), 3);
+                tc::umma_commit_pair(bar_empty + 8 * ((s0 & 1u) ? s6 : s7), 3);
+              }
+              __syncwarp();
+              rs += 2 * kWaitGroup;
+              if (rs >= (uint32_t)kRingSlots) { rs -= kRingSlots; par ^= 1u; }
+              a_cur += 2 * kWaitGroup * kStepLo;
+              cnt -= 2 * kWaitGroup; k_done += 2 * kWaitGroup;
+            }
             while (cnt > 0) {
               const int kn = cnt < kWaitGroup ? cnt : kWaitGroup;
               uint32_t ready = 1u;

@@ -213,11 +213,8 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
     w.dy_off = dy_off; w.m_kcores = m_kcores; w.x_off = x_off; w.n = n; w.n_valid = n_valid;
     w.w_off = m.w_off[lin]; w.in_f = m.in_f[lin]; w.col0 = col0;
     w.b_off = owns_bias ? m.b_off[lin] : -1;
-    // cost per 128-row tile in SM cycles: UMMA time (128xNx16 = N/2 cycles, 8 k-steps per M half) vs.
-    // the time to stream both operand blocks at one SM's share of HBM (~20 B/cycle), whichever binds
-    const int mma = (m_kcores / 16) * 4 * n;
-    const int ld = (m_kcores + n / 8) * (kKcoreBytes / 20);
-    w.cost = mma > ld ? mma : ld;
+    // cost per 128-row tile: the bytes of both operand blocks (the kernel is HBM-bound; k-cores of 2 KB)
+    w.cost = m_kcores + n / 8;
     m.wg[m.n_wgrad++] = w;
   };
   const int pos_n = pos_ks * 16, dir_n = dir_ks * 16;
