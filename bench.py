@@ -10,7 +10,8 @@ generateBatch + render + MSE + backward + Adam + weight repack.  `value` = rays/
 with every input resident in HBM (rays are drawn on the GPU); `e2e` = the same step fed from a pinned
 HOST ray batch (H2D copy inside the timed region) with the loss read back to the host every step,
 i.e. the reference's train.py:447-468 loop body.  N > 1: data-parallel, 4096 rays per rank (weak
-scaling) + NCCL allreduce of the flat fp32 gradient.  Timing: CUDA events on the launch stream,
+scaling); the gradient exchange is fused into the Adam kernel (NVLS multimem.ld_reduce / peer loads over symmetric memory,
+NCCL allreduce as fallback).  Timing: CUDA events on the launch stream,
 barrier + synchronize on both sides, max over ranks.  The per-step working set (activation stash +
 gradient stash, ~2.8 GB) is far larger than the 126 MB L2, so no explicit L2 flush is needed.
 """
@@ -230,6 +231,8 @@ def run_ours(args):
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = trainer.launches_per_step * args.steps            # this repo's kernels only (the gradient memset is the driver's)
+    grad_exchange = "none" if trainer.exchange is None else trainer.exchange.mode
+    grad_exchange_note = "" if trainer.exchange is None else trainer.exchange.why
     final_loss = float(trainer.loss.item())
 
     # ---- end to end through the public API with host buffers --------------------------------
@@ -374,6 +377,8 @@ def run_ours(args):
         "e2e": {"value": n_rays * world * e2e_steps / e2e_ms * 1e3, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 9 * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": launches,
+        "grad_exchange": {"mode": grad_exchange, "note": grad_exchange_note,
+                          "what": "nvls / p2p: gradient sum over ranks read through NVLink inside the Adam kernel (symmetric memory, one barrier); nccl: allreduce"},
         "clocks": clocks,
         "roofline": roofline,
         "kernels": kern,

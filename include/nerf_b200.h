@@ -151,6 +151,17 @@ int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
                    int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
                    float grad_scale, void* stream);
 
+/* Data-parallel form of nerf_adam_step (train.py:401, 456-465 on N GPUs): the gradient exchange is fused into the optimiser
+ * kernel.  Every rank's nerf_mlp_wgrad has written its local gradient into a buffer that is peer-mapped on all ranks
+ * (symmetric memory); after a cross-rank barrier (the caller's) this kernel reads the gradient as the SUM over ranks --
+ * multicast_grads != NULL: through the NVLink multicast address of the buffers (multimem.ld_reduce, the switch adds);
+ * else: from peer_grads_host[0..n_ranks) (HOST array of device pointers, rank order) over NVLink -- and applies Adam with
+ * grad_scale (= 1/n_ranks for the mean).  n must be a multiple of 4 and all pointers 16-byte aligned.  Every rank gets
+ * bit-identical parameters. */
+int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, int n_ranks, const float* multicast_grads,
+                          float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                          int64_t step, float grad_scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Self tests (device): exercise the tcgen05 descriptor encodings used by K4 on a small GEMM.
  * variant selects the operand layout hypothesis; result_host[0..3] receives max-abs-error

@@ -417,6 +417,32 @@ int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
   return NERF_OK;
 }
 
+int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, int n_ranks, const float* multicast_grads,
+                          float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
+                          float grad_scale, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!params || !exp_avg || !exp_avg_sq || n < 0 || step < 1 || n_ranks < 1 || n_ranks > 8 || (n & 3)) return NERF_ERR_ARG;
+  if (!multicast_grads && !peer_grads_host) return NERF_ERR_ARG;
+  PeerGrads peers{};
+  for (int r = 0; r < n_ranks && peer_grads_host; ++r) {
+    if (!peer_grads_host[r] || !nerf_aligned(peer_grads_host[r], 16)) return NERF_ERR_ALIGN;
+    peers.ptr[r] = peer_grads_host[r];
+  }
+  if (!nerf_aligned(params, 16) || !nerf_aligned(exp_avg, 16) || !nerf_aligned(exp_avg_sq, 16) ||
+      (multicast_grads && !nerf_aligned(multicast_grads, 16)))
+    return NERF_ERR_ALIGN;
+  if (n == 0) return NERF_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_reduce_kernel<<<blocks_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(params, peers, n_ranks, multicast_grads, exp_avg, exp_avg_sq,
+                                                                             n / 4, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2),
+                                                                             grad_scale);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
 // ------------------------------------------------------------------------------------ diagnostics
 int nerf_debug_trace(void* device_buffer) {
   g_trace = static_cast<long long*>(device_buffer);

@@ -169,4 +169,39 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = p[i] - (lr / bc1) * (mi / denom);
 }
 
+// Data-parallel Adam with the gradient exchange FUSED into the optimiser kernel: every rank's wgrad has written its local
+// fp32 gradient into a symmetric (peer-mapped) buffer; this kernel sums them while it reads them --
+//   * NVLS: one multimem.ld_reduce on the multicast address of the buffer, the NVSwitch adds the ranks' values in flight;
+//   * otherwise: loads from every rank's buffer over NVLink, summed in rank order
+// -- so there is no allreduce kernel and no reduced copy in HBM.  Both forms give every rank the same bits (the same
+// operation on the same operands in the same order), so the replicated weights stay bit-identical.  4 elements per thread.
+struct PeerGrads { const float* ptr[8]; };
+__global__ void adam_reduce_kernel(float* __restrict__ p, PeerGrads peers, int n_ranks, const float* mc_grads, float* __restrict__ m,
+                                   float* __restrict__ v, int64_t n4, float lr, float b1, float b2, float eps, float bc1,
+                                   float bc2_sqrt, float grad_scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 g;
+  if (mc_grads != nullptr) {
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(reinterpret_cast<const float4*>(mc_grads) + i) : "memory");
+  } else {
+    g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < n_ranks; ++r) {
+      const float4 t = __ldcv(reinterpret_cast<const float4*>(peers.ptr[r]) + i);     // volatile: written by another GPU
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+  }
+  float4 pi = reinterpret_cast<float4*>(p)[i], mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
+  const float gg[4] = {g.x * grad_scale, g.y * grad_scale, g.z * grad_scale, g.w * grad_scale};
+  float* pp = &pi.x; float* mm = &mi.x; float* vv = &vi.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    mm[k] = mm[k] + (gg[k] - mm[k]) * (1.0f - b1);
+    vv[k] = vv[k] * b2 + (1.0f - b2) * gg[k] * gg[k];
+    pp[k] = pp[k] - (lr / bc1) * (mm[k] / (sqrtf(vv[k]) / bc2_sqrt + eps));
+  }
+  reinterpret_cast<float4*>(p)[i] = pi; reinterpret_cast<float4*>(m)[i] = mi; reinterpret_cast<float4*>(v)[i] = vi;
+}
+
 }  // namespace nerf

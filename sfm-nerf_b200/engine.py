@@ -319,7 +319,9 @@ class Trainer:
         self.perturb, self.seed, self.rank, self.world, self.pg = bool(perturb), int(seed), int(rank), int(world), process_group
         dev = self.st.device
         n = self.st.n_params
-        self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
+        # world > 1: symmetric (peer-mapped) gradient buffers; the exchange happens inside the Adam kernel (parallel.GradExchange)
+        self.exchange = parallel.GradExchange(n, dev, self.world, process_group) if self.world > 1 else None
+        self.grads = torch.zeros(n, dtype=torch.float32, device=dev) if self.exchange is None else self.exchange.local(0)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -366,16 +368,28 @@ class Trainer:
         with _timed(timers, "mlp_dgrad"):
             call("nerf_mlp_dgrad", ptr(st.packed), st.layout, ptr(self.stash), ptr(sigma_rgb), ptr(dsr), rows,
                  ptr(self.dstash), stream_ptr())
+        ex = self.exchange
+        if ex is not None:
+            self.grads = ex.local(self.iteration)
         with _timed(timers, "mlp_wgrad"):
             call("nerf_mlp_wgrad", st.layout, ptr(self.stash), ptr(self.dstash), rows, ptr(self.grads), 0, stream_ptr())
         launches += 8                               # sample, mlp fwd, comp fwd, mse, comp bwd, dgrad, wgrad, heads (+1 memset)
-        if self.world > 1:
-            with _timed(timers, "allreduce"):
-                parallel.allreduce_sum_(self.grads, self.pg)
         lr = self.lr()
-        self.iteration += 1
-        call("nerf_adam_step", ptr(st.flat), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), st.n_params,
-             lr, self.betas[0], self.betas[1], self.eps, self.iteration, parallel.mean_scale(self.world), stream_ptr())
+        if ex is not None and ex.mode != "nccl":
+            # the gradient exchange is fused into the optimiser: barrier, then Adam reads the sum over ranks through NVLink
+            with _timed(timers, "grad_barrier"):
+                ex.barrier()
+            peers, mc = ex.peer_pointers(self.iteration)
+            self.iteration += 1
+            call("nerf_adam_step_reduce", ptr(st.flat), peers, self.world, mc, ptr(self.exp_avg), ptr(self.exp_avg_sq), st.n_params,
+                 lr, self.betas[0], self.betas[1], self.eps, self.iteration, parallel.mean_scale(self.world), stream_ptr())
+        else:
+            if self.world > 1:
+                with _timed(timers, "allreduce"):
+                    parallel.allreduce_sum_(self.grads, self.pg)
+            self.iteration += 1
+            call("nerf_adam_step", ptr(st.flat), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), st.n_params,
+                 lr, self.betas[0], self.betas[1], self.eps, self.iteration, parallel.mean_scale(self.world), stream_ptr())
         st.pack()
         launches += 4
         self.launches_per_step = launches

@@ -7,6 +7,12 @@ combine.  Rays are independent through K1-K5, so
     2.6 MB) is sum-allreduced over NCCL/NVLink; Adam applies it scaled by 1/world, which equals the
     gradient of the global-batch mean (train.py:460) because the shards are equal-sized.
 Pure host functions: usable (and tested) with the gloo backend on CPU.
+
+On GPUs the exchange is fused into the optimiser kernel (``GradExchange``): wgrad writes the local gradient into a
+symmetric (peer-mapped) buffer, one stream-ordered cross-rank barrier follows, and ``nerf_adam_step_reduce`` reads the
+gradient as the sum over ranks while applying Adam -- through the NVLink multicast address (NVLS, ``multimem.ld_reduce``)
+or by loading every peer's buffer in rank order.  NCCL's allreduce remains the fallback where symmetric memory is not
+available (and the only mode on CPU / gloo).
 """
 from __future__ import annotations
 
@@ -52,3 +58,58 @@ def gather_frame(local_rgb: torch.Tensor, n_items: int, group=None) -> torch.Ten
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad, group=group)
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+
+
+class GradExchange:
+    """Double-buffered symmetric gradient buffers of one data-parallel group.
+
+    ``mode``: ``"nvls"`` (multicast address available), ``"p2p"`` (peer pointers only) or ``"nccl"`` (symmetric memory
+    unavailable: plain local buffers + ``allreduce_sum_``).  ``NERF_GRAD_EXCHANGE=nccl|p2p|nvls`` forces a mode.
+    Buffer ``step % 2`` is used in step ``step``: a rank can be at most one step ahead of another (each step has one
+    barrier), so the buffer a slow rank is still reading is never the one a fast rank is already overwriting.
+    """
+
+    def __init__(self, n_params: int, device, world: int, group=None):
+        import os
+        self.n, self.world, self.group, self.device = int(n_params), int(world), group, torch.device(device)
+        self.n_pad = (self.n + 63) // 64 * 64                                  # 256-byte aligned second buffer
+        self.mode, self.why, self.handle = "nccl", "", None
+        want = os.environ.get("NERF_GRAD_EXCHANGE", "")
+        if self.world > 1 and self.device.type == "cuda" and want != "nccl":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else dist.group.WORLD
+                buf = symm_mem.empty(2 * self.n_pad, dtype=torch.float32, device=self.device)
+                buf.zero_()
+                self.handle = symm_mem.rendezvous(buf, grp)
+                self.buf = buf
+                self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+                mc = int(self.handle.multicast_ptr or 0)                      # 0: no NVLS multicast mapping for this buffer
+                self.mc_ptr = mc
+                self.mode = "nvls" if (mc and want != "p2p") else "p2p"
+                if want == "nvls" and not mc:
+                    raise RuntimeError("NERF_GRAD_EXCHANGE=nvls but the symmetric buffer has no multicast address")
+            except Exception as e:                                             # noqa: BLE001 -- any failure means: use NCCL
+                if want in ("p2p", "nvls"):
+                    raise
+                self.mode, self.why, self.handle = "nccl", f"{type(e).__name__}: {e}", None
+        if self.handle is None:
+            self.buf = torch.zeros(2 * self.n_pad, dtype=torch.float32, device=self.device)
+
+    def local(self, step: int) -> torch.Tensor:
+        """This rank's gradient buffer of ``step`` (wgrad writes it)."""
+        o = (step & 1) * self.n_pad
+        return self.buf[o:o + self.n]
+
+    def barrier(self):
+        """Stream-ordered cross-rank barrier: every rank's gradient of this step is complete and visible."""
+        if self.handle is not None:
+            self.handle.barrier(channel=0)
+
+    def peer_pointers(self, step: int):
+        """(ctypes array of the ranks' buffer addresses in rank order, multicast address or None) for ``step``."""
+        import ctypes as C
+        off = (step & 1) * self.n_pad * 4
+        arr = (C.c_void_p * self.world)(*[p + off for p in self.peer_ptrs])
+        mc = C.c_void_p(self.mc_ptr + off) if self.mode == "nvls" else None
+        return arr, mc

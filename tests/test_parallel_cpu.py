@@ -51,6 +51,12 @@ def _worker(rank, world, port, out):
     flat = torch.cat([g.reshape(-1) for g in g_local.values()])
     par.allreduce_sum_(flat)
     flat *= par.mean_scale(world)
+    # the exchange object on a CPU group: no symmetric memory -> the NCCL/gloo allreduce mode, double-buffered by step parity
+    ex = par.GradExchange(flat.numel(), "cpu", world)
+    assert ex.mode == "nccl" and ex.handle is None
+    assert ex.local(0).data_ptr() != ex.local(1).data_ptr() and ex.local(0).data_ptr() == ex.local(2).data_ptr()
+    assert ex.local(1).numel() == flat.numel() and (ex.local(1).data_ptr() - ex.local(0).data_ptr()) % 256 == 0
+    ex.barrier()                                     # no-op in this mode
     # frame assembly
     frame = par.gather_frame(torch.arange(b, e, dtype=torch.float32).unsqueeze(1), 8)
     if rank == 0:
