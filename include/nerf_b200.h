@@ -39,7 +39,12 @@ enum {
 /* Model layouts. Hidden width is 256, rgb hidden 128 (NeRFModel.py:116-140). */
 enum {
   NERF_LAYOUT_LIVE_PE = 0,   /* NeRFmodel(10, 4, 256, pos_encoding=True): 661,636 params */
-  NERF_LAYOUT_LIVE_NOPE = 1  /* NeRFmodel(.., pos_encoding=False):      627,844 params */
+  NERF_LAYOUT_LIVE_NOPE = 1, /* NeRFmodel(.., pos_encoding=False):      627,844 params */
+  /* the same parameter layouts with density = relu(.) instead of softplus(.): what the reference's shipped (legacy)
+   * checkpoints evaluate once remapped onto the live layer table (commented class NeRFModel.py:7-99; no-PE layout of
+   * Phase2/checkpoints_no_pos_encoding) -- see sfm-nerf_b200/legacy.py */
+  NERF_LAYOUT_LIVE_PE_RELU = 2,
+  NERF_LAYOUT_LIVE_NOPE_RELU = 3
 };
 
 int nerf_abi_version(void);

@@ -167,7 +167,7 @@ def _round_st(x, dtype):
 
 
 def model_forward(sd, pos, direction, embed_pos_L=10, embed_direction_L=4, pos_encoding=True,
-                  return_hidden=False, operand_dtype=None):
+                  return_hidden=False, operand_dtype=None, density_activation="softplus"):
     """density [...,1] (softplus), rgb [...,3] (sigmoid).  ``return_hidden`` also returns the
     post-activation tensors in layer order (used by per-layer parity tests).
 
@@ -195,12 +195,71 @@ def model_forward(sd, pos, direction, embed_pos_L=10, embed_direction_L=4, pos_e
     for i in range(3):
         h_full = F.relu(lin(f"fc_layers2.{i}", h))
         h = q(h_full); hidden.append(h)
-    density = F.softplus(head("density_layer", h))             # head reads the (rounded) activation tile
+    dens_act = F.softplus if density_activation == "softplus" else F.relu    # "relu": remapped legacy checkpoints
+    density = dens_act(head("density_layer", h))               # head reads the (rounded) activation tile
     feature = q(F.relu(lin("feature_layer", h))); hidden.append(feature)
     r = q(F.relu(lin("rgb_layer1", torch.cat([feature, de], dim=-1)))); hidden.append(r)
     rgb = torch.sigmoid(head("rgb_layer2", r))
     if return_hidden:
         return density, rgb, hidden
+    return density, rgb
+
+
+# ----------------------------------------------------------------------------------------
+# Legacy checkpoint layouts: the commented-out class NeRFModel.py:7-99 (LEGACY_PE) and the layout of
+# Phase2/checkpoints_no_pos_encoding/final_model.pth (LEGACY_NOPE: no source, by analogy).  ReLU after every Linear of the
+# trunk including the 257-wide one; density = channel 0, feature = channels 1..256; density_fc unused.
+# ----------------------------------------------------------------------------------------
+
+def legacy_init_state_dict(kind, seed=0):
+    """Random legacy-format state_dict: nn.Linear default init, modules created in the order of NeRFModel.py:24-59
+    (fc1, block1, skip_layer, block2, density_fc, rgb_fc), so torch.manual_seed(seed) reproduces the commented class."""
+    torch.manual_seed(seed)
+    sd = OrderedDict()
+
+    def lin(name, i, o):
+        m = torch.nn.Linear(i, o)
+        sd[name + ".weight"], sd[name + ".bias"] = m.weight.detach().clone(), m.bias.detach().clone()
+
+    if kind == "pe":
+        lin("fc1.0", 63, 256)
+        for k in (0, 2): lin(f"block1.{k}", 256, 256)
+        lin("block1.4", 256, 256)
+        lin("skip_layer.0", 319, 256)
+        for k in (0, 2): lin(f"block2.{k}", 256, 256)
+        lin("block2.4", 256, 257)
+        lin("density_fc", 256, 1)
+        lin("rgb_fc.0", 283, 128); lin("rgb_fc.2", 128, 3)
+    else:
+        lin("fc1.0", 3, 256)
+        for k in (0, 2, 4, 6, 8, 10): lin(f"block1.{k}", 256, 256)
+        lin("block1.12", 256, 257)
+        lin("density_fc", 256, 1)
+        lin("rgb_fc.0", 259, 128); lin("rgb_fc.2", 128, 3)
+    return sd
+
+
+def legacy_forward(sd, pos, direction):
+    """(density [...,1], rgb [...,3]) of a legacy state_dict -- NeRFModel.py:74-99 (commented) for the PE layout."""
+    pe_kind = "skip_layer.0.weight" in sd
+    lin = lambda name, x: F.linear(x, sd[name + ".weight"], sd[name + ".bias"])
+    if pe_kind:
+        p, d = position_encoding(pos, 10), position_encoding(direction, 4)
+        out = F.relu(lin("fc1.0", p))
+        for k in (0, 2, 4):
+            out = F.relu(lin(f"block1.{k}", out))
+        out = F.relu(lin("skip_layer.0", torch.cat([out, p], dim=-1)))
+        for k in (0, 2, 4):
+            out = F.relu(lin(f"block2.{k}", out))
+    else:
+        p, d = pos, direction
+        out = F.relu(lin("fc1.0", p))
+        for k in (0, 2, 4, 6, 8, 10, 12):
+            out = F.relu(lin(f"block1.{k}", out))
+    density = out[..., 0:1]
+    feature = out[..., 1:]
+    h = F.relu(lin("rgb_fc.0", torch.cat([feature, d], dim=-1)))
+    rgb = torch.sigmoid(lin("rgb_fc.2", h))
     return density, rgb
 
 

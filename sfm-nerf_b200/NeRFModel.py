@@ -58,6 +58,8 @@ class NeRFmodel(nn.Module):
         self.feature_layer = made["feature_layer"]
         self.rgb_layer1 = made["rgb_layer1"]
         self.rgb_layer2 = made["rgb_layer2"]
+        # "softplus" (NeRFModel.py:192) or "relu": the density activation of the reference's legacy checkpoints (legacy.py)
+        self.density_activation = "softplus"
         self._kernel_state = None        # engine.ModelState, created lazily on the CUDA device
 
     # ------------------------------------------------------------------ kernel plumbing
@@ -69,8 +71,12 @@ class NeRFmodel(nn.Module):
         if self.pos_encoding:
             if (self.embed_pos_L, self.embed_direction_L) != (10, 4):
                 raise NotImplementedError("libnerf_b200 kernels are built for embed_pos_L=10, embed_direction_L=4")
-            return _lib.LAYOUT_LIVE_PE
-        return _lib.LAYOUT_LIVE_NOPE
+            base = _lib.LAYOUT_LIVE_PE
+        else:
+            base = _lib.LAYOUT_LIVE_NOPE
+        if self.density_activation not in ("softplus", "relu"):
+            raise NotImplementedError("density_activation must be 'softplus' or 'relu'")
+        return base + (2 if self.density_activation == "relu" else 0)
 
     def ordered_parameters(self):
         """The 26 parameter tensors in state_dict order (weight, bias per layer)."""
@@ -88,7 +94,7 @@ class NeRFmodel(nn.Module):
             raise _lib.NerfB200Error("NeRFmodel parameters are on %s: the sm_100a kernels need a CUDA device "
                                      "(there is no CPU fallback)" % dev)
         st = self._kernel_state
-        if st is None or st.device != dev or not st.owns(params):
+        if st is None or st.device != dev or st.layout != self.layout_id or not st.owns(params):
             st = engine.ModelState.adopt(self.layout_id, params)
             self._kernel_state = st
         st.refresh_packed(params)

@@ -3,10 +3,12 @@ Phase2 call surface of ColinBalfour/SfM-NeRF.  The directory name carries a hyph
 name); import it as ``sfmnerf_b200`` (alias module at the repo root) or with
 ``importlib.import_module("sfm-nerf_b200")``.
 """
-from . import _lib, engine, parallel, synthetic  # noqa: F401
+from . import _lib, engine, legacy, parallel, synthetic  # noqa: F401
 from .NeRFModel import NeRFmodel  # noqa: F401
+from .legacy import convert_legacy_state_dict, load_legacy_checkpoint  # noqa: F401
 from .train import (PixelToRay, configParser, generateBatch, loadDataset, loss, main, render,  # noqa: F401
                     render_full, test, test_image, train)
 
 __all__ = ["NeRFmodel", "PixelToRay", "generateBatch", "render", "render_full", "loss", "test_image", "train",
-           "test", "main", "configParser", "loadDataset", "engine", "synthetic"]
+           "test", "main", "configParser", "loadDataset", "engine", "synthetic", "legacy", "load_legacy_checkpoint",
+           "convert_legacy_state_dict"]

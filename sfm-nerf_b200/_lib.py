@@ -19,6 +19,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 LAYOUT_LIVE_PE = 0
 LAYOUT_LIVE_NOPE = 1
+LAYOUT_LIVE_PE_RELU = 2       # same parameters, density = relu(.): remapped legacy checkpoints (legacy.py)
+LAYOUT_LIVE_NOPE_RELU = 3
 
 
 class NerfB200Error(RuntimeError):

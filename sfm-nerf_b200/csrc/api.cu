@@ -64,9 +64,9 @@ inline int mlp_grid(const DeviceInfo& dev, int n_tiles) {
 inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
 const ModelLayout* get_layout(int layout) {
-  static ModelLayout cache[2];
-  static bool ready[2] = {false, false};
-  if (layout < 0 || layout > 1) return nullptr;
+  static ModelLayout cache[kNumLayouts];
+  static bool ready[kNumLayouts] = {};
+  if (layout < 0 || layout >= kNumLayouts) return nullptr;
   if (!ready[layout]) { build_model_layout(layout, cache[layout]); ready[layout] = true; }
   return &cache[layout];
 }
@@ -75,7 +75,7 @@ void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t
   std::memset(&a, 0, sizeof(a));
   a.packed = static_cast<const uint8_t*>(packed);
   a.small = reinterpret_cast<const float*>(a.packed + m.small_off);
-  a.pos_L = m.pos_L; a.dir_L = m.dir_L;
+  a.pos_L = m.pos_L; a.dir_L = m.dir_L; a.density_relu = m.density_relu;
   a.sm_wd = m.sm_wd; a.sm_bd = m.sm_bd; a.sm_w2 = m.sm_w2; a.sm_b2 = m.sm_b2;
   a.n_rows = n_rows;
   a.n_tiles = (int)((n_rows + 127) / 128);

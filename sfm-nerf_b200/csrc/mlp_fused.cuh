@@ -50,6 +50,7 @@ struct MlpArgs {
   const float* z;
   int32_t n_sample;
   int32_t pos_L, dir_L;
+  int32_t density_relu;      // density head activation: 1 = ReLU (legacy checkpoints), 0 = softplus
   int32_t sm_wd, sm_bd, sm_w2, sm_b2;
   int64_t n_rows;
   int32_t n_tiles;
@@ -438,7 +439,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           o = reinterpret_cast<const float4*>(a.sigma_rgb)[grow];
         }
         if (tile_ok) r1m = __ldg(reinterpret_cast<const uint4*>(stash_tile + a.st_mask + 10 * 4096) + row * 2);
-        dsp = d.x * (1.0f - expf(-o.x));               // softplus'(x) = 1 - exp(-softplus(x))
+        dsp = a.density_relu ? (o.x > 0.0f ? d.x : 0.0f)                 // relu'
+                             : d.x * (1.0f - expf(-o.x));              // softplus'(x) = 1 - exp(-softplus(x))
         const float d0 = d.y * o.y * (1.0f - o.y), d1 = d.z * o.z * (1.0f - o.z), d2 = d.w * o.w * (1.0f - o.w);
         if (tile_ok) reinterpret_cast<float4*>(dstash_tile + a.ds_sr)[row] = make_float4(dsp, d0, d1, d2);
         const float* w2 = sm + a.sm_w2;
@@ -569,7 +571,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
               d0 = fmaf(__uint_as_float(x2 << 16), wb.x, d0); d1 = fmaf(__uint_as_float(x2 & 0xffff0000u), wb.y, d1);
               d2 = fmaf(__uint_as_float(x3 << 16), wb.z, d2); d3 = fmaf(__uint_as_float(x3 & 0xffff0000u), wb.w, d3);
             }
-            sigma_keep = softplus_f((d0 + d1) + (d2 + d3) + sm[a.sm_bd]);
+            const float pre = (d0 + d1) + (d2 + d3) + sm[a.sm_bd];
+            sigma_keep = a.density_relu ? fmaxf(pre, 0.0f) : softplus_f(pre);
           }
           if (is_rgb) {                                // rgb_layer2 + sigmoid on r1 (NeRFModel.py:199-200)
             const float4* w2 = reinterpret_cast<const float4*>(sm + a.sm_w2);

@@ -82,8 +82,14 @@ struct WgradItem {
 };
 constexpr int kMaxWgradItems = 16;
 
+// layout ids: 0 = live, positional encoding (10, 4); 1 = live, pos_encoding=False; 2 / 3 = the same parameter layouts with a
+// ReLU density head instead of softplus -- what the reference's shipped (legacy) checkpoints evaluate once their weights
+// are remapped onto the live layer table (sfm-nerf_b200/legacy.py; SURVEY A.4, commented class NeRFModel.py:7-99).
+constexpr int kNumLayouts = 4;
+
 struct ModelLayout {
   int32_t layout;
+  int32_t density_relu;              // 1: density = relu(.) (legacy checkpoints), 0: softplus (NeRFModel.py:192)
   int32_t pos_in, dir_in;            // 63/27 or 3/3
   int32_t pos_L, dir_L;              // 10/4 or 0/0
   int32_t n_params;
@@ -107,10 +113,11 @@ struct ModelLayout {
 enum { L_FC1 = 0, L_FC0 = 1, L_SKIP = 5, L_FC2_0 = 6, L_DENS = 9, L_FEAT = 10, L_RGB1 = 11, L_RGB2 = 12 };
 
 inline bool build_model_layout(int layout, ModelLayout& m) {
-  if (layout != 0 && layout != 1) return false;
+  if (layout < 0 || layout >= kNumLayouts) return false;
   m = ModelLayout{};
   m.layout = layout;
-  const bool pe = (layout == 0);
+  m.density_relu = layout >= 2 ? 1 : 0;
+  const bool pe = (layout & 1) == 0;
   m.pos_L = pe ? 10 : 0; m.dir_L = pe ? 4 : 0;
   m.pos_in = pe ? 63 : 3; m.dir_in = pe ? 27 : 3;
   const int C = 256;

@@ -262,7 +262,14 @@ def test(images, poses, camera_info, args):
     if not found:
         raise FileNotFoundError(f"no checkpoint under {args.checkpoint_path}")
     ckpt = torch.load(found[0], map_location=dev, weights_only=False)
-    model.load_state_dict(ckpt["model_state_dict"] if "model_state_dict" in ckpt else ckpt)
+    sd = ckpt["model_state_dict"] if "model_state_dict" in ckpt else ckpt
+    if "fc1.0.weight" in sd:
+        # one of the reference's shipped checkpoints (legacy key names): the reference's own loader fails on
+        # these (train.py:603); here they are remapped onto the live layer table and run on the same kernels
+        from .legacy import load_legacy_checkpoint
+        model = load_legacy_checkpoint(sd, dev)
+    else:
+        model.load_state_dict(sd)
     model.eval()
     picks = np.random.choice(len(images), size=min(5, len(images)), replace=False)
     os.makedirs(args.images_path, exist_ok=True)

@@ -523,3 +523,48 @@ def test_short_training_tracks_oracle(pkg, orc):
     assert abs(mine[0] - ref[0]) < 1e-3
     assert np.mean(np.abs(mine[-10:] - ref[-10:])) < 0.15 * np.mean(ref[-10:]) + 2e-3
     assert mine[-10:].mean() < mine[:5].mean()
+
+
+@pytest.mark.parametrize("kind", ["pe", "nope"])
+def test_legacy_checkpoint_layouts(pkg, orc, kind):
+    """The reference's shipped checkpoint layouts (BASELINE config 3 names the no-PE one): imported with
+    sfm-nerf_b200/legacy.py they run on the same kernels (layouts 2 / 3: ReLU density head).  Forward against the oracle's
+    restatement of the legacy class, render + backward against the bf16-operand restatement of the remapped model."""
+    sd = orc.legacy_init_state_dict(kind, 3)
+    m = pkg.load_legacy_checkpoint(sd, "cuda")
+    assert m.density_activation == "relu" and m.layout_id == (2 if kind == "pe" else 3)
+    gen = torch.Generator().manual_seed(21)
+    pos = (torch.rand(700, 3, generator=gen) - 0.5) * 4.0
+    dirs = torch.nn.functional.normalize(torch.randn(700, 3, generator=gen), dim=-1)
+    with torch.no_grad():
+        density, rgb = m(pos.cuda(), dirs.cuda())
+        d0, c0 = orc.legacy_forward(sd, pos, dirs)
+    assert float(d0.max()) > 0.0
+    assert float((density.cpu() - d0).abs().max()) < 5e-3 + 2e-2 * float(d0.abs().max())
+    assert float((rgb.cpu() - c0).abs().max()) < 5e-3
+    assert bool(((density.cpu() == 0) == (d0 == 0)).float().mean() > 0.98)       # the ReLU clips the same samples (up to bf16 ties)
+
+    # training through the ReLU density head: gradients of the remapped model
+    live, pos_encoding = pkg.convert_legacy_state_dict(sd)
+    cam = orc.make_camera_info(48, 48)
+    pose = orc.look_at_pose(75.0, -15.0)
+    px = torch.randint(0, 48, (150, 2), generator=gen).numpy()
+    rays = orc.rays_from_indices(np.zeros((1, 48, 48, 3)), pose[None], cam, np.zeros(150, int), px[:, 0], px[:, 1])
+    o, d = torch.tensor(rays[:, 0:3]), torch.tensor(rays[:, 3:6])
+    target = torch.rand(150, 3, generator=gen)
+    kw = dict(pos_encoding=pos_encoding, density_activation="relu")
+    loss_ref, _ = orc.loss_and_grads(live, o, d, target, 64, **kw)
+    _, g_bf = orc.loss_and_grads(live, o, d, target, 64, operand_dtype=torch.bfloat16, **kw)
+    loss = pkg.loss(pkg.render(m, o.cuda(), d.cuda(), _ns(n_sample=64, perturb=False)), target.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 2e-3
+    worst = 0.0
+    for name, p in m.named_parameters():
+        ref = g_bf[name]
+        if float(ref.norm()) < 1e-12:
+            assert float(p.grad.norm()) < 1e-6, name                  # e.g. the unused position columns see no gradient signal
+            continue
+        rel = float((p.grad.cpu() - ref).norm() / ref.norm())
+        worst = max(worst, rel)
+        assert rel < 2.5 * GRAD_REL_TOL, (name, rel)
+    print(f"legacy {kind}: loss {loss.item():.5f} (oracle {loss_ref.item():.5f}), worst gradient rel-L2 vs bf16-operand oracle {worst:.2e}")
