@@ -34,7 +34,8 @@ def test_abi_queries_without_gpu(libmod):
     lib = libmod.load()
     assert lib.nerf_abi_version() == 1
     assert lib.nerf_param_count(0) == 661636 and lib.nerf_param_count(1) == 627844
-    assert lib.nerf_param_count(2) == -4
+    assert lib.nerf_param_count(2) == 661636 and lib.nerf_param_count(3) == 627844      # ReLU-density (legacy checkpoint) layouts
+    assert lib.nerf_param_count(4) == -4
     assert b"sm_100" in lib.nerf_error_string(-3)
     # tile rounding of the stash queries
     assert lib.nerf_mlp_stash_bytes(0, 1) == lib.nerf_mlp_stash_bytes(0, 128)
