@@ -4,6 +4,7 @@ name); import it as ``sfmnerf_b200`` (alias module at the repo root) or with
 ``importlib.import_module("sfm-nerf_b200")``.
 """
 from . import _lib, engine, legacy, parallel, synthetic  # noqa: F401
+from . import Wrapper  # noqa: F401  (name-compatible mirror of the reference's older Phase2/Wrapper.py driver)
 from .NeRFModel import NeRFmodel  # noqa: F401
 from .legacy import convert_legacy_state_dict, load_legacy_checkpoint  # noqa: F401
 from .train import (PixelToRay, configParser, generateBatch, loadDataset, loss, main, render,  # noqa: F401
