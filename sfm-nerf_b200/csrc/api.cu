@@ -16,7 +16,11 @@ using namespace nerf;
 
 namespace {
 
-struct DeviceInfo { int device = -1; int sms = 0; int cc_major = 0; int mlp_clusters = 0; bool attrs_set = false; };
+struct DeviceInfo {
+  int device = -1; int sms = 0; int cc_major = 0; int mlp_clusters = 0; bool attrs_set = false;
+  // fork/join helpers of nerf_mlp_wgrad: the CUDA-core head-gradient kernel runs beside the tcgen05 kernel (stream-ordered)
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
 thread_local DeviceInfo g_dev;
 long long* g_trace = nullptr;      // diagnostics only (nerf_debug_trace)
 
@@ -336,18 +340,29 @@ int nerf_mlp_wgrad(int layout, const void* stash, const void* dstash, int64_t n_
     ctas += n_cta[i];
   }
   w.cta_begin[m->n_wgrad] = ctas;
-  wgrad_kernel<<<ctas, 192, kWgSmemBytes, s>>>(w);
-  NERF_LAUNCH_CHECK();
-
-  // head gradients (density_layer, rgb_layer2)
+  // head gradients (density_layer, rgb_layer2) on CUDA cores.  Both kernels are HBM-bound streams over the same stashes and
+  // fit on an SM together (no shared memory / 21 K registers here, one 197 KB CTA there), so the small one is forked onto a
+  // side stream after the gradient memset and joined back: everything stays ordered on the caller's stream.
   HeadGradArgs h{};
   h.stash = w.stash; h.dstash = w.dstash; h.grads = grads;
   h.stash_tile_bytes = m->stash_tile_bytes; h.dstash_tile_bytes = m->dstash_tile_bytes; h.n_tiles = n_tiles;
   h.st_h8 = m->st_h[8]; h.st_r1 = m->st_r1; h.ds_sr = m->ds_sr;
   h.g_wd = m->w_off[L_DENS]; h.g_bd = m->b_off[L_DENS]; h.g_w2 = m->w_off[L_RGB2]; h.g_b2 = m->b_off[L_RGB2];
-  const int hgrid = n_tiles < 4 * dev->sms ? n_tiles : 4 * dev->sms;
-  head_grad_kernel<<<hgrid, 384, 0, s>>>(h);
+  // few blocks: every block ends with one atomic per gradient element (644 addresses), which serialise per address in L2
+  const int hgrid = n_tiles < 2 * dev->sms ? n_tiles : 2 * dev->sms;
+  if (!dev->side) {
+    NERF_CUDA_TRY(cudaStreamCreateWithFlags(&dev->side, cudaStreamNonBlocking));
+    NERF_CUDA_TRY(cudaEventCreateWithFlags(&dev->ev_fork, cudaEventDisableTiming));
+    NERF_CUDA_TRY(cudaEventCreateWithFlags(&dev->ev_join, cudaEventDisableTiming));
+  }
+  NERF_CUDA_TRY(cudaEventRecord(dev->ev_fork, s));
+  NERF_CUDA_TRY(cudaStreamWaitEvent(dev->side, dev->ev_fork, 0));
+  head_grad_kernel<<<hgrid, 384, 0, dev->side>>>(h);
   NERF_LAUNCH_CHECK();
+  NERF_CUDA_TRY(cudaEventRecord(dev->ev_join, dev->side));
+  wgrad_kernel<<<ctas, 192, kWgSmemBytes, s>>>(w);
+  NERF_LAUNCH_CHECK();
+  NERF_CUDA_TRY(cudaStreamWaitEvent(s, dev->ev_join, 0));
   return NERF_OK;
 }
 

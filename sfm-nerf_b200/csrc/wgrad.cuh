@@ -237,7 +237,6 @@ struct HeadGradArgs {
 // Every thread owns one k-core (8 channels) and every 8th row of a tile: 16-byte loads, eight neighbouring threads read 128
 // contiguous bytes.  Partial sums are reduced over the 8 row-phases with shuffles at the end.
 __global__ void __launch_bounds__(384) head_grad_kernel(const HeadGradArgs a) {
-  __shared__ float4 dsr[128];
   const int t = threadIdx.x;
   const bool dens = t < 256;
   const int kc = dens ? (t >> 3) : ((t - 256) >> 3);       // k-core of h8 (32) / r1 (16)
@@ -248,17 +247,17 @@ __global__ void __launch_bounds__(384) head_grad_kernel(const HeadGradArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
   float accb0 = 0.f, accb1 = 0.f, accb2 = 0.f, accbd = 0.f;
+  // no block-level staging or barriers: the per-row cotangents (16 B) are read through L1 by the 48 threads that need them,
+  // so consecutive tiles' loads overlap freely
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const uint8_t* st = a.stash + (size_t)tile * a.stash_tile_bytes;
-    __syncthreads();
-    if (t < 128) dsr[t] = reinterpret_cast<const float4*>(a.dstash + (size_t)tile * a.dstash_tile_bytes + a.ds_sr)[t];
-    __syncthreads();
+    const float4* dsr = reinterpret_cast<const float4*>(a.dstash + (size_t)tile * a.dstash_tile_bytes + a.ds_sr);
     const uint4* src = reinterpret_cast<const uint4*>(st + (dens ? a.st_h8 : a.st_r1) + kc * kKcoreBytes);
-#pragma unroll 4
+#pragma unroll 8
     for (int i = 0; i < 16; ++i) {
       const int r = rp + 8 * i;
       const uint4 u = __ldg(src + r);
-      const float4 d = dsr[r];
+      const float4 d = __ldg(dsr + r);
       float v[8] = {__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u),
                     __uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u), __uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u)};
       if (dens) {
@@ -269,7 +268,7 @@ __global__ void __launch_bounds__(384) head_grad_kernel(const HeadGradArgs a) {
         for (int j = 0; j < 8; ++j) { acc[0][j] = fmaf(d.y, v[j], acc[0][j]); acc[1][j] = fmaf(d.z, v[j], acc[1][j]); acc[2][j] = fmaf(d.w, v[j], acc[2][j]); }
       }
     }
-    if (t < 128) { const float4 d = dsr[t]; accbd += d.x; accb0 += d.y; accb1 += d.z; accb2 += d.w; }   // bias sums: thread = row
+    if (t < 128) { const float4 d = __ldg(dsr + t); accbd += d.x; accb0 += d.y; accb1 += d.z; accb2 += d.w; }   // bias sums: thread = row
   }
   // reduce over the 8 row phases (lanes differing in bits 0-2)
 #pragma unroll
