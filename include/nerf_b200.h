@@ -174,9 +174,9 @@ int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, in
  * Diagnostics only: synchronises the device and is the one entry point that allocates.
  * ------------------------------------------------------------------------------------- */
 int nerf_selftest_umma(int variant, float* result_host);
-/* Diagnostics: when device_buffer != NULL, CTA 0 of the fused MLP kernels writes clock64 stamps
- * [pair][step 0..11][tile slot 0..1][4] = (MMA issue start, MMA issue end, accumulator ready seen by
- * the epilogue, next-layer release) into it (int64; 8 pairs fit in 8*12*2*4 entries).  NULL disables. */
+/* Diagnostics: when device_buffer != NULL, CTA 0 (the leader of cluster 0) of the fused MLP kernels writes clock64 stamps
+ * [cluster iteration][step 0..11][tile slot 0..1][4] = (MMA issue start, MMA issue end, accumulator ready seen by the
+ * epilogue, next-layer release) into it (int64; 8 iterations fit in 8*12*2*4 entries).  NULL disables.  tools/trace_mlp.py. */
 int nerf_debug_trace(void* device_buffer);
 /* Diagnostics: issue-rate microbenchmark of 128x256x16 UMMAs on one SM (variant: 0 one thread / one accumulator,
  * 1 one thread / two accumulators, 2 two threads / one accumulator each, 3 one thread / N=128 halves,

@@ -85,7 +85,6 @@ void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t
   a.n_tiles = (int)((n_rows + 127) / 128);
   a.stash_tile_bytes = m.stash_tile_bytes; a.dstash_tile_bytes = m.dstash_tile_bytes;
   a.trace = g_trace;
-  { const char* e = getenv("NERF_EXP"); a.exp_flags = e ? atoi(e) : 0; }
   a.st_pe = m.st_pe; a.st_de = m.st_de; a.st_r1 = m.st_r1; a.st_mask = m.st_mask; a.ds_y10 = m.ds_y[10]; a.ds_sr = m.ds_sr;
 }
 

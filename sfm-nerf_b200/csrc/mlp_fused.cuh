@@ -60,7 +60,6 @@ struct MlpArgs {
   uint8_t* dstash;           // bwd: written
   int32_t stash_tile_bytes, dstash_tile_bytes;
   int32_t st_pe, st_de, st_r1, st_mask, ds_y10, ds_sr;
-  int32_t exp_flags;         // diagnostics (NERF_EXP env): 1 = skip stash stores
   long long* trace;          // diagnostics: per-(pair,step,slot) clock64 stamps of CTA 0 (or null)
   Program prog;
 };
@@ -600,7 +599,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             }
           }
         }
-        if (MODE == MODE_FWD && store_out && !(a.exp_flags & 1)) {
+        if (MODE == MODE_FWD && store_out) {
           // Training stash: this thread reads back the 16-byte pieces of ITS OWN row of the bf16 tile it
           // just wrote and streams them to HBM (a warp writes 512 contiguous bytes per instruction), and
           // folds them into the ReLU bit masks (bit of column c in a 32-column chunk: (c>>1) + 16*(c&1)).
