@@ -142,6 +142,15 @@ int nerf_composite_forward(const float* sigma_rgb, const float* z, int64_t n_ray
                            float* rgb, float* depth, float* acc, void* stream);
 int nerf_composite_backward(const float* sigma_rgb, const float* z, const float* g_rgb,
                             int64_t n_rays, int n_sample, float* d_sigma_rgb, void* stream);
+/* Training form of K5 (train.py:248-269 + 460 + autograd): compositing forward, MSE over n_rays*3, its gradient and the
+ * compositing backward in ONE launch: loss[0] = mean((rgb - target)^2), d_sigma_rgb[n,4] = grad_scale * dL/d(sigma, r, g, b).
+ * The loss is reduced deterministically (per-block partial sums, last block adds them in order).  workspace:
+ * nerf_composite_train_workspace_bytes(n_rays) bytes, zero-filled before the FIRST use (the kernel leaves it ready for the
+ * next call).  n_sample <= 256. */
+int64_t nerf_composite_train_workspace_bytes(int64_t n_rays);
+int nerf_composite_train(const float* sigma_rgb, const float* z, const float* target, int64_t n_rays, int n_sample,
+                         float grad_scale, float* loss, float* d_sigma_rgb, void* workspace, void* stream);
+
 /* MSE over n_rays*3 (train.py:460): loss[0] = mean((rgb-target)^2) and, when g_rgb != NULL,
  * g_rgb = grad_scale * 2*(rgb-target)/(3*n_rays). */
 int nerf_mse_loss(const float* rgb, const float* target, int64_t n_rays, float grad_scale,

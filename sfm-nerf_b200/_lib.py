@@ -81,6 +81,8 @@ PROTOTYPES = {
     "nerf_composite_backward": (_I, [_P, _P, _P, _L, _I, _P, _P]),
     "nerf_debug_umma_rate": (_I, [_I, _I, _P]),
     "nerf_adam_step_reduce": (_I, [_P, _P, _I, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
+    "nerf_composite_train_workspace_bytes": (_L, [_L]),
+    "nerf_composite_train": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P, _P]),
     "nerf_mse_loss": (_I, [_P, _P, _L, _F, _P, _P, _P]),
     "nerf_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
     "nerf_selftest_umma": (_I, [_I, _P]),

@@ -236,14 +236,12 @@ int nerf_mlp_pack_weights(const float* params, int layout, void* packed, void* s
   if (!params || !packed) return NERF_ERR_ARG;
   if (!nerf_aligned(packed, 16)) return NERF_ERR_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
-  pack_images_kernel<<<dim3(64, m->fwd.n_steps), 256, 0, s>>>(params, m->fwd, static_cast<uint8_t*>(packed));
-  NERF_LAUNCH_CHECK();
-  pack_images_kernel<<<dim3(64, m->bwd.n_steps), 256, 0, s>>>(params, m->bwd, static_cast<uint8_t*>(packed));
-  NERF_LAUNCH_CHECK();
   PackSmallArgs p{};
   p.wd_src = m->w_off[L_DENS]; p.bd_src = m->b_off[L_DENS]; p.w2_src = m->w_off[L_RGB2]; p.b2_src = m->b_off[L_RGB2];
   p.sm_wd = m->sm_wd; p.sm_bd = m->sm_bd; p.sm_w2 = m->sm_w2; p.sm_b2 = m->sm_b2;
-  pack_small_kernel<<<2, 256, 0, s>>>(params, p, reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + m->small_off));
+  // one launch: grid.y = forward steps, dgrad steps, then one row of blocks for the fp32 head table
+  pack_all_kernel<<<dim3(64, m->fwd.n_steps + m->bwd.n_steps + 1), 256, 0, s>>>(
+      params, m->fwd, m->bwd, p, static_cast<uint8_t*>(packed), reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + m->small_off));
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
@@ -400,6 +398,30 @@ int nerf_composite_backward(const float* sigma_rgb, const float* z, const float*
   if (n_rays == 0) return NERF_OK;
   composite_backward_kernel<<<blocks_for(n_rays, kCompWarpsPerBlock), kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(sigma_rgb), z, g_rgb, n_rays, n_sample, reinterpret_cast<float4*>(d_sigma_rgb));
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int64_t nerf_composite_train_workspace_bytes(int64_t n_rays) {
+  if (n_rays < 0) return NERF_ERR_ARG;
+  return (int64_t)sizeof(float) * (blocks_for(n_rays, kCompWarpsPerBlock) + 1);
+}
+
+int nerf_composite_train(const float* sigma_rgb, const float* z, const float* target, int64_t n_rays, int n_sample,
+                         float grad_scale, float* loss, float* d_sigma_rgb, void* workspace, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!sigma_rgb || !z || !target || !loss || !d_sigma_rgb || !workspace || n_rays <= 0 || n_sample <= 0 ||
+      n_sample > 32 * kCompMaxChunks)
+    return NERF_ERR_ARG;
+  if (!nerf_aligned(sigma_rgb, 16) || !nerf_aligned(d_sigma_rgb, 16) || !nerf_aligned(workspace, 4)) return NERF_ERR_ALIGN;
+  const unsigned blocks = blocks_for(n_rays, kCompWarpsPerBlock);
+  float* partial = static_cast<float*>(workspace);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + blocks);      /* zero before first use; the kernel re-zeroes it */
+  composite_train_kernel<<<blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(sigma_rgb), z, target, n_rays, n_sample, grad_scale, loss, partial, ticket,
+      reinterpret_cast<float4*>(d_sigma_rgb));
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }

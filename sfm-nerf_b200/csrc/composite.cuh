@@ -133,6 +133,90 @@ composite_backward_kernel(const float4* __restrict__ sigma_rgb, const float* __r
   }
 }
 
+// Training form: compositing forward + MSE (train.py:460) + its gradient + compositing backward in ONE launch.  One warp
+// per ray runs the forward pass, forms g = dL/d rgb of its ray, then the backward pass (the second read of the ray's
+// samples hits L1/L2).  The loss is reduced deterministically: per-block partial sums go to `partial`, the last block to
+// finish (ticket counter behind `partial`) adds them in index order and resets the counter.
+__global__ void __launch_bounds__(kCompWarpsPerBlock * 32)
+composite_train_kernel(const float4* __restrict__ sigma_rgb, const float* __restrict__ z, const float* __restrict__ target,
+                       int64_t n_rays, int S, float grad_scale, float* __restrict__ loss, float* __restrict__ partial,
+                       unsigned int* __restrict__ ticket, float4* __restrict__ d_sigma_rgb) {
+  __shared__ float red[kCompWarpsPerBlock];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t ray = (int64_t)blockIdx.x * kCompWarpsPerBlock + wib;
+  const int n_chunks = (S + 31) >> 5;
+  float sq = 0.0f;
+  if (ray < n_rays) {
+    const float4* sr = sigma_rgb + ray * S;
+    const float* zr = z + ray * S;
+    float Tk[kCompMaxChunks], wk[kCompMaxChunks], fk[kCompMaxChunks], omk[kCompMaxChunks];
+    float carry = 1.0f, ar = 0.f, ag = 0.f, ab = 0.f;
+#pragma unroll
+    for (int c = 0; c < kCompMaxChunks; ++c) {
+      if (c < n_chunks) {
+        const int s = c * 32 + lane;
+        float om = 1.0f, alpha = 0.0f, delta = 0.0f;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < S) {
+          v = __ldg(sr + s);
+          sample_alpha(zr, s, S, v.x, delta, alpha);
+          om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+        }
+        const float incl = warp_incl_prod(om, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        Tk[c] = carry * excl;
+        wk[c] = alpha * Tk[c];
+        fk[c] = delta * (1.0f - alpha);
+        omk[c] = om;
+        ar += wk[c] * v.y; ag += wk[c] * v.z; ab += wk[c] * v.w;
+        carry *= __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab);
+    const float d0 = ar - target[3 * ray + 0], d1 = ag - target[3 * ray + 1], d2 = ab - target[3 * ray + 2];
+    sq = d0 * d0 + d1 * d1 + d2 * d2;
+    const float gs = grad_scale * 2.0f / (float)(3 * n_rays);
+    const float g0 = gs * d0, g1 = gs * d1, g2 = gs * d2;
+    float tail = 0.0f;
+#pragma unroll
+    for (int c = kCompMaxChunks - 1; c >= 0; --c) {
+      if (c < n_chunks) {
+        const int s = c * 32 + lane;
+        float gc = 0.0f;
+        if (s < S) { const float4 v = __ldg(sr + s); gc = g0 * v.y + g1 * v.z + g2 * v.w; }
+        const float wgc = wk[c] * gc;
+        const float incl = warp_incl_sum(wgc, lane);
+        const float total = __shfl_sync(0xffffffffu, incl, 31);
+        const float suffix = tail + (total - incl);
+        if (s < S) {
+          const float dalpha = Tk[c] * gc - suffix / omk[c];
+          d_sigma_rgb[ray * S + s] = make_float4(fk[c] * dalpha, wk[c] * g0, wk[c] * g1, wk[c] * g2);
+        }
+        tail += total;
+      }
+    }
+  }
+  if (lane == 0) red[wib] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.0f;
+    for (int w = 0; w < kCompWarpsPerBlock; ++w) b += red[w];
+    partial[blockIdx.x] = b;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && wib == 0) {
+    __threadfence();
+    float acc = 0.0f;
+    for (unsigned int i = lane; i < gridDim.x; i += 32) acc += __ldcg(partial + i);     // fixed order per lane, fixed tree below
+    acc = warp_sum(acc);
+    if (lane == 0) { loss[0] = acc / (float)(3 * n_rays); *ticket = 0u; }
+  }
+}
+
 // train.py:460 nn.MSELoss (mean over n*3) and its gradient; single block.
 __global__ void __launch_bounds__(1024)
 mse_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ target, int64_t n3,

@@ -639,8 +639,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
 // ---------------------------------------------------------------------------------------------
 // Weight packing: flat fp32 parameters -> bf16 UMMA images (fwd + transposed dgrad) + fp32 table.
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_images_kernel(const float* __restrict__ params, Program prog, uint8_t* __restrict__ packed) {
-  const Step st = prog.s[blockIdx.y];
+__device__ __forceinline__ void pack_image_step(const float* __restrict__ params, const Step& st, uint8_t* __restrict__ packed) {
   const int total_k = (st.act_ksteps + st.enc_ksteps + st.bias_kstep) * 16;
   const int n_elems = total_k * st.n;
   __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(packed + st.w_off);
@@ -676,12 +675,22 @@ struct PackSmallArgs {
   int32_t wd_src, bd_src, w2_src, b2_src;
   int32_t sm_wd, sm_bd, sm_w2, sm_b2;
 };
-__global__ void pack_small_kernel(const float* __restrict__ params, PackSmallArgs p, float* __restrict__ small) {
+__device__ __forceinline__ void pack_small(const float* __restrict__ params, const PackSmallArgs& p, float* __restrict__ small) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 256) small[p.sm_wd + i] = params[p.wd_src + i];
   if (i < 384) small[p.sm_w2 + i] = params[p.w2_src + i];
   if (i < 3) small[p.sm_b2 + i] = params[p.b2_src + i];
   if (i == 0) { small[p.sm_bd] = params[p.bd_src]; small[p.sm_bd + 1] = 0.f; small[p.sm_bd + 2] = 0.f; small[p.sm_bd + 3] = 0.f; small[p.sm_b2 + 3] = 0.f; }
+}
+
+// Everything the MLP kernels read, from the flat fp32 parameters, in one launch: blockIdx.y selects a forward step, a dgrad
+// step, or (last row) the fp32 head table.
+__global__ void pack_all_kernel(const float* __restrict__ params, const __grid_constant__ Program fwd, const __grid_constant__ Program bwd,
+                                const PackSmallArgs small_args, uint8_t* __restrict__ packed, float* __restrict__ small) {
+  const int y = blockIdx.y;
+  if (y < fwd.n_steps) pack_image_step(params, fwd.s[y], packed);
+  else if (y < fwd.n_steps + bwd.n_steps) pack_image_step(params, bwd.s[y - fwd.n_steps], packed);
+  else if (blockIdx.x < 2) pack_small(params, small_args, small);
 }
 
 }  // namespace nerf

@@ -328,7 +328,7 @@ class Trainer:
         rows = self.n_rays * self.n_sample
         self.stash = alloc_stash(self.st, rows)
         self.dstash = alloc_dstash(self.st, rows)
-        self.g_rgb = torch.empty((self.n_rays, 3), dtype=torch.float32, device=dev)
+        self.comp_ws, self.comp_ws_rays = None, 0     # workspace of nerf_composite_train, sized for the largest batch seen
         self.iteration = 0
         self.launches_per_step = 0
 
@@ -358,12 +358,15 @@ class Trainer:
                      offset=ctr * ((n_rays * S + 3) // 4))
         with _timed(timers, "mlp_fwd"):
             sigma_rgb = mlp_forward_rays(st, o, d, z, self.stash)
-        with _timed(timers, "composite_fwd"):
-            rgb, _, _ = composite_forward(sigma_rgb, z, extras=False)
-        # local mean over this rank's rays; the allreduce sum is scaled by 1/world inside Adam
-        call("nerf_mse_loss", ptr(rgb), ptr(tgt), n_rays, 1.0, ptr(self.loss), ptr(self.g_rgb), stream_ptr())
-        with _timed(timers, "composite_bwd"):
-            dsr = composite_backward(sigma_rgb, z, self.g_rgb[:n_rays])
+        # compositing forward + MSE + compositing backward in one launch; local mean over this rank's rays (the sum over
+        # ranks is scaled by 1/world inside Adam)
+        if n_rays > self.comp_ws_rays:
+            self.comp_ws = torch.zeros(int(_lib.load().nerf_composite_train_workspace_bytes(n_rays)) // 4 + 1, dtype=torch.float32, device=dev)
+            self.comp_ws_rays = n_rays
+        with _timed(timers, "composite_train"):
+            dsr = torch.empty_like(sigma_rgb)
+            call("nerf_composite_train", ptr(sigma_rgb), ptr(z), ptr(tgt), n_rays, S, 1.0, ptr(self.loss), ptr(dsr),
+                 ptr(self.comp_ws), stream_ptr())
         rows = n_rays * S
         with _timed(timers, "mlp_dgrad"):
             call("nerf_mlp_dgrad", ptr(st.packed), st.layout, ptr(self.stash), ptr(sigma_rgb), ptr(dsr), rows,
@@ -373,7 +376,7 @@ class Trainer:
             self.grads = ex.local(self.iteration)
         with _timed(timers, "mlp_wgrad"):
             call("nerf_mlp_wgrad", st.layout, ptr(self.stash), ptr(self.dstash), rows, ptr(self.grads), 0, stream_ptr())
-        launches += 8                               # sample, mlp fwd, comp fwd, mse, comp bwd, dgrad, wgrad, heads (+1 memset)
+        launches += 6                               # sample, mlp fwd, composite_train, dgrad, wgrad, heads (+1 memset)
         lr = self.lr()
         if ex is not None and ex.mode != "nccl":
             # the gradient exchange is fused into the optimiser: barrier, then Adam reads the sum over ranks through NVLink
@@ -391,6 +394,6 @@ class Trainer:
             call("nerf_adam_step", ptr(st.flat), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), st.n_params,
                  lr, self.betas[0], self.betas[1], self.eps, self.iteration, parallel.mean_scale(self.world), stream_ptr())
         st.pack()
-        launches += 4
+        launches += 2                               # adam, pack
         self.launches_per_step = launches
         return self.loss

@@ -154,6 +154,26 @@ def test_composite_forward_backward(pkg, orc):
         np.testing.assert_allclose(d[..., 1:].numpy(), dc_ref.numpy(), rtol=1e-5, atol=2e-6)
 
 
+def test_composite_train_fused(pkg, orc):
+    """nerf_composite_train (forward + MSE + backward in one launch) equals the three separate entry points."""
+    gen = torch.Generator().manual_seed(4)
+    for n_rays, S in ((5, 64), (257, 192), (33, 17)):
+        sr = torch.rand(n_rays, S, 4, generator=gen).cuda(); sr[..., 0] *= 8.0
+        z = (2.0 + 4.0 * torch.sort(torch.rand(n_rays, S, generator=gen), dim=1).values).cuda()
+        tgt = torch.rand(n_rays, 3, generator=gen).cuda()
+        rgb, _, _ = pkg.engine.composite_forward(sr, z, extras=False)
+        loss_ref = torch.zeros(1, device="cuda"); g = torch.empty(n_rays, 3, device="cuda")
+        L, P, SP = pkg._lib.call, pkg._lib.ptr, pkg._lib.stream_ptr
+        L("nerf_mse_loss", P(rgb), P(tgt), n_rays, 1.0, P(loss_ref), P(g), SP())
+        d_ref = pkg.engine.composite_backward(sr, z, g)
+        ws = torch.zeros(int(pkg._lib.load().nerf_composite_train_workspace_bytes(n_rays)) // 4 + 1, device="cuda")
+        for _ in range(2):                                      # twice: the kernel leaves its ticket counter ready for the next call
+            loss = torch.full((1,), -1.0, device="cuda"); d = torch.empty_like(sr)
+            L("nerf_composite_train", P(sr), P(z), P(tgt), n_rays, S, 1.0, P(loss), P(d), P(ws), SP())
+            assert abs(float(loss) - float(loss_ref)) <= 1e-6 * max(1.0, float(loss_ref))
+            np.testing.assert_allclose(d.cpu().numpy(), d_ref.cpu().numpy(), rtol=1e-5, atol=1e-9)
+
+
 def test_mlp_forward_hidden_activations(pkg, orc, model_pe, sd_pe256, golden):
     """Every layer's activation (read back from the training stash) against the fp32 oracle."""
     g = golden("render_pe256")
