@@ -131,7 +131,7 @@ __device__ __forceinline__ void write_encoding(uint32_t enc_smem, int row, const
     const uint4 p = make_uint4(tc::pack_bf16x2(e[8 * kc + 0], e[8 * kc + 1]), tc::pack_bf16x2(e[8 * kc + 2], e[8 * kc + 3]),
                                tc::pack_bf16x2(e[8 * kc + 4], e[8 * kc + 5]), tc::pack_bf16x2(e[8 * kc + 6], e[8 * kc + 7]));
     tc::st_shared_v4(enc_smem + kc * kKcoreBytes + row * 16, p.x, p.y, p.z, p.w);
-    if (gdst != nullptr) reinterpret_cast<uint4*>(gdst + kc * kKcoreBytes)[row] = p;   // training stash copy
+    if (gdst != nullptr) __stcs(reinterpret_cast<uint4*>(gdst + kc * kKcoreBytes) + row, p);   // training stash copy (streaming store)
   }
 }
 
@@ -194,6 +194,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
     // together, and two warps overlap their trips.  The copy is issued before the expect_tx arrival (the phase cannot
     // complete while that arrival is pending, so the order is free) to get it on its way ~130 cycles earlier.
     const int which = (warp - 8) >> 1;
+    const uint64_t keep_in_l2 = tc::l2_policy_evict_last();    // the 2.6 MB of weight images are re-read by every CTA, all the time
     uint32_t it0 = 0, chunk = 0;                         // slabs issued before the current (layer, pass); trip counter
     for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
       for (int si = 0; si < P.n_steps; ++si) {
@@ -209,7 +210,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
               const uint32_t it = it0 + (uint32_t)k;
               const uint32_t rs = it % kRingSlots, ph = (it / kRingSlots) & 1u;
               tc::mbar_wait(bar_empty + 8 * (rs | (uint32_t)(kCommitGroup - 1)), ph ^ 1u);   // slots are released in groups
-              tc::bulk_g2s(s_ring + rs * kRingSlotBytes, src + (size_t)k * (2u * bytes), bytes, bar_full + 8 * rs);
+              tc::bulk_g2s_hint(s_ring + rs * kRingSlotBytes, src + (size_t)k * (2u * bytes), bytes, bar_full + 8 * rs, keep_in_l2);
               tc::mbar_arrive_expect_tx(bar_full + 8 * rs, bytes);
             }
             __syncwarp();
@@ -456,7 +457,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           const uint4 pk = make_uint4(tc::pack_bf16x2(g[0], g[1]), tc::pack_bf16x2(g[2], g[3]),
                                       tc::pack_bf16x2(g[4], g[5]), tc::pack_bf16x2(g[6], g[7]));
           tc::st_shared_v4(s_act + kc * kKcoreBytes + row * 16, pk.x, pk.y, pk.z, pk.w);
-          if (store_out) reinterpret_cast<uint4*>(dstash_tile + a.ds_y10 + kc * kKcoreBytes)[row] = pk;
+          if (store_out) __stcs(reinterpret_cast<uint4*>(dstash_tile + a.ds_y10 + kc * kKcoreBytes) + row, pk);
         }
       }
       tc::fence_proxy_async_smem();
@@ -521,7 +522,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
                 p[t] = tc::pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & (((w >> (i & 15)) & 0x00010001u) * 0xFFFFu);
               }
               tc::st_shared_v4(s_act + (u * 8 + q) * kKcoreBytes + row * 16, p[0], p[1], p[2], p[3]);
-              if (g_out != nullptr) g_out[(u * 8 + q) * 128] = make_uint4(p[0], p[1], p[2], p[3]);
+              if (g_out != nullptr) __stcs(g_out + (u * 8 + q) * 128, make_uint4(p[0], p[1], p[2], p[3]));   // streaming: keep the weights in L2
             }
           }
         };
@@ -616,7 +617,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
                 uint4 pk;
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "r"(s_act + (ch * 4 + q) * kKcoreBytes + row * 16));
-                gdst[(ch * 4 + q) * 128] = pk;
+                __stcs(gdst + (ch * 4 + q) * 128, pk);               // streaming (evict-first) store: the hot weight images stay in L2
                 mw[ch] |= ((pk.x + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 0));
                 mw[ch] |= ((pk.y + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 1));
                 mw[ch] |= ((pk.z + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 2));
@@ -625,8 +626,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             }
           }
           uint4* mp = reinterpret_cast<uint4*>(stash_tile + st.mask_off) + row * 2;
-          mp[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-          mp[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+          __stcs(mp, make_uint4(mw[0], mw[1], mw[2], mw[3]));
+          __stcs(mp + 1, make_uint4(mw[4], mw[5], mw[6], mw[7]));
         }
       }
     }
