@@ -84,6 +84,20 @@ int nerf_raygen_batch(const double* poses, int n_images, double fx, double fy, d
 int nerf_draw_pixels(uint64_t seed, uint64_t offset, int n_images, int width, int height,
                      int64_t n_rays, int32_t* img_idx, int32_t* px, int32_t* py, void* stream);
 
+/* One train step's inputs in ONE launch (train.py:104-127 generateBatch + train.py:205-217 depths): for ray i draws
+ * (image, x, y) exactly like nerf_draw_pixels(seed, ray_offset), generates the ray and gathers its target colour like
+ * nerf_raygen_batch, and writes z[n_rays, n_sample] exactly like nerf_sample_z(perturb, t_rand = NULL, z_seed, z_offset). */
+int nerf_train_batch(const double* poses, int n_images, double fx, double fy, double cx, double cy, int width, int height,
+                     const float* images, uint64_t seed, uint64_t ray_offset, int64_t n_rays, float* rays_o, float* rays_d,
+                     float* target, int n_sample, float near, float far, int perturb, uint64_t z_seed, uint64_t z_offset,
+                     float* z, void* stream);
+
+/* The same launch for a batch that already exists: batch9 is a generateBatch() result [n_rays, 9] = o | d | rgb fp32
+ * (train.py:127, 448 -- e.g. just uploaded from host memory).  Splits it into rays_o / rays_d / target [n_rays, 3] and writes
+ * z exactly like nerf_sample_z(perturb, t_rand = NULL, z_seed, z_offset). */
+int nerf_unpack_batch(const float* batch9, int64_t n_rays, float* rays_o, float* rays_d, float* target, int n_sample, float near,
+                      float far, int perturb, uint64_t z_seed, uint64_t z_offset, float* z, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K2  stratified depths -- train.py:205-217.  z is [n_rays, n_sample] fp32.
  *   perturb == 0            : t = linspace(0,1,S)
@@ -175,6 +189,42 @@ int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
 int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, int n_ranks, const float* multicast_grads,
                           float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
                           int64_t step, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * One optimisation step (train.py:447-465: generateBatch -> render -> MSE -> backward -> Adam [StepLR] -> weight re-pack)
+ * enqueued by ONE call, and replayable as a CUDA graph: nothing that changes from step to step is a launch argument.
+ * The iteration counter lives in device memory (step_state[0], one unsigned 64-bit word, zero before the first step;
+ * the last launch of the step advances it); the RNG counters (ray draw: (iteration * world + rank) * n_rays; depth jitter:
+ * (iteration * world + rank) * ceil(n_rays * n_sample / 4)), the StepLR step size lr0 * lr_decay^(iteration / lr_decay_steps)
+ * and Adam's bias corrections are derived from it on the device -- the same values the host forms above compute.
+ *   batch9 == NULL : the batch is drawn like nerf_train_batch(seed, ...) from poses / images
+ *   batch9 != NULL : [n_rays, 9] device array, a generateBatch() result (the caller refreshes it between steps)
+ * The launches are exactly those of nerf_train_batch | nerf_unpack_batch, nerf_mlp_forward_rays (with stash),
+ * nerf_composite_train (grad_scale 1), nerf_mlp_dgrad, nerf_mlp_wgrad (accumulate 0), nerf_adam_step(grad_scale),
+ * nerf_mlp_pack_weights; every buffer is the caller's and must be sized as for those calls.  Single-rank optimiser: a
+ * data-parallel caller uses world / rank for the RNG streams only and exchanges gradients itself (nerf_adam_step_reduce).
+ * struct_bytes = sizeof(NerfTrainStep) (checked).
+ * ------------------------------------------------------------------------------------- */
+typedef struct NerfTrainStep {
+  int64_t struct_bytes;
+  int32_t layout, n_sample, perturb, world, rank, n_images, width, height;
+  int64_t n_rays;
+  double fx, fy, cx, cy;
+  float near, far;
+  uint64_t seed, z_seed;
+  double lr0, lr_decay;
+  int64_t lr_decay_steps;
+  float beta1, beta2, eps, grad_scale;
+  const double* poses;
+  const float* images;
+  const float* batch9;
+  float *rays_o, *rays_d, *target, *z, *sigma_rgb, *d_sigma_rgb, *loss;
+  void* composite_ws;
+  void *stash, *dstash, *packed;
+  float *params, *grads, *exp_avg, *exp_avg_sq;
+  unsigned long long* step_state;
+} NerfTrainStep;
+int nerf_train_step(const NerfTrainStep* cfg, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Self tests (device): exercise the tcgen05 descriptor encodings used by K4 on a small GEMM.

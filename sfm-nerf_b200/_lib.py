@@ -56,6 +56,17 @@ _U = C.c_uint64
 _F = C.c_float
 _D = C.c_double
 
+
+
+class NerfTrainStep(C.Structure):
+    """Mirror of `struct NerfTrainStep` (include/nerf_b200.h); struct_bytes guards against drift."""
+    _fields_ = [("struct_bytes", _L)] + [(n, C.c_int32) for n in ("layout", "n_sample", "perturb", "world", "rank", "n_images", "width", "height")] + \
+        [("n_rays", _L), ("fx", _D), ("fy", _D), ("cx", _D), ("cy", _D), ("near", _F), ("far", _F), ("seed", _U), ("z_seed", _U),
+         ("lr0", _D), ("lr_decay", _D), ("lr_decay_steps", _L), ("beta1", _F), ("beta2", _F), ("eps", _F), ("grad_scale", _F)] + \
+        [(n, _P) for n in ("poses", "images", "batch9", "rays_o", "rays_d", "target", "z", "sigma_rgb", "d_sigma_rgb", "loss",
+                           "composite_ws", "stash", "dstash", "packed", "params", "grads", "exp_avg", "exp_avg_sq", "step_state")]
+
+
 # name -> (restype, argtypes); must list every symbol include/nerf_b200.h declares
 PROTOTYPES = {
     "nerf_abi_version": (_I, []),
@@ -66,6 +77,8 @@ PROTOTYPES = {
     "nerf_raygen_image": (_I, [_P, _I, _D, _D, _D, _D, _I, _I, _L, _L, _P, _P, _P]),
     "nerf_raygen_batch": (_I, [_P, _I, _D, _D, _D, _D, _I, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P]),
     "nerf_draw_pixels": (_I, [_U, _U, _I, _I, _I, _L, _P, _P, _P, _P]),
+    "nerf_train_batch": (_I, [_P, _I, _D, _D, _D, _D, _I, _I, _P, _U, _U, _L, _P, _P, _P, _I, _F, _F, _I, _U, _U, _P, _P]),
+    "nerf_unpack_batch": (_I, [_P, _L, _P, _P, _P, _I, _F, _F, _I, _U, _U, _P, _P]),
     "nerf_sample_z": (_I, [_L, _I, _F, _F, _I, _P, _U, _U, _P, _P]),
     "nerf_encode": (_I, [_P, _L, _I, _P, _P]),
     "nerf_mlp_packed_bytes": (_L, [_I]),
@@ -85,6 +98,7 @@ PROTOTYPES = {
     "nerf_composite_train": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P, _P]),
     "nerf_mse_loss": (_I, [_P, _P, _L, _F, _P, _P, _P]),
     "nerf_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
+    "nerf_train_step": (_I, [C.POINTER(NerfTrainStep), _P]),
     "nerf_selftest_umma": (_I, [_I, _P]),
     "nerf_debug_trace": (_I, [_P]),
 }

@@ -193,6 +193,40 @@ int nerf_draw_pixels(uint64_t seed, uint64_t offset, int n_images, int width, in
   return NERF_OK;
 }
 
+int nerf_train_batch(const double* poses, int n_images, double fx, double fy, double cx, double cy, int width, int height,
+                     const float* images, uint64_t seed, uint64_t ray_offset, int64_t n_rays, float* rays_o, float* rays_d,
+                     float* target, int n_sample, float near, float far, int perturb, uint64_t z_seed, uint64_t z_offset,
+                     float* z, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!poses || !images || !rays_o || !rays_d || !target || !z || n_images <= 0 || width <= 0 || height <= 0 || n_rays < 0 ||
+      n_sample <= 0 || fx == 0.0 || fy == 0.0)
+    return NERF_ERR_ARG;
+  if (n_rays == 0) return NERF_OK;
+  const unsigned ray_blocks = blocks_for(n_rays, 256), z_blocks = blocks_for(n_rays * n_sample, 256);
+  train_batch_kernel<<<ray_blocks + z_blocks, 256, 0, (cudaStream_t)stream>>>(nullptr, 1, 0, nullptr, poses, fx, fy, cx, cy, width, height, n_images, images, seed,
+                                                                             ray_offset, n_rays, rays_o, rays_d, target, n_sample, near,
+                                                                             far, perturb, z_seed, z_offset, z, ray_blocks);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int nerf_unpack_batch(const float* batch9, int64_t n_rays, float* rays_o, float* rays_d, float* target, int n_sample, float near,
+                      float far, int perturb, uint64_t z_seed, uint64_t z_offset, float* z, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!batch9 || !rays_o || !rays_d || !target || !z || n_rays < 0 || n_sample <= 0) return NERF_ERR_ARG;
+  if (n_rays == 0) return NERF_OK;
+  const unsigned ray_blocks = blocks_for(n_rays, 256), z_blocks = blocks_for(n_rays * n_sample, 256);
+  train_batch_kernel<<<ray_blocks + z_blocks, 256, 0, (cudaStream_t)stream>>>(nullptr, 1, 0, batch9, nullptr, 1.0, 1.0, 0.0, 0.0, 1, 1, 1, nullptr, 0, 0, n_rays,
+                                                                             rays_o, rays_d, target, n_sample, near, far, perturb, z_seed,
+                                                                             z_offset, z, ray_blocks);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
 // ------------------------------------------------------------------------------------ K2
 int nerf_sample_z(int64_t n_rays, int n_sample, float near, float far, int perturb, const float* t_rand,
                   uint64_t seed, uint64_t offset, float* z, void* stream) {
@@ -227,7 +261,7 @@ int64_t nerf_mlp_packed_bytes(int layout) {
   return m ? m->packed_bytes : NERF_ERR_LAYOUT;
 }
 
-int nerf_mlp_pack_weights(const float* params, int layout, void* packed, void* stream) {
+static int launch_pack(const float* params, int layout, void* packed, unsigned long long* bump, void* stream) {
   DeviceInfo* dev;
   int rc = device_info(&dev);
   if (rc != NERF_OK) return rc;
@@ -241,9 +275,14 @@ int nerf_mlp_pack_weights(const float* params, int layout, void* packed, void* s
   p.sm_wd = m->sm_wd; p.sm_bd = m->sm_bd; p.sm_w2 = m->sm_w2; p.sm_b2 = m->sm_b2;
   // one launch: grid.y = forward steps, dgrad steps, then one row of blocks for the fp32 head table
   pack_all_kernel<<<dim3(64, m->fwd.n_steps + m->bwd.n_steps + 1), 256, 0, s>>>(
-      params, m->fwd, m->bwd, p, static_cast<uint8_t*>(packed), reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + m->small_off));
+      params, m->fwd, m->bwd, p, static_cast<uint8_t*>(packed), reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + m->small_off),
+      bump);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
+}
+
+int nerf_mlp_pack_weights(const float* params, int layout, void* packed, void* stream) {
+  return launch_pack(params, layout, packed, nullptr, stream);
 }
 
 int64_t nerf_mlp_stash_bytes(int layout, int64_t n_rows) {
@@ -448,9 +487,44 @@ int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                                    eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+                                                                    eps, (float)bc1, (float)sqrt(bc2), grad_scale, AdamSchedule{});
   NERF_LAUNCH_CHECK();
   return NERF_OK;
+}
+
+// ------------------------------------------------------------------------------------ whole train step
+int nerf_train_step(const NerfTrainStep* c, void* stream) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (!c || c->struct_bytes != (int64_t)sizeof(NerfTrainStep)) return NERF_ERR_ARG;
+  const ModelLayout* m = get_layout(c->layout);
+  if (!m) return NERF_ERR_LAYOUT;
+  if (c->n_rays <= 0 || c->n_sample <= 0 || c->world < 1 || c->rank < 0 || c->rank >= c->world || c->lr_decay_steps < 1 ||
+      !c->step_state || !c->rays_o || !c->rays_d || !c->target || !c->z || !c->sigma_rgb || !c->d_sigma_rgb || !c->loss ||
+      !c->composite_ws || !c->stash || !c->dstash || !c->packed || !c->params || !c->grads || !c->exp_avg || !c->exp_avg_sq)
+    return NERF_ERR_ARG;
+  if (!c->batch9 && (!c->poses || !c->images || c->n_images <= 0 || c->width <= 0 || c->height <= 0 || c->fx == 0.0 || c->fy == 0.0))
+    return NERF_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t rows = c->n_rays * c->n_sample;
+  const unsigned ray_blocks = blocks_for(c->n_rays, 256), z_blocks = blocks_for(rows, 256);
+  train_batch_kernel<<<ray_blocks + z_blocks, 256, 0, s>>>(c->step_state, (unsigned)c->world, (unsigned)c->rank, c->batch9, c->poses, c->fx,
+                                                          c->fy, c->cx, c->cy, c->width, c->height, c->n_images, c->images, c->seed, 0,
+                                                          c->n_rays, c->rays_o, c->rays_d, c->target, c->n_sample, c->near, c->far,
+                                                          c->perturb, c->z_seed, 0, c->z, ray_blocks);
+  NERF_LAUNCH_CHECK();
+  if ((rc = nerf_mlp_forward_rays(c->packed, c->layout, c->rays_o, c->rays_d, c->z, c->n_rays, c->n_sample, c->sigma_rgb, c->stash, stream)))
+    return rc;
+  if ((rc = nerf_composite_train(c->sigma_rgb, c->z, c->target, c->n_rays, c->n_sample, 1.0f, c->loss, c->d_sigma_rgb, c->composite_ws, stream)))
+    return rc;
+  if ((rc = nerf_mlp_dgrad(c->packed, c->layout, c->stash, c->sigma_rgb, c->d_sigma_rgb, rows, c->dstash, stream))) return rc;
+  if ((rc = nerf_mlp_wgrad(c->layout, c->stash, c->dstash, rows, c->grads, 0, stream))) return rc;
+  adam_kernel<<<blocks_for(m->n_params, 256), 256, 0, s>>>(c->params, c->grads, c->exp_avg, c->exp_avg_sq, m->n_params, 0.f, c->beta1,
+                                                           c->beta2, c->eps, 1.f, 1.f, c->grad_scale,
+                                                           AdamSchedule{c->step_state, c->lr0, c->lr_decay, (long long)c->lr_decay_steps});
+  NERF_LAUNCH_CHECK();
+  return launch_pack(c->params, c->layout, c->packed, c->step_state, stream);
 }
 
 int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, int n_ranks, const float* multicast_grads,

@@ -685,10 +685,13 @@ __device__ __forceinline__ void pack_small(const float* __restrict__ params, con
 }
 
 // Everything the MLP kernels read, from the flat fp32 parameters, in one launch: blockIdx.y selects a forward step, a dgrad
-// step, or (last row) the fp32 head table.
+// step, or (last row) the fp32 head table.  `bump` (optional) is the device-side iteration counter of nerf_train_step: this
+// is the last launch of a step and does not read it, so one thread advances it here for the next step.
 __global__ void pack_all_kernel(const float* __restrict__ params, const __grid_constant__ Program fwd, const __grid_constant__ Program bwd,
-                                const PackSmallArgs small_args, uint8_t* __restrict__ packed, float* __restrict__ small) {
+                                const PackSmallArgs small_args, uint8_t* __restrict__ packed, float* __restrict__ small,
+                                unsigned long long* __restrict__ bump) {
   const int y = blockIdx.y;
+  if (bump != nullptr && blockIdx.x == 0 && y == 0 && threadIdx.x == 0) *bump += 1ull;
   if (y < fwd.n_steps) pack_image_step(params, fwd.s[y], packed);
   else if (y < fwd.n_steps + bwd.n_steps) pack_image_step(params, bwd.s[y - fwd.n_steps], packed);
   else if (blockIdx.x < 2) pack_small(params, small_args, small);

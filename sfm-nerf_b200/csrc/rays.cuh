@@ -106,6 +106,59 @@ __global__ void sample_z_kernel(int64_t total, int S, float near, float far, int
   z[i] = __fadd_rn(near, __fmul_rn(__fsub_rn(far, near), t));   // train.py:217
 }
 
+// generateBatch (train.py:104-127) + the depths of render (train.py:205-217) for one train step in ONE launch: the first
+// `ray_blocks` blocks draw (image, x, y) per ray (draw_pixels_kernel), generate the ray and gather its target colour
+// (raygen_batch_kernel); the remaining blocks write z (sample_z_kernel).  Bit-identical to the three separate kernels.
+// With `batch9` != nullptr the rays are not drawn: batch9 is a generateBatch() result [n_rays, 9] = o | d | rgb
+// (train.py:127, e.g. just uploaded from the host) and the ray blocks only split it into the three [n_rays, 3] arrays.
+// With `iter_ptr` != nullptr the RNG counters come from the device-side iteration counter (graph-replayable step):
+// batch index c = iteration * world + rank, ray_offset = c * n_rays, z_offset = c * ceil(n_rays * S / 4).
+__global__ void train_batch_kernel(const unsigned long long* __restrict__ iter_ptr, unsigned world, unsigned rank,
+                                   const float* __restrict__ batch9, const double* __restrict__ poses, double fx, double fy, double cx, double cy, int width, int height,
+                                   int n_images, const float* __restrict__ images, uint64_t seed, uint64_t ray_offset, int64_t n_rays,
+                                   float* __restrict__ rays_o, float* __restrict__ rays_d, float* __restrict__ target, int S, float near,
+                                   float far, int perturb, uint64_t z_seed, uint64_t z_offset, float* __restrict__ z,
+                                   unsigned ray_blocks) {
+  if (iter_ptr != nullptr) {
+    const uint64_t c = (uint64_t)(*iter_ptr) * world + rank;
+    ray_offset = c * (uint64_t)n_rays;
+    z_offset = c * (uint64_t)((n_rays * S + 3) / 4);
+  }
+  if (blockIdx.x < ray_blocks) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    if (batch9 != nullptr) {
+      const float* b = batch9 + 9 * i;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { rays_o[3 * i + c] = __ldg(b + c); rays_d[3 * i + c] = __ldg(b + 3 + c); target[3 * i + c] = __ldg(b + 6 + c); }
+      return;
+    }
+    uint32_t r[4];
+    philox4x32_10(seed, ray_offset + (uint64_t)i, r);
+    const int k = (int)(((uint64_t)r[0] * (uint32_t)n_images) >> 32);
+    const int x = (int)(((uint64_t)r[1] * (uint32_t)width) >> 32);
+    const int y = (int)(((uint64_t)r[2] * (uint32_t)height) >> 32);
+    float o[3], d[3];
+    pixel_to_ray(poses + 16 * (int64_t)k, fx, fy, cx, cy, x, y, o, d);
+    const float* p = images + (((int64_t)k * height + y) * width + x) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { rays_o[3 * i + c] = o[c]; rays_d[3 * i + c] = d[c]; target[3 * i + c] = __ldg(p + c); }
+  } else {
+    const int64_t i = (int64_t)(blockIdx.x - ray_blocks) * blockDim.x + threadIdx.x;
+    if (i >= n_rays * S) return;
+    const int s = (int)(i % S);
+    float t;
+    if (!perturb) {
+      t = linspace01(s, S);
+    } else {
+      uint32_t r[4];
+      philox4x32_10(z_seed, z_offset + (uint64_t)(i >> 2), r);
+      t = stratified_t(s, S, u32_to_unit_float(r[i & 3]));
+    }
+    z[i] = __fadd_rn(near, __fmul_rn(__fsub_rn(far, near), t));
+  }
+}
+
 // NeRFModel.py:142-156.  One thread per output element (coalesced stores).
 __global__ void encode_kernel(const float* __restrict__ x, int64_t n, int L, float* __restrict__ out) {
   const int C = 3 * (2 * L + 1);

@@ -308,7 +308,7 @@ class Trainer:
 
     def __init__(self, model, images_dev, poses_dev, camera_info, n_rays, n_sample, near=2.0, far=6.0, lr=5e-4,
                  betas=(0.9, 0.999), eps=1e-8, lr_decay_steps=50000, lr_decay=0.1, perturb=True, seed=0, rank=0, world=1,
-                 process_group=None):
+                 process_group=None, graph=True):
         self.model = model
         self.st = model.kernel_state()
         self.st.frozen = True                      # this class repacks right after each Adam step
@@ -331,6 +331,16 @@ class Trainer:
         self.comp_ws, self.comp_ws_rays = None, 0     # workspace of nerf_composite_train, sized for the largest batch seen
         self.iteration = 0
         self.launches_per_step = 0
+        # whole-step entry point (nerf_train_step): fixed per-step buffers + the device-side iteration counter, so that the
+        # step has no step-dependent launch argument and replays as a CUDA graph (single rank; world > 1 keeps the
+        # per-kernel sequence below because its gradient barrier is a torch op)
+        self.use_graph = bool(graph)
+        self.step_state = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._dev_iteration = 0
+        self._fixed = None                          # (odt, z, sigma_rgb, dsr, batch9) once the first fast step allocates them
+        self._cfg = {}                              # from_batch9 -> NerfTrainStep
+        self._graphs = {}                           # from_batch9 -> torch.cuda.CUDAGraph
+        self._direct_steps = {False: 0, True: 0}
 
     def lr(self):
         return self.lr0 * self.lr_decay ** (self.iteration // self.lr_decay_steps)
@@ -338,24 +348,101 @@ class Trainer:
     def close(self):
         self.st.frozen = False
 
+    def _train_step_cfg(self, from_batch9):
+        import ctypes
+        st, dev, n, S = self.st, self.st.device, self.n_rays, self.n_sample
+        if self._fixed is None:
+            ws = torch.zeros(int(_lib.load().nerf_composite_train_workspace_bytes(n)) // 4 + 1, dtype=torch.float32, device=dev)
+            self._fixed = (torch.empty((3, n, 3), dtype=torch.float32, device=dev), torch.empty((n, S), dtype=torch.float32, device=dev),
+                           torch.empty((n, S, 4), dtype=torch.float32, device=dev), torch.empty((n, S, 4), dtype=torch.float32, device=dev),
+                           torch.empty((n, 9), dtype=torch.float32, device=dev), ws)
+        odt, z, sigma_rgb, dsr, batch9, ws = self._fixed
+        c = _lib.NerfTrainStep()
+        c.struct_bytes = ctypes.sizeof(_lib.NerfTrainStep)
+        c.layout, c.n_sample, c.perturb, c.world, c.rank = st.layout, S, 1 if self.perturb else 0, self.world, self.rank
+        c.n_rays, c.near, c.far, c.seed, c.z_seed = n, self.near, self.far, self.seed, self.seed ^ 0x5bd1e995
+        c.lr0, c.lr_decay, c.lr_decay_steps = self.lr0, self.lr_decay, self.lr_decay_steps
+        c.beta1, c.beta2, c.eps, c.grad_scale = self.betas[0], self.betas[1], self.eps, parallel.mean_scale(self.world)
+        if from_batch9:
+            c.batch9 = batch9.data_ptr()
+        else:
+            c.fx, c.fy, c.cx, c.cy = _intrinsics(self.cam)
+            c.n_images, c.width, c.height = int(self.images.shape[0]), int(self.cam["width"]), int(self.cam["height"])
+            c.poses, c.images = self.poses.data_ptr(), self.images.data_ptr()
+        c.rays_o, c.rays_d, c.target, c.z = odt[0].data_ptr(), odt[1].data_ptr(), odt[2].data_ptr(), z.data_ptr()
+        c.sigma_rgb, c.d_sigma_rgb, c.loss, c.composite_ws = sigma_rgb.data_ptr(), dsr.data_ptr(), self.loss.data_ptr(), ws.data_ptr()
+        c.stash, c.dstash, c.packed = self.stash.data_ptr(), self.dstash.data_ptr(), st.packed.data_ptr()
+        c.params, c.grads, c.exp_avg, c.exp_avg_sq = st.flat.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        c.step_state = self.step_state.data_ptr()
+        return c
+
+    def _step_whole(self, batch9):
+        """The whole step through nerf_train_step: one C call, and from the third step on one CUDA-graph replay."""
+        import ctypes
+        key = batch9 is not None
+        if key not in self._cfg:
+            self._cfg[key] = self._train_step_cfg(key)
+        if self._dev_iteration != self.iteration:            # the per-kernel path ran in between, or a checkpoint was resumed
+            self.step_state.fill_(self.iteration)
+            self._dev_iteration = self.iteration
+        if key:
+            self._fixed[4].copy_(batch9, non_blocking=True)   # H2D (pinned host batch) or D2D, straight into the step's input
+        g = self._graphs.get(key)
+        if g is not None:
+            g.replay()
+        else:
+            call("nerf_train_step", ctypes.byref(self._cfg[key]), stream_ptr())
+            self._direct_steps[key] += 1
+            if self.use_graph and self._direct_steps[key] == 2:      # warmed up: capture the same call for replay
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                saved = self.step_state.clone()
+                with torch.cuda.graph(g):
+                    call("nerf_train_step", ctypes.byref(self._cfg[key]), stream_ptr())
+                self.step_state.copy_(saved)                         # capture does not execute, but be explicit
+                self._graphs[key] = g
+        self.iteration += 1
+        self._dev_iteration += 1
+        self.launches_per_step = 8                  # batch, mlp fwd, composite_train, dgrad, wgrad, heads, adam, pack (+1 memset)
+        return self.loss
+
     def step(self, rays=None, timers=None):
-        """One optimisation step.  ``rays`` = optional (rays_o, rays_d, target) device tensors (e.g. a
-        batch uploaded from the host like train.py:448); default draws the batch on the GPU.
+        """One optimisation step.  ``rays`` = optional batch: a generateBatch() array [N,9] already on the device (e.g. uploaded
+        from the host like train.py:448) or (rays_o, rays_d, target) device tensors; default draws the batch on the GPU.
         ``timers`` = optional dict: CUDA-event pairs per kernel are appended to timers[name]."""
         st, S = self.st, self.n_sample
+        if self.exchange is None and timers is None:
+            if rays is None and self.images is not None:
+                return self._step_whole(None)
+            if torch.is_tensor(rays) and rays.dim() == 2 and tuple(rays.shape) == (self.n_rays, 9) and rays.dtype == torch.float32:
+                return self._step_whole(rays)
         W, H = int(self.cam["width"]), int(self.cam["height"])
         dev = st.device
         launches = 0
         ctr = parallel.batch_counter(self.iteration, self.rank, self.world)
-        if rays is None:
-            k, x, y = draw_pixels(self.seed, ctr * self.n_rays, self.images.shape[0], W, H, self.n_rays, dev)
-            o, d, tgt = raygen_batch(self.poses, self.cam, k, x, y, self.images)
-            launches += 2
+        z_seed = self.seed ^ 0x5bd1e995
+        if rays is None or (torch.is_tensor(rays) and rays.dim() == 2 and rays.shape[1] == 9):
+            # one launch: draw + ray generation + target gather (or the split of a generateBatch() [N,9] array) + depths
+            n_rays = self.n_rays if rays is None else int(rays.shape[0])
+            odt = torch.empty((3, n_rays, 3), dtype=torch.float32, device=dev)
+            o, d, tgt = odt[0], odt[1], odt[2]
+            z = torch.empty((n_rays, S), dtype=torch.float32, device=dev)
+            z_off = ctr * ((n_rays * S + 3) // 4)
+            if rays is None:
+                fx, fy, cx, cy = _intrinsics(self.cam)
+                call("nerf_train_batch", ptr(self.poses), int(self.poses.shape[0]), fx, fy, cx, cy, W, H, ptr(self.images), self.seed,
+                     ctr * self.n_rays, n_rays, ptr(o), ptr(d), ptr(tgt), S, self.near, self.far, 1 if self.perturb else 0, z_seed, z_off,
+                     ptr(z), stream_ptr())
+            else:
+                _need_cuda(rays)
+                call("nerf_unpack_batch", ptr(_f32c(rays)), n_rays, ptr(o), ptr(d), ptr(tgt), S, self.near, self.far,
+                     1 if self.perturb else 0, z_seed, z_off, ptr(z), stream_ptr())
+            launches += 1
         else:
             o, d, tgt = rays
-        n_rays = o.shape[0]
-        z = sample_z(n_rays, S, self.near, self.far, dev, perturb=self.perturb, seed=self.seed ^ 0x5bd1e995,
-                     offset=ctr * ((n_rays * S + 3) // 4))
+            n_rays = o.shape[0]
+            z = sample_z(n_rays, S, self.near, self.far, dev, perturb=self.perturb, seed=z_seed, offset=ctr * ((n_rays * S + 3) // 4))
+            launches += 1
         with _timed(timers, "mlp_fwd"):
             sigma_rgb = mlp_forward_rays(st, o, d, z, self.stash)
         # compositing forward + MSE + compositing backward in one launch; local mean over this rank's rays (the sum over
@@ -376,7 +463,7 @@ class Trainer:
             self.grads = ex.local(self.iteration)
         with _timed(timers, "mlp_wgrad"):
             call("nerf_mlp_wgrad", st.layout, ptr(self.stash), ptr(self.dstash), rows, ptr(self.grads), 0, stream_ptr())
-        launches += 6                               # sample, mlp fwd, composite_train, dgrad, wgrad, heads (+1 memset)
+        launches += 5                               # mlp fwd, composite_train, dgrad, wgrad, heads (+1 memset)
         lr = self.lr()
         if ex is not None and ex.mode != "nccl":
             # the gradient exchange is fused into the optimiser: barrier, then Adam reads the sum over ranks through NVLink

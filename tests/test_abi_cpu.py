@@ -30,6 +30,20 @@ def test_header_symbols_are_exported(libmod):
     assert declared == set(libmod.PROTOTYPES), declared ^ set(libmod.PROTOTYPES)
 
 
+def test_train_step_struct_matches_header(libmod, tmp_path):
+    """The ctypes mirror of NerfTrainStep has the size and field offsets gcc gives the header's struct."""
+    import subprocess
+    fields = [f[0] for f in libmod.NerfTrainStep._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nerf_b200.h"\nint main(void){printf("%zu\\n", sizeof(NerfTrainStep));\n' +
+                   "".join(f'printf("%zu\\n", offsetof(NerfTrainStep, {f}));\n' for f in fields) + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(libmod.NerfTrainStep)
+    assert out[1:] == [getattr(libmod.NerfTrainStep, f).offset for f in fields]
+
+
 def test_abi_queries_without_gpu(libmod):
     lib = libmod.load()
     assert lib.nerf_abi_version() == 1

@@ -515,6 +515,111 @@ def test_trainer_device_batches_match_host_rays(pkg, orc):
     np.testing.assert_allclose(losses[0], losses[1], rtol=1e-4)
 
 
+def test_fused_train_batch_launch_is_bit_identical(pkg, orc):
+    """nerf_train_batch (one launch) == nerf_draw_pixels + nerf_raygen_batch + nerf_sample_z bit for bit, with and
+    without jitter, on a ragged ray count; nerf_unpack_batch splits a generateBatch() [N,9] array exactly and a train
+    step fed with that array equals the step fed with the three tensors."""
+    E = pkg.engine
+    cam = orc.make_camera_info(40, 30)
+    poses_np = orc.sphere_poses(4, seed=3)
+    poses = E.poses_to_device(poses_np, "cuda")
+    images = torch.tensor(np.random.default_rng(1).random((4, 30, 40, 3)).astype(np.float32)).cuda()
+    fx, fy, cx, cy = E._intrinsics(cam)
+    n, S = 301, 48
+    for perturb in (0, 1):
+        k, x, y = E.draw_pixels(11, 7 * n, 4, 40, 30, n, "cuda")
+        o, d, tgt = E.raygen_batch(poses, cam, k, x, y, images)
+        z = E.sample_z(n, S, 2.0, 6.0, "cuda", perturb=bool(perturb), seed=99, offset=1234)
+        o2, d2, t2 = (torch.empty_like(o) for _ in range(3))
+        z2 = torch.empty_like(z)
+        E.call("nerf_train_batch", E.ptr(poses), 4, fx, fy, cx, cy, 40, 30, E.ptr(images), 11, 7 * n, n, E.ptr(o2), E.ptr(d2), E.ptr(t2),
+               S, 2.0, 6.0, perturb, 99, 1234, E.ptr(z2), E.stream_ptr())
+        for a, b in ((o, o2), (d, d2), (tgt, t2), (z, z2)):
+            assert torch.equal(a, b)
+        b9 = torch.cat([o, d, tgt], 1).contiguous()
+        o3, d3, t3 = (torch.empty_like(o) for _ in range(3))
+        z3 = torch.empty_like(z)
+        E.call("nerf_unpack_batch", E.ptr(b9), n, E.ptr(o3), E.ptr(d3), E.ptr(t3), S, 2.0, 6.0, perturb, 99, 1234, E.ptr(z3), E.stream_ptr())
+        for a, b in ((o, o3), (d, d3), (tgt, t3), (z, z3)):
+            assert torch.equal(a, b)
+    losses = []
+    for as_array in (False, True):
+        torch.manual_seed(0)
+        m = pkg.NeRFmodel().cuda()
+        tr = E.Trainer(m, images, poses, cam, n, 32, perturb=True, seed=5)
+        losses.append(float(tr.step(rays=b9 if as_array else (o, d, tgt)).item()))
+        tr.close()
+    assert losses[0] == losses[1]
+    with pytest.raises(pkg._lib.NerfB200Error):
+        E.call("nerf_unpack_batch", None, n, E.ptr(o3), E.ptr(d3), E.ptr(t3), S, 2.0, 6.0, 0, 0, 0, E.ptr(z3), E.stream_ptr())
+
+
+def test_whole_step_call_and_graph_replay_match_per_kernel_path(pkg, orc):
+    """nerf_train_step (one C call; replayed as a CUDA graph from the third step on, iteration counter / StepLR / bias
+    corrections on the device) follows the per-kernel sequence with host-side scalars: same batches, same losses, same
+    weights -- including across a StepLR boundary and for batches uploaded from pinned host memory."""
+    E = pkg.engine
+    cam = orc.make_camera_info(40, 30)
+    poses = E.poses_to_device(orc.sphere_poses(4, seed=3), "cuda")
+    images = torch.tensor(np.random.default_rng(1).random((4, 30, 40, 3)).astype(np.float32)).cuda()
+    n, S, steps = 256, 32, 7
+
+    def run(whole, host_batches=None):
+        torch.manual_seed(0)
+        m = pkg.NeRFmodel().cuda()
+        tr = E.Trainer(m, images, poses, cam, n, S, perturb=True, seed=5, lr_decay_steps=3, lr_decay=0.5)
+        losses = []
+        for i in range(steps):
+            rays = None if host_batches is None else host_batches[i]
+            if not whole:
+                rays = rays.cuda() if rays is not None else None
+            losses.append(float((tr.step(rays=rays) if whole else tr.step(rays=rays, timers={})).item()))
+        assert tr.iteration == steps
+        if whole:
+            assert int(tr.step_state.item()) == steps and len(tr._graphs) == 1
+        w = tr.st.flat.clone()
+        tr.close()
+        return losses, w
+
+    la, wa = run(True)
+    lb, wb = run(False)
+    assert la[0] == lb[0]
+    np.testing.assert_allclose(la, lb, rtol=2e-4)
+    # fp32 atomics reorder the gradient sums, and Adam turns a sign flip of a near-zero gradient into a full +-lr step: compare
+    # the bulk (a wrong step size / bias correction / RNG counter on the device would shift the mean by ~1e-4)
+    assert float((wa - wb).abs().mean()) < 2e-5 and float((wa - wb).abs().max()) < 7 * 5e-4
+    k, x, y = E.draw_pixels(3, 0, 4, 40, 30, n * steps, "cuda")
+    o, d, t = E.raygen_batch(poses, cam, k, x, y, images)
+    hb = [b.contiguous().cpu().pin_memory() for b in torch.cat([o, d, t], 1).split(n)]
+    lc, wc = run(True, hb)
+    ld, wd = run(False, hb)
+    assert lc[0] == ld[0]
+    np.testing.assert_allclose(lc, ld, rtol=2e-4)
+    assert float((wc - wd).abs().mean()) < 2e-5 and float((wc - wd).abs().max()) < 7 * 5e-4
+
+
+def test_whole_step_resumes_and_interleaves(pkg, orc):
+    """The device-side iteration counter follows Trainer.iteration when a checkpoint is resumed or the per-kernel path
+    runs in between (same RNG stream, same Adam step number)."""
+    E = pkg.engine
+    cam = orc.make_camera_info(40, 30)
+    poses = E.poses_to_device(orc.sphere_poses(4, seed=3), "cuda")
+    images = torch.tensor(np.random.default_rng(1).random((4, 30, 40, 3)).astype(np.float32)).cuda()
+    out = []
+    for mixed in (False, True):
+        torch.manual_seed(0)
+        m = pkg.NeRFmodel().cuda()
+        tr = E.Trainer(m, images, poses, cam, 128, 32, perturb=True, seed=9)
+        tr.iteration = 1000
+        ls = []
+        for i in range(6):
+            ls.append(float((tr.step(timers={}) if (mixed and i in (1, 4)) else tr.step()).item()))
+        assert tr.iteration == 1006 and int(tr.step_state.item()) in (1005, 1006)
+        out.append(ls)
+        tr.close()
+    np.testing.assert_allclose(out[0], out[1], rtol=2e-4)
+
+
 def test_short_training_tracks_oracle(pkg, orc):
     """40 optimisation steps on identical pre-drawn batches: the fused CUDA train step and the fp32 oracle
     (autograd + Adam) follow the same loss curve."""
