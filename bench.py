@@ -260,18 +260,18 @@ def run_ours(args):
     loss_host = 0.0
 
     def host_step(i):
-        hb = host_batches[i % 4]                                          # pinned host memory, n_rays x 9 fp32 (train.py:448)
-        # single rank: H2D straight into the step's input buffer, then the graph; else upload + per-kernel sequence
-        return trainer.step(rays=hb if world == 1 else hb.to(dev, non_blocking=True))
+        # pinned host batch n_rays x 9 fp32 (train.py:448) -> H2D inside step(); the loss comes back as a Python float every
+        # step (train.py:468).  Single rank: forward graph, async D2H of the loss, backward graph; the host waits for the loss only.
+        return trainer.step(rays=host_batches[i % 4], loss_to_host=True)
 
     for i in range(3):
-        loss_host = host_step(i).item()
+        loss_host = host_step(i)
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev2.record()
     for i in range(e2e_steps):
-        loss_host = host_step(i).item()                                   # D2H: 4 bytes, syncs every step (train.py:468)
+        loss_host = host_step(i)
     ev3.record()
     barrier()
     e2e_ms = max_over_ranks(max(ev2.elapsed_time(ev3), 1e3 * (time.perf_counter() - t_wall0)))

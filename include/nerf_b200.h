@@ -191,6 +191,19 @@ int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, in
                           int64_t step, float grad_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * One frame (or a contiguous slice of its rays) by ONE call -- the body of test_image (train.py:735-757): K1 rays of ray ids
+ * [ray_begin, ray_begin + ray_count) of pose `pose_index`, K2 depths (like nerf_sample_z with t_rand = NULL), K4 inference
+ * forward, K5 compositing -> rgb [ray_count, 3] and optionally depth / acc [ray_count].  A multi-GPU host gives each rank its
+ * parallel.shard_range slice; no collective.  workspace: nerf_render_workspace_bytes(ray_count, n_sample) bytes, 256-byte
+ * aligned, the caller's (holds the rays, depths and per-sample sigma/rgb between the launches).
+ * ------------------------------------------------------------------------------------- */
+int64_t nerf_render_workspace_bytes(int64_t n_rays, int n_sample);
+int nerf_render_image(const void* packed, int layout, const double* poses, int pose_index, double fx, double fy, double cx,
+                      double cy, int width, int height, int64_t ray_begin, int64_t ray_count, int n_sample, float near,
+                      float far, int perturb, uint64_t seed, uint64_t offset, float* rgb, float* depth, float* acc,
+                      void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * One optimisation step (train.py:447-465: generateBatch -> render -> MSE -> backward -> Adam [StepLR] -> weight re-pack)
  * enqueued by ONE call, and replayable as a CUDA graph: nothing that changes from step to step is a launch argument.
  * The iteration counter lives in device memory (step_state[0], one unsigned 64-bit word, zero before the first step;
@@ -224,7 +237,14 @@ typedef struct NerfTrainStep {
   float *params, *grads, *exp_avg, *exp_avg_sq;
   unsigned long long* step_state;
 } NerfTrainStep;
-int nerf_train_step(const NerfTrainStep* cfg, void* stream);
+/* phases: NERF_STEP_FORWARD = batch + render + loss (cfg->loss[0] is final when these launches complete),
+ * NERF_STEP_BACKWARD = dgrad + wgrad + Adam + re-pack + counter advance, NERF_STEP_ALL = both.  A host that wants the loss of
+ * every step (train.py:468) enqueues FORWARD, an async D2H copy of the loss + event, then BACKWARD, and waits on the event
+ * only: the backward launches are still running while it prepares the next step. */
+#define NERF_STEP_FORWARD 1
+#define NERF_STEP_BACKWARD 2
+#define NERF_STEP_ALL 3
+int nerf_train_step(const NerfTrainStep* cfg, int phases, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Self tests (device): exercise the tcgen05 descriptor encodings used by K4 on a small GEMM.

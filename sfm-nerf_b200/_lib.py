@@ -98,7 +98,9 @@ PROTOTYPES = {
     "nerf_composite_train": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P, _P]),
     "nerf_mse_loss": (_I, [_P, _P, _L, _F, _P, _P, _P]),
     "nerf_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
-    "nerf_train_step": (_I, [C.POINTER(NerfTrainStep), _P]),
+    "nerf_render_workspace_bytes": (_L, [_L, _I]),
+    "nerf_render_image": (_I, [_P, _I, _P, _I, _D, _D, _D, _D, _I, _I, _L, _L, _I, _F, _F, _I, _U, _U, _P, _P, _P, _P, _P]),
+    "nerf_train_step": (_I, [C.POINTER(NerfTrainStep), _I, _P]),
     "nerf_selftest_umma": (_I, [_I, _P]),
     "nerf_debug_trace": (_I, [_P]),
 }

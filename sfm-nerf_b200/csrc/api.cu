@@ -426,6 +426,34 @@ int nerf_composite_forward(const float* sigma_rgb, const float* z, int64_t n_ray
   return NERF_OK;
 }
 
+// ------------------------------------------------------------------------------------ whole frame (slice)
+static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+
+int64_t nerf_render_workspace_bytes(int64_t n_rays, int n_sample) {
+  if (n_rays < 0 || n_sample <= 0) return NERF_ERR_ARG;
+  return 2 * align256(n_rays * 12) + align256(n_rays * n_sample * 4) + align256(n_rays * n_sample * 16);
+}
+
+int nerf_render_image(const void* packed, int layout, const double* poses, int pose_index, double fx, double fy, double cx,
+                      double cy, int width, int height, int64_t ray_begin, int64_t ray_count, int n_sample, float near,
+                      float far, int perturb, uint64_t seed, uint64_t offset, float* rgb, float* depth, float* acc,
+                      void* workspace, void* stream) {
+  if (ray_count < 0 || n_sample <= 0) return NERF_ERR_ARG;
+  if (ray_count == 0) return NERF_OK;
+  if (!workspace) return NERF_ERR_ARG;
+  if (!nerf_aligned(workspace, 256)) return NERF_ERR_ALIGN;
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  float* o = reinterpret_cast<float*>(w);
+  float* d = reinterpret_cast<float*>(w + align256(ray_count * 12));
+  float* z = reinterpret_cast<float*>(w + 2 * align256(ray_count * 12));
+  float* sr = reinterpret_cast<float*>(w + 2 * align256(ray_count * 12) + align256(ray_count * n_sample * 4));
+  int rc;
+  if ((rc = nerf_raygen_image(poses, pose_index, fx, fy, cx, cy, width, height, ray_begin, ray_count, o, d, stream))) return rc;
+  if ((rc = nerf_sample_z(ray_count, n_sample, near, far, perturb, nullptr, seed, offset, z, stream))) return rc;
+  if ((rc = nerf_mlp_forward_rays(packed, layout, o, d, z, ray_count, n_sample, sr, nullptr, stream))) return rc;
+  return nerf_composite_forward(sr, z, ray_count, n_sample, rgb, depth, acc, stream);
+}
+
 int nerf_composite_backward(const float* sigma_rgb, const float* z, const float* g_rgb, int64_t n_rays, int n_sample,
                             float* d_sigma_rgb, void* stream) {
   DeviceInfo* dev;
@@ -493,11 +521,11 @@ int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
 }
 
 // ------------------------------------------------------------------------------------ whole train step
-int nerf_train_step(const NerfTrainStep* c, void* stream) {
+int nerf_train_step(const NerfTrainStep* c, int phases, void* stream) {
   DeviceInfo* dev;
   int rc = device_info(&dev);
   if (rc != NERF_OK) return rc;
-  if (!c || c->struct_bytes != (int64_t)sizeof(NerfTrainStep)) return NERF_ERR_ARG;
+  if (!c || c->struct_bytes != (int64_t)sizeof(NerfTrainStep) || phases < 1 || phases > 3) return NERF_ERR_ARG;
   const ModelLayout* m = get_layout(c->layout);
   if (!m) return NERF_ERR_LAYOUT;
   if (c->n_rays <= 0 || c->n_sample <= 0 || c->world < 1 || c->rank < 0 || c->rank >= c->world || c->lr_decay_steps < 1 ||
@@ -509,6 +537,7 @@ int nerf_train_step(const NerfTrainStep* c, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t rows = c->n_rays * c->n_sample;
   const unsigned ray_blocks = blocks_for(c->n_rays, 256), z_blocks = blocks_for(rows, 256);
+  if (phases & NERF_STEP_FORWARD) {
   train_batch_kernel<<<ray_blocks + z_blocks, 256, 0, s>>>(c->step_state, (unsigned)c->world, (unsigned)c->rank, c->batch9, c->poses, c->fx,
                                                           c->fy, c->cx, c->cy, c->width, c->height, c->n_images, c->images, c->seed, 0,
                                                           c->n_rays, c->rays_o, c->rays_d, c->target, c->n_sample, c->near, c->far,
@@ -518,6 +547,8 @@ int nerf_train_step(const NerfTrainStep* c, void* stream) {
     return rc;
   if ((rc = nerf_composite_train(c->sigma_rgb, c->z, c->target, c->n_rays, c->n_sample, 1.0f, c->loss, c->d_sigma_rgb, c->composite_ws, stream)))
     return rc;
+  }
+  if (!(phases & NERF_STEP_BACKWARD)) return NERF_OK;
   if ((rc = nerf_mlp_dgrad(c->packed, c->layout, c->stash, c->sigma_rgb, c->d_sigma_rgb, rows, c->dstash, stream))) return rc;
   if ((rc = nerf_mlp_wgrad(c->layout, c->stash, c->dstash, rows, c->grads, 0, stream))) return rc;
   adam_kernel<<<blocks_for(m->n_params, 256), 256, 0, s>>>(c->params, c->grads, c->exp_avg, c->exp_avg_sq, m->n_params, 0.f, c->beta1,

@@ -221,6 +221,28 @@ def render_inference(st, rays_o, rays_d, z):
     return composite_forward(mlp_forward_rays(st, rays_o, rays_d, z, None), z, extras=True)
 
 
+def render_image(st, poses_dev, pose_index, camera_info, n_sample, near=2.0, far=6.0, ray_begin=0, ray_count=None, perturb=False,
+                 seed=0, offset=0, workspace=None):
+    """A frame (or the slice [ray_begin, ray_begin + ray_count) of its ray ids) by one nerf_render_image call:
+    ray generation, depths, inference MLP, compositing -> (rgb [n,3], depth [n], acc [n])."""
+    _need_cuda(poses_dev)
+    W, H = int(camera_info["width"]), int(camera_info["height"])
+    if ray_count is None:
+        ray_count = W * H - ray_begin
+    fx, fy, cx, cy = _intrinsics(camera_info)
+    dev = poses_dev.device
+    need = int(_lib.load().nerf_render_workspace_bytes(int(ray_count), int(n_sample)))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    rgb = torch.empty((ray_count, 3), dtype=torch.float32, device=dev)
+    depth = torch.empty((ray_count,), dtype=torch.float32, device=dev)
+    acc = torch.empty((ray_count,), dtype=torch.float32, device=dev)
+    call("nerf_render_image", ptr(st.packed), st.layout, ptr(poses_dev), int(pose_index), fx, fy, cx, cy, W, H, int(ray_begin),
+         int(ray_count), int(n_sample), float(near), float(far), 1 if perturb else 0, int(seed), int(offset), ptr(rgb), ptr(depth),
+         ptr(acc), ptr(workspace), stream_ptr())
+    return rgb, depth, acc
+
+
 class MLPFunction(torch.autograd.Function):
     """NeRFmodel.forward: (pos [n,3], dir [n,3]) -> sigma_rgb [n,4]; gradients reach the parameters."""
 
@@ -339,8 +361,9 @@ class Trainer:
         self._dev_iteration = 0
         self._fixed = None                          # (odt, z, sigma_rgb, dsr, batch9) once the first fast step allocates them
         self._cfg = {}                              # from_batch9 -> NerfTrainStep
-        self._graphs = {}                           # from_batch9 -> torch.cuda.CUDAGraph
-        self._direct_steps = {False: 0, True: 0}
+        self._graphs = {}                           # (from_batch9, phases) -> torch.cuda.CUDAGraph
+        self._direct_steps = {}
+        self._loss_host, self._loss_event = None, None
 
     def lr(self):
         return self.lr0 * self.lr_decay ** (self.iteration // self.lr_decay_steps)
@@ -376,9 +399,26 @@ class Trainer:
         c.step_state = self.step_state.data_ptr()
         return c
 
-    def _step_whole(self, batch9):
-        """The whole step through nerf_train_step: one C call, and from the third step on one CUDA-graph replay."""
+    def _launch_phases(self, key, phases):
+        """nerf_train_step(phases): direct C call for the first two steps, then a CUDA-graph replay of the same call."""
         import ctypes
+        g = self._graphs.get((key, phases))
+        if g is not None:
+            g.replay()
+            return
+        call("nerf_train_step", ctypes.byref(self._cfg[key]), phases, stream_ptr())
+        n = self._direct_steps[(key, phases)] = self._direct_steps.get((key, phases), 0) + 1
+        if self.use_graph and n == 2:                                # warmed up: capture the same call for replay
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):                                # capture only records; nothing executes
+                call("nerf_train_step", ctypes.byref(self._cfg[key]), phases, stream_ptr())
+            self._graphs[(key, phases)] = g
+
+    def _step_whole(self, batch9, loss_to_host=False):
+        """The whole step through nerf_train_step.  ``loss_to_host``: the step is enqueued as its two phases with an async
+        D2H copy of the loss between them; the host waits for that copy only (the backward phase is still running when it
+        returns), so a loop that reads every step's loss (train.py:468) keeps the GPU busy."""
         key = batch9 is not None
         if key not in self._cfg:
             self._cfg[key] = self._train_step_cfg(key)
@@ -387,35 +427,37 @@ class Trainer:
             self._dev_iteration = self.iteration
         if key:
             self._fixed[4].copy_(batch9, non_blocking=True)   # H2D (pinned host batch) or D2D, straight into the step's input
-        g = self._graphs.get(key)
-        if g is not None:
-            g.replay()
+        if loss_to_host:
+            if self._loss_host is None:
+                self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+                self._loss_event = torch.cuda.Event()
+            self._launch_phases(key, 1)
+            self._loss_host.copy_(self.loss, non_blocking=True)
+            self._loss_event.record()
+            self._launch_phases(key, 2)
         else:
-            call("nerf_train_step", ctypes.byref(self._cfg[key]), stream_ptr())
-            self._direct_steps[key] += 1
-            if self.use_graph and self._direct_steps[key] == 2:      # warmed up: capture the same call for replay
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                saved = self.step_state.clone()
-                with torch.cuda.graph(g):
-                    call("nerf_train_step", ctypes.byref(self._cfg[key]), stream_ptr())
-                self.step_state.copy_(saved)                         # capture does not execute, but be explicit
-                self._graphs[key] = g
+            self._launch_phases(key, 3)
         self.iteration += 1
         self._dev_iteration += 1
         self.launches_per_step = 8                  # batch, mlp fwd, composite_train, dgrad, wgrad, heads, adam, pack (+1 memset)
+        if loss_to_host:
+            self._loss_event.synchronize()
+            return float(self._loss_host[0])
         return self.loss
 
-    def step(self, rays=None, timers=None):
-        """One optimisation step.  ``rays`` = optional batch: a generateBatch() array [N,9] already on the device (e.g. uploaded
+    def step(self, rays=None, timers=None, loss_to_host=False):
+        """One optimisation step.  Returns the loss as a device tensor, or with ``loss_to_host`` as a Python float (read back
+        as soon as the forward phase has finished, see _step_whole).  ``rays`` = optional batch: a generateBatch() array [N,9] already on the device (e.g. uploaded
         from the host like train.py:448) or (rays_o, rays_d, target) device tensors; default draws the batch on the GPU.
         ``timers`` = optional dict: CUDA-event pairs per kernel are appended to timers[name]."""
         st, S = self.st, self.n_sample
         if self.exchange is None and timers is None:
             if rays is None and self.images is not None:
-                return self._step_whole(None)
+                return self._step_whole(None, loss_to_host)
             if torch.is_tensor(rays) and rays.dim() == 2 and tuple(rays.shape) == (self.n_rays, 9) and rays.dtype == torch.float32:
-                return self._step_whole(rays)
+                return self._step_whole(rays, loss_to_host)
+        if torch.is_tensor(rays) and rays.device.type != "cuda":
+            rays = rays.to(st.device, non_blocking=True)
         W, H = int(self.cam["width"]), int(self.cam["height"])
         dev = st.device
         launches = 0
@@ -483,4 +525,4 @@ class Trainer:
         st.pack()
         launches += 2                               # adam, pack
         self.launches_per_step = launches
-        return self.loss
+        return float(self.loss.item()) if loss_to_host else self.loss

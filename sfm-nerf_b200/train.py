@@ -21,7 +21,7 @@ import random
 import numpy as np
 import torch
 
-from . import engine
+from . import _lib, engine
 from .NeRFModel import NeRFmodel
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
@@ -134,15 +134,19 @@ def test_image(model, image, pose, camera_info, args):
     poses_dev = engine.poses_to_device(np.asarray(pose, dtype=np.float64), dev)
     prediction = torch.zeros((H * W, 3), device=dev)
     step = int(args.n_rays_batch)
-    st = model.kernel_state()
-    with torch.no_grad():
-        st.frozen = True                     # weights do not change inside this loop: pack once
-        try:
-            for i in range(0, H * W, step):
-                o, d = engine.raygen_image(poses_dev, 0, camera_info, i, min(step, H * W - i))
-                prediction[i:i + step] = render(model, o, d, args, near=args.near, far=args.far)
-        finally:
-            st.frozen = False
+    st = model.kernel_state()                # packs the current weights once for the whole frame
+    S, perturb = int(args.n_sample), bool(getattr(args, "perturb", False))
+    workspace = None
+    for i in range(0, H * W, step):          # train.py:745-757, one nerf_render_image call per batch of rays
+        n = min(step, H * W - i)
+        off = _jitter_counter[0]
+        if perturb:
+            _jitter_counter[0] += (n * S + 3) // 4
+        if workspace is None:
+            workspace = torch.empty(int(_lib.load().nerf_render_workspace_bytes(n, S)), dtype=torch.uint8, device=dev)
+        prediction[i:i + n] = engine.render_image(st, poses_dev, 0, camera_info, S, near=args.near, far=args.far, ray_begin=i,
+                                                  ray_count=n, perturb=perturb, seed=torch.initial_seed() & 0xFFFFFFFFFFFFFFFF,
+                                                  offset=off, workspace=workspace)[0]
     gt = torch.as_tensor(np.asarray(image).reshape(-1, 3)).to(dev)
     mse = torch.mean((gt - prediction.to(gt.dtype)) ** 2)
     return prediction.reshape(H, W, 3), mse.item()

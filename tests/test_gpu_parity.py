@@ -554,6 +554,25 @@ def test_fused_train_batch_launch_is_bit_identical(pkg, orc):
         E.call("nerf_unpack_batch", None, n, E.ptr(o3), E.ptr(d3), E.ptr(t3), S, 2.0, 6.0, 0, 0, 0, E.ptr(z3), E.stream_ptr())
 
 
+def test_render_image_one_call_equals_the_four_launches(pkg, model_pe):
+    """nerf_render_image (K1 + K2 + K4 + K5 in one call) is bit-identical to raygen_image + sample_z + mlp_forward_rays +
+    composite_forward, for a ragged ray slice, with and without jitter; an empty slice is a no-op."""
+    E = pkg.engine
+    cam = pkg.synthetic.make_camera_info(37, 23)
+    poses = E.poses_to_device(pkg.synthetic.sphere_poses(3, seed=2), "cuda")
+    with torch.no_grad():
+        st = model_pe.kernel_state()
+        for perturb in (False, True):
+            begin, count, S = 101, 333, 48
+            o, d = E.raygen_image(poses, 2, cam, begin, count)
+            z = E.sample_z(count, S, 2.0, 6.0, "cuda", perturb=perturb, seed=17, offset=5)
+            rgb, depth, acc = E.composite_forward(E.mlp_forward_rays(st, o, d, z, None), z, extras=True)
+            rgb2, depth2, acc2 = E.render_image(st, poses, 2, cam, S, ray_begin=begin, ray_count=count, perturb=perturb, seed=17, offset=5)
+            assert torch.equal(rgb, rgb2) and torch.equal(depth, depth2) and torch.equal(acc, acc2)
+        rgb0, _, _ = E.render_image(st, poses, 0, cam, 16, ray_begin=0, ray_count=0)
+        assert rgb0.shape == (0, 3)
+
+
 def test_whole_step_call_and_graph_replay_match_per_kernel_path(pkg, orc):
     """nerf_train_step (one C call; replayed as a CUDA graph from the third step on, iteration counter / StepLR / bias
     corrections on the device) follows the per-kernel sequence with host-side scalars: same batches, same losses, same
@@ -564,7 +583,7 @@ def test_whole_step_call_and_graph_replay_match_per_kernel_path(pkg, orc):
     images = torch.tensor(np.random.default_rng(1).random((4, 30, 40, 3)).astype(np.float32)).cuda()
     n, S, steps = 256, 32, 7
 
-    def run(whole, host_batches=None):
+    def run(whole, host_batches=None, host_loss=False):
         torch.manual_seed(0)
         m = pkg.NeRFmodel().cuda()
         tr = E.Trainer(m, images, poses, cam, n, S, perturb=True, seed=5, lr_decay_steps=3, lr_decay=0.5)
@@ -573,10 +592,14 @@ def test_whole_step_call_and_graph_replay_match_per_kernel_path(pkg, orc):
             rays = None if host_batches is None else host_batches[i]
             if not whole:
                 rays = rays.cuda() if rays is not None else None
-            losses.append(float((tr.step(rays=rays) if whole else tr.step(rays=rays, timers={})).item()))
+            if host_loss:
+                losses.append(tr.step(rays=rays, loss_to_host=True))
+                assert isinstance(losses[-1], float)
+            else:
+                losses.append(float((tr.step(rays=rays) if whole else tr.step(rays=rays, timers={})).item()))
         assert tr.iteration == steps
         if whole:
-            assert int(tr.step_state.item()) == steps and len(tr._graphs) == 1
+            assert int(tr.step_state.item()) == steps and len(tr._graphs) == (2 if host_loss else 1)
         w = tr.st.flat.clone()
         tr.close()
         return losses, w
@@ -596,6 +619,10 @@ def test_whole_step_call_and_graph_replay_match_per_kernel_path(pkg, orc):
     assert lc[0] == ld[0]
     np.testing.assert_allclose(lc, ld, rtol=2e-4)
     assert float((wc - wd).abs().mean()) < 2e-5 and float((wc - wd).abs().max()) < 7 * 5e-4
+    le, we = run(True, hb, host_loss=True)          # forward graph | loss D2H | backward graph
+    assert le[0] == ld[0]
+    np.testing.assert_allclose(le, ld, rtol=2e-4)
+    assert float((we - wd).abs().mean()) < 2e-5
 
 
 def test_whole_step_resumes_and_interleaves(pkg, orc):

@@ -1,0 +1,16 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, smoke, the bench (plain), then the ncu launch list of the same bench command.
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err || tail -5 gpurun_out/bench.err
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["e2e"], d["step_launch"], d["kernels"], d["clocks"])
+PY
+if [ "$1" = "ncu" ]; then
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+  tail -c 300 gpurun_out/ncu_bench.log
+fi
