@@ -10,7 +10,9 @@ d = json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
 print(d["value"], d["ms_per_step"], d["e2e"], d["step_launch"], d["kernels"], d["clocks"])
 PY
 if [ "$1" = "ncu" ]; then
+  # only this library's kernels: the synthetic-scene generation in front of the bench is thousands of torch launches
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+      --kernel-name 'regex:mlp_fused|wgrad_kernel|head_grad|pack_|adam_|composite_|train_batch|sample_z|raygen_|draw_pixels|mse_loss' \
       python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
   tail -c 300 gpurun_out/ncu_bench.log
 fi
