@@ -392,9 +392,9 @@ def run_ours(args):
         "e2e": {"value": n_rays * world * e2e_steps / e2e_ms * 1e3, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 9 * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": launches,
-        "step_launch": {"mode": "cuda graph replay of nerf_train_step (8 kernels + 1 memset per step)" if graph_replay else
+        "step_launch": {"mode": ("cuda graph replay of nerf_train_step (8 kernels + 1 memset per step" + (", cross-rank barrier inside the graph)" if world > 1 else ")")) if graph_replay else
                                 "per-kernel sequence from the host",
-                        "ms_per_step_instrumented": ms_instrumented / args.steps,
+                        "graph_error": trainer.graph_error, "ms_per_step_instrumented": ms_instrumented / args.steps,
                         "note": "`kernels` / `roofline` durations: the same steps launched kernel by kernel with CUDA events, timed right after the headline region"},
         "grad_exchange": {"mode": grad_exchange, "note": grad_exchange_note,
                           "what": "nvls / p2p: gradient sum over ranks read through NVLink inside the Adam kernel (symmetric memory, one barrier); nccl: allreduce"},

@@ -214,8 +214,8 @@ int nerf_render_image(const void* packed, int layout, const double* poses, int p
  *   batch9 != NULL : [n_rays, 9] device array, a generateBatch() result (the caller refreshes it between steps)
  * The launches are exactly those of nerf_train_batch | nerf_unpack_batch, nerf_mlp_forward_rays (with stash),
  * nerf_composite_train (grad_scale 1), nerf_mlp_dgrad, nerf_mlp_wgrad (accumulate 0), nerf_adam_step(grad_scale),
- * nerf_mlp_pack_weights; every buffer is the caller's and must be sized as for those calls.  Single-rank optimiser: a
- * data-parallel caller uses world / rank for the RNG streams only and exchanges gradients itself (nerf_adam_step_reduce).
+ * nerf_mlp_pack_weights; every buffer is the caller's and must be sized as for those calls.  world / rank select the RNG
+ * streams; with peer_grads / multicast_grads the optimiser is nerf_adam_step_reduce (see the phases below).
  * struct_bytes = sizeof(NerfTrainStep) (checked).
  * ------------------------------------------------------------------------------------- */
 typedef struct NerfTrainStep {
@@ -236,14 +236,20 @@ typedef struct NerfTrainStep {
   void *stash, *dstash, *packed;
   float *params, *grads, *exp_avg, *exp_avg_sq;
   unsigned long long* step_state;
+  const float* peer_grads[8];      /* data parallel (world > 1), as nerf_adam_step_reduce: the ranks' gradient buffers ... */
+  const float* multicast_grads;    /* ... or their NVLink multicast address; both NULL: plain Adam on `grads` */
 } NerfTrainStep;
-/* phases: NERF_STEP_FORWARD = batch + render + loss (cfg->loss[0] is final when these launches complete),
- * NERF_STEP_BACKWARD = dgrad + wgrad + Adam + re-pack + counter advance, NERF_STEP_ALL = both.  A host that wants the loss of
- * every step (train.py:468) enqueues FORWARD, an async D2H copy of the loss + event, then BACKWARD, and waits on the event
- * only: the backward launches are still running while it prepares the next step. */
+/* phases (bit mask): NERF_STEP_FORWARD = batch + render + loss (cfg->loss[0] is final when these launches complete);
+ * NERF_STEP_GRADS = dgrad + wgrad (cfg->grads is final); NERF_STEP_UPDATE = Adam + re-pack + counter advance.
+ * A host that wants the loss of every step (train.py:468) enqueues FORWARD, an async D2H copy of the loss + event, then
+ * BACKWARD, and waits on the event only: the backward launches are still running while it prepares the next step.
+ * A data-parallel host enqueues FORWARD | GRADS, its cross-rank barrier, then UPDATE with peer_grads / multicast_grads set
+ * (the gradient sum over ranks is read through NVLink inside the Adam kernel; grad_scale = 1/world). */
 #define NERF_STEP_FORWARD 1
-#define NERF_STEP_BACKWARD 2
-#define NERF_STEP_ALL 3
+#define NERF_STEP_GRADS 2
+#define NERF_STEP_UPDATE 4
+#define NERF_STEP_BACKWARD 6
+#define NERF_STEP_ALL 7
 int nerf_train_step(const NerfTrainStep* cfg, int phases, void* stream);
 
 /* ---------------------------------------------------------------------------------------

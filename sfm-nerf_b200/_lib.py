@@ -64,7 +64,8 @@ class NerfTrainStep(C.Structure):
         [("n_rays", _L), ("fx", _D), ("fy", _D), ("cx", _D), ("cy", _D), ("near", _F), ("far", _F), ("seed", _U), ("z_seed", _U),
          ("lr0", _D), ("lr_decay", _D), ("lr_decay_steps", _L), ("beta1", _F), ("beta2", _F), ("eps", _F), ("grad_scale", _F)] + \
         [(n, _P) for n in ("poses", "images", "batch9", "rays_o", "rays_d", "target", "z", "sigma_rgb", "d_sigma_rgb", "loss",
-                           "composite_ws", "stash", "dstash", "packed", "params", "grads", "exp_avg", "exp_avg_sq", "step_state")]
+                           "composite_ws", "stash", "dstash", "packed", "params", "grads", "exp_avg", "exp_avg_sq", "step_state")] + \
+        [("peer_grads", _P * 8), ("multicast_grads", _P)]
 
 
 # name -> (restype, argtypes); must list every symbol include/nerf_b200.h declares

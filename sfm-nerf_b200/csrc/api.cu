@@ -525,7 +525,7 @@ int nerf_train_step(const NerfTrainStep* c, int phases, void* stream) {
   DeviceInfo* dev;
   int rc = device_info(&dev);
   if (rc != NERF_OK) return rc;
-  if (!c || c->struct_bytes != (int64_t)sizeof(NerfTrainStep) || phases < 1 || phases > 3) return NERF_ERR_ARG;
+  if (!c || c->struct_bytes != (int64_t)sizeof(NerfTrainStep) || phases < 1 || phases > NERF_STEP_ALL) return NERF_ERR_ARG;
   const ModelLayout* m = get_layout(c->layout);
   if (!m) return NERF_ERR_LAYOUT;
   if (c->n_rays <= 0 || c->n_sample <= 0 || c->world < 1 || c->rank < 0 || c->rank >= c->world || c->lr_decay_steps < 1 ||
@@ -548,12 +548,29 @@ int nerf_train_step(const NerfTrainStep* c, int phases, void* stream) {
   if ((rc = nerf_composite_train(c->sigma_rgb, c->z, c->target, c->n_rays, c->n_sample, 1.0f, c->loss, c->d_sigma_rgb, c->composite_ws, stream)))
     return rc;
   }
-  if (!(phases & NERF_STEP_BACKWARD)) return NERF_OK;
-  if ((rc = nerf_mlp_dgrad(c->packed, c->layout, c->stash, c->sigma_rgb, c->d_sigma_rgb, rows, c->dstash, stream))) return rc;
-  if ((rc = nerf_mlp_wgrad(c->layout, c->stash, c->dstash, rows, c->grads, 0, stream))) return rc;
-  adam_kernel<<<blocks_for(m->n_params, 256), 256, 0, s>>>(c->params, c->grads, c->exp_avg, c->exp_avg_sq, m->n_params, 0.f, c->beta1,
-                                                           c->beta2, c->eps, 1.f, 1.f, c->grad_scale,
-                                                           AdamSchedule{c->step_state, c->lr0, c->lr_decay, (long long)c->lr_decay_steps});
+  if (phases & NERF_STEP_GRADS) {
+    if ((rc = nerf_mlp_dgrad(c->packed, c->layout, c->stash, c->sigma_rgb, c->d_sigma_rgb, rows, c->dstash, stream))) return rc;
+    if ((rc = nerf_mlp_wgrad(c->layout, c->stash, c->dstash, rows, c->grads, 0, stream))) return rc;
+  }
+  if (!(phases & NERF_STEP_UPDATE)) return NERF_OK;
+  const AdamSchedule sched{c->step_state, c->lr0, c->lr_decay, (long long)c->lr_decay_steps};
+  if (c->world > 1 && (c->multicast_grads || c->peer_grads[0])) {
+    // data parallel: the gradient sum over ranks is read through NVLink inside the optimiser kernel (nerf_adam_step_reduce)
+    if (c->world > 8 || (m->n_params & 3) || !nerf_aligned(c->params, 16) || !nerf_aligned(c->exp_avg, 16) ||
+        !nerf_aligned(c->exp_avg_sq, 16) || (c->multicast_grads && !nerf_aligned(c->multicast_grads, 16)))
+      return NERF_ERR_ALIGN;
+    PeerGrads peers{};
+    for (int r = 0; r < c->world && !c->multicast_grads; ++r) {
+      if (!c->peer_grads[r] || !nerf_aligned(c->peer_grads[r], 16)) return NERF_ERR_ALIGN;
+      peers.ptr[r] = c->peer_grads[r];
+    }
+    adam_reduce_kernel<<<blocks_for(m->n_params / 4, 256), 256, 0, s>>>(c->params, peers, c->world, c->multicast_grads, c->exp_avg,
+                                                                        c->exp_avg_sq, m->n_params / 4, 0.f, c->beta1, c->beta2, c->eps,
+                                                                        1.f, 1.f, c->grad_scale, sched);
+  } else {
+    adam_kernel<<<blocks_for(m->n_params, 256), 256, 0, s>>>(c->params, c->grads, c->exp_avg, c->exp_avg_sq, m->n_params, 0.f, c->beta1,
+                                                             c->beta2, c->eps, 1.f, 1.f, c->grad_scale, sched);
+  }
   NERF_LAUNCH_CHECK();
   return launch_pack(c->params, c->layout, c->packed, c->step_state, stream);
 }
@@ -579,7 +596,7 @@ int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, in
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_reduce_kernel<<<blocks_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(params, peers, n_ranks, multicast_grads, exp_avg, exp_avg_sq,
                                                                              n / 4, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2),
-                                                                             grad_scale);
+                                                                             grad_scale, AdamSchedule{});
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }

@@ -244,22 +244,25 @@ mse_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ target,
 // evaluated in fp64 like the host path of nerf_adam_step and rounded to fp32 once.
 struct AdamSchedule { const unsigned long long* iter_ptr; double lr0, gamma; long long decay_steps; };
 
+__device__ __forceinline__ void adam_device_schedule(const AdamSchedule& sched, float b1, float b2, float& lr, float& bc1, float& bc2_sqrt) {
+  if (sched.iter_ptr == nullptr) return;                 // block-uniform
+  __shared__ float sh[3];
+  if (threadIdx.x == 0) {
+    const unsigned long long it = *sched.iter_ptr;
+    const double step = (double)(it + 1ull);
+    sh[0] = (float)(sched.lr0 * pow(sched.gamma, (double)(it / (unsigned long long)sched.decay_steps)));
+    sh[1] = (float)(1.0 - pow((double)b1, step));
+    sh[2] = (float)sqrt(1.0 - pow((double)b2, step));
+  }
+  __syncthreads();
+  lr = sh[0]; bc1 = sh[1]; bc2_sqrt = sh[2];
+}
+
 // torch.optim.Adam (train.py:401) over the flat parameter vector.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                             float bc1, float bc2_sqrt, float grad_scale, AdamSchedule sched) {
-  if (sched.iter_ptr != nullptr) {                       // block-uniform
-    __shared__ float sh[3];
-    if (threadIdx.x == 0) {
-      const unsigned long long it = *sched.iter_ptr;
-      const double step = (double)(it + 1ull);
-      sh[0] = (float)(sched.lr0 * pow(sched.gamma, (double)(it / (unsigned long long)sched.decay_steps)));
-      sh[1] = (float)(1.0 - pow((double)b1, step));
-      sh[2] = (float)sqrt(1.0 - pow((double)b2, step));
-    }
-    __syncthreads();
-    lr = sh[0]; bc1 = sh[1]; bc2_sqrt = sh[2];
-  }
+  adam_device_schedule(sched, b1, b2, lr, bc1, bc2_sqrt);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gi = g[i] * grad_scale;
@@ -279,7 +282,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 struct PeerGrads { const float* ptr[8]; };
 __global__ void adam_reduce_kernel(float* __restrict__ p, PeerGrads peers, int n_ranks, const float* mc_grads, float* __restrict__ m,
                                    float* __restrict__ v, int64_t n4, float lr, float b1, float b2, float eps, float bc1,
-                                   float bc2_sqrt, float grad_scale) {
+                                   float bc2_sqrt, float grad_scale, AdamSchedule sched) {
+  adam_device_schedule(sched, b1, b2, lr, bc1, bc2_sqrt);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 g;

@@ -354,15 +354,16 @@ class Trainer:
         self.iteration = 0
         self.launches_per_step = 0
         # whole-step entry point (nerf_train_step): fixed per-step buffers + the device-side iteration counter, so that the
-        # step has no step-dependent launch argument and replays as a CUDA graph (single rank; world > 1 keeps the
-        # per-kernel sequence below because its gradient barrier is a torch op)
-        self.use_graph = bool(graph)
+        # step has no step-dependent launch argument and replays as a CUDA graph (world > 1: one graph per step parity, the
+        # symmetric-memory barrier captured with it; the NCCL-allreduce fallback keeps the per-kernel sequence below)
+        import os
+        self.use_graph = bool(graph) and os.environ.get("NERF_TRAIN_GRAPH", "1") != "0"
         self.step_state = torch.zeros(1, dtype=torch.int64, device=dev)
         self._dev_iteration = 0
         self._fixed = None                          # (odt, z, sigma_rgb, dsr, batch9) once the first fast step allocates them
-        self._cfg = {}                              # from_batch9 -> NerfTrainStep
-        self._graphs = {}                           # (from_batch9, phases) -> torch.cuda.CUDAGraph
-        self._direct_steps = {}
+        self._cfg = {}                              # (from_batch9, step parity) -> NerfTrainStep
+        self._graphs, self._graph_tried = {}, set() # (from_batch9, step parity, segment) -> torch.cuda.CUDAGraph
+        self.graph_error = ""
         self._loss_host, self._loss_event = None, None
 
     def lr(self):
@@ -371,7 +372,7 @@ class Trainer:
     def close(self):
         self.st.frozen = False
 
-    def _train_step_cfg(self, from_batch9):
+    def _train_step_cfg(self, from_batch9, parity):
         import ctypes
         st, dev, n, S = self.st, self.st.device, self.n_rays, self.n_sample
         if self._fixed is None:
@@ -395,48 +396,79 @@ class Trainer:
         c.rays_o, c.rays_d, c.target, c.z = odt[0].data_ptr(), odt[1].data_ptr(), odt[2].data_ptr(), z.data_ptr()
         c.sigma_rgb, c.d_sigma_rgb, c.loss, c.composite_ws = sigma_rgb.data_ptr(), dsr.data_ptr(), self.loss.data_ptr(), ws.data_ptr()
         c.stash, c.dstash, c.packed = self.stash.data_ptr(), self.dstash.data_ptr(), st.packed.data_ptr()
-        c.params, c.grads, c.exp_avg, c.exp_avg_sq = st.flat.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        c.params, c.exp_avg, c.exp_avg_sq = st.flat.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
         c.step_state = self.step_state.data_ptr()
+        if self.exchange is None:
+            c.grads = self.grads.data_ptr()
+        else:
+            # data parallel: wgrad writes this step's symmetric gradient buffer (double-buffered by step parity); the Adam
+            # kernel reads the sum over ranks through the peers' mappings / the multicast address
+            c.grads = self.exchange.local(parity).data_ptr()
+            peers, mc = self.exchange.peer_pointers(parity)
+            for r in range(self.world):
+                c.peer_grads[r] = peers[r]
+            c.multicast_grads = mc
         return c
 
-    def _launch_phases(self, key, phases):
-        """nerf_train_step(phases): direct C call for the first two steps, then a CUDA-graph replay of the same call."""
-        import ctypes
-        g = self._graphs.get((key, phases))
+    def _run_segment(self, name, fn):
+        """Run ``fn`` (a fixed sequence of nerf_train_step phases [+ the cross-rank barrier]) directly the first time, then
+        capture the same sequence into a CUDA graph and replay it from then on."""
+        g = self._graphs.get(name)
         if g is not None:
             g.replay()
             return
-        call("nerf_train_step", ctypes.byref(self._cfg[key]), phases, stream_ptr())
-        n = self._direct_steps[(key, phases)] = self._direct_steps.get((key, phases), 0) + 1
-        if self.use_graph and n == 2:                                # warmed up: capture the same call for replay
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):                                # capture only records; nothing executes
-                call("nerf_train_step", ctypes.byref(self._cfg[key]), phases, stream_ptr())
-            self._graphs[(key, phases)] = g
+        fn()
+        if self.use_graph and name not in self._graph_tried:
+            self._graph_tried.add(name)
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):                            # capture only records; nothing executes
+                    fn()
+                self._graphs[name] = g
+            except Exception as e:                                   # noqa: BLE001 -- keep training with direct calls
+                self.use_graph, self.graph_error = False, f"{type(e).__name__}: {e}"
+                torch.cuda.synchronize()
 
     def _step_whole(self, batch9, loss_to_host=False):
-        """The whole step through nerf_train_step.  ``loss_to_host``: the step is enqueued as its two phases with an async
-        D2H copy of the loss between them; the host waits for that copy only (the backward phase is still running when it
-        returns), so a loop that reads every step's loss (train.py:468) keeps the GPU busy."""
-        key = batch9 is not None
-        if key not in self._cfg:
-            self._cfg[key] = self._train_step_cfg(key)
+        """The whole step through nerf_train_step (one C call per phase group, CUDA-graph replays after the first step).
+        ``loss_to_host``: the forward phase, an async D2H copy of the loss, then the rest; the host waits for that copy only
+        (the backward phases are still running when it returns), so a loop that reads every step's loss (train.py:468)
+        keeps the GPU busy.  world > 1: forward + gradients, the stream-ordered cross-rank barrier, then the update phase
+        whose Adam kernel reads the gradient sum over ranks through NVLink."""
+        import ctypes
+        key, ex = batch9 is not None, self.exchange
+        parity = self.iteration & 1 if ex is not None else 0
+        if (key, parity) not in self._cfg:
+            self._cfg[(key, parity)] = self._train_step_cfg(key, parity)
+        cfg = ctypes.byref(self._cfg[(key, parity)])
         if self._dev_iteration != self.iteration:            # the per-kernel path ran in between, or a checkpoint was resumed
             self.step_state.fill_(self.iteration)
             self._dev_iteration = self.iteration
         if key:
             self._fixed[4].copy_(batch9, non_blocking=True)   # H2D (pinned host batch) or D2D, straight into the step's input
+
+        def phases(mask):
+            call("nerf_train_step", cfg, mask, stream_ptr())
+
+        def rest(first):                                      # everything after (or including) the forward phase
+            if ex is None:
+                phases(first | 6)
+            else:
+                phases(first | 2)
+                ex.barrier()
+                phases(4)
+
         if loss_to_host:
             if self._loss_host is None:
                 self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
                 self._loss_event = torch.cuda.Event()
-            self._launch_phases(key, 1)
+            self._run_segment((key, parity, "forward"), lambda: phases(1))
             self._loss_host.copy_(self.loss, non_blocking=True)
             self._loss_event.record()
-            self._launch_phases(key, 2)
+            self._run_segment((key, parity, "backward"), lambda: rest(0))
         else:
-            self._launch_phases(key, 3)
+            self._run_segment((key, parity, "step"), lambda: rest(1))
         self.iteration += 1
         self._dev_iteration += 1
         self.launches_per_step = 8                  # batch, mlp fwd, composite_train, dgrad, wgrad, heads, adam, pack (+1 memset)
@@ -451,7 +483,7 @@ class Trainer:
         from the host like train.py:448) or (rays_o, rays_d, target) device tensors; default draws the batch on the GPU.
         ``timers`` = optional dict: CUDA-event pairs per kernel are appended to timers[name]."""
         st, S = self.st, self.n_sample
-        if self.exchange is None and timers is None:
+        if (self.exchange is None or self.exchange.mode != "nccl") and timers is None:
             if rays is None and self.images is not None:
                 return self._step_whole(None, loss_to_host)
             if torch.is_tensor(rays) and rays.dim() == 2 and tuple(rays.shape) == (self.n_rays, 9) and rays.dtype == torch.float32:

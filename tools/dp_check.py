@@ -47,7 +47,8 @@ for mode in ("nccl", "nccl_again", "p2p", "nvls"):
         ref = flat3
     diff = float((flat3 - ref).abs().max()) if ref is not None else None
     res[mode] = {"exchange_mode": tr.exchange.mode, "ms_per_step": ev0.elapsed_time(ev1) / 20, "replicas_bit_identical": identical,
-                 "max_abs_weight_diff_vs_nccl_after_3_steps": diff, "loss": float(tr.loss.item())}
+                 "max_abs_weight_diff_vs_nccl_after_3_steps": diff, "loss": float(tr.loss.item()),
+                 "cuda_graphs": len(tr._graphs), "graph_error": tr.graph_error}
     tr.close()
     assert identical, f"{mode}: replicas diverged"
     if ref is not None and mode != "nccl":
