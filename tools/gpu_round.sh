@@ -16,3 +16,10 @@ if [ "$1" = "ncu" ]; then
       python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
   tail -c 300 gpurun_out/ncu_bench.log
 fi
+if [ "$2" = "full" ]; then
+  # one full-section capture of each hot kernel (inference fwd, training fwd, dgrad, wgrad, head-grad) at the C2 shape
+  python tools/profile_kernels.py > gpurun_out/profile_plain.log 2>&1 && \
+  ncu --set full --import-source on --clock-control none --kernel-name 'regex:mlp_fused|wgrad_kernel|head_grad' \
+      --launch-skip 10 -c 5 -f -o gpurun_out/prof_r1f python tools/profile_kernels.py > gpurun_out/ncu_full.log 2>&1
+  tail -2 gpurun_out/ncu_full.log
+fi
