@@ -328,6 +328,24 @@ def run_ours(args):
     mlp_infer_ms = ev6.elapsed_time(ev7) / 5
     render_rays_s = IMG * IMG * n_frames / render_ms * 1e3
     trainer.close()
+    # BASELINE config 1 (the reference's CPU-runnable case): test_image of one 100x100 view x 64 deterministic samples through the
+    # public API -- host image in, prediction + MSE (a host float) out; rank 0 only
+    c1 = None
+    if rank == 0:
+        cam1 = s.synthetic.make_camera_info(100, 100)
+        img1 = np.random.default_rng(7).random((100, 100, 3)).astype(np.float32)
+        args_c1 = argparse.Namespace(n_sample=N_SAMPLE, perturb=False, chunk_size=32768, n_rays_batch=4096, near=2.0, far=6.0)
+        torch.manual_seed(0)
+        model_c1 = s.NeRFmodel().to(dev)              # random-init weights, as the config says (the trained model above renders black)
+        for _ in range(2):
+            pred1, mse1 = s.test_image(model_c1, img1, poses_np[0], cam1, args_c1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            pred1, mse1 = s.test_image(model_c1, img1, poses_np[0], cam1, args_c1)
+        torch.cuda.synchronize()
+        c1 = {"gpu_ms": 1e3 * (time.perf_counter() - t0) / 5, "pred": pred1.cpu(), "mse": mse1, "img": img1, "cam": cam1,
+              "sd": {k: v.detach().cpu().clone() for k, v in model_c1.state_dict().items()}}
 
     if rank != 0:
         if world > 1:
@@ -374,6 +392,20 @@ def run_ours(args):
                         "sample": f"3 train steps of {n_rays} rays x {N_SAMPLE} samples (oracle port of train.py:447-465 on torch CPU, "
                                   f"{threads} threads, per-ray Python ray generation included as in the reference)"}
 
+    render_c1 = None
+    if c1 is not None:
+        render_c1 = {"workload": "test_image: one 100x100 view x 64 deterministic samples, random-init weights, wall clock incl. host<->device copies",
+                     "gpu_ms": c1["gpu_ms"], "gpu_rays_per_s": 1e4 / c1["gpu_ms"] * 1e3}
+        if world == 1 and not args.no_cpu_baseline:
+            import torch as _t
+            from oracle import nerf_oracle as orc
+            _t.set_num_threads(os.cpu_count() or 1)
+            t0 = time.perf_counter()
+            ref_pred, ref_mse = orc.test_image(c1["sd"], c1["img"], poses_np[0], c1["cam"], N_SAMPLE, 4096)
+            cpu_s = time.perf_counter() - t0
+            render_c1.update({"cpu_port_s": cpu_s, "cpu_port_rays_per_s": 1e4 / cpu_s, "cpu_cores": _t.get_num_threads(),
+                              "max_abs_rgb_err_vs_cpu_port": float((c1["pred"] - ref_pred).abs().max()),
+                              "mse_gpu": c1["mse"], "mse_cpu_port": ref_mse})
     value = n_rays * world * args.steps / ms_total * 1e3
     line = {
         "metric": "train_step_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -387,6 +419,7 @@ def run_ours(args):
                                   "tflops": round(per_rank * N_SAMPLE * FLOP_FWD / mlp_infer_ms / 1e9, 1),
                                   "tensor_frac": round(per_rank * N_SAMPLE * FLOP_FWD / mlp_infer_ms / 1e9 / measured_peaks()["tflops"], 4),
                                   "samples_per_s": per_rank * N_SAMPLE / mlp_infer_ms * 1e3}},
+        "render_c1": render_c1,
         "render_c4": {"workload": f"800x800 frame x 192 samples, rays sharded over {world} GPU(s)", "ms_per_frame": c4_ms,
                       "rays_per_s": 800 * 800 / c4_ms * 1e3, "samples_per_s": 800 * 800 * 192 / c4_ms * 1e3},
         "e2e": {"value": n_rays * world * e2e_steps / e2e_ms * 1e3, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 9 * 4,
