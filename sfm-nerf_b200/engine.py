@@ -324,8 +324,10 @@ class Trainer:
     ``images_dev`` [n,H,W,3] fp32 and ``poses_dev`` [n,4,4] fp64 stay resident in HBM; rays are drawn
     on the GPU (counter-based RNG: (seed, step, rank) fully determine the batch), so a step moves no
     bytes across PCIe unless the caller asks for the loss.  With ``world > 1`` each rank renders
-    ``n_rays`` of the global batch and the flat fp32 gradient is sum-allreduced over NCCL before
-    Adam (scaled by 1/world) -- weights stay bit-identical on every rank.
+    ``n_rays`` of the global batch; the gradient sum over ranks is read through NVLink inside the Adam
+    kernel (parallel.GradExchange; NCCL allreduce as fallback) and scaled by 1/world -- weights stay
+    bit-identical on every rank.  ``step()`` is one ``nerf_train_step`` call, replayed as a CUDA graph
+    (``graph=False`` or ``NERF_TRAIN_GRAPH=0``: plain calls); ``step(timers=...)`` launches kernel by kernel.
     """
 
     def __init__(self, model, images_dev, poses_dev, camera_info, n_rays, n_sample, near=2.0, far=6.0, lr=5e-4,
