@@ -204,7 +204,7 @@ int nerf_train_batch(const double* poses, int n_images, double fx, double fy, do
       n_sample <= 0 || fx == 0.0 || fy == 0.0)
     return NERF_ERR_ARG;
   if (n_rays == 0) return NERF_OK;
-  const unsigned ray_blocks = blocks_for(n_rays, 256), z_blocks = blocks_for(n_rays * n_sample, 256);
+  const unsigned ray_blocks = blocks_for(n_rays, 256), z_blocks = blocks_for((n_rays * n_sample + 3) / 4, 256);
   train_batch_kernel<<<ray_blocks + z_blocks, 256, 0, (cudaStream_t)stream>>>(nullptr, 1, 0, nullptr, poses, fx, fy, cx, cy, width, height, n_images, images, seed,
                                                                              ray_offset, n_rays, rays_o, rays_d, target, n_sample, near,
                                                                              far, perturb, z_seed, z_offset, z, ray_blocks);
@@ -219,7 +219,7 @@ int nerf_unpack_batch(const float* batch9, int64_t n_rays, float* rays_o, float*
   if (rc != NERF_OK) return rc;
   if (!batch9 || !rays_o || !rays_d || !target || !z || n_rays < 0 || n_sample <= 0) return NERF_ERR_ARG;
   if (n_rays == 0) return NERF_OK;
-  const unsigned ray_blocks = blocks_for(n_rays, 256), z_blocks = blocks_for(n_rays * n_sample, 256);
+  const unsigned ray_blocks = blocks_for(n_rays, 256), z_blocks = blocks_for((n_rays * n_sample + 3) / 4, 256);
   train_batch_kernel<<<ray_blocks + z_blocks, 256, 0, (cudaStream_t)stream>>>(nullptr, 1, 0, batch9, nullptr, 1.0, 1.0, 0.0, 0.0, 1, 1, 1, nullptr, 0, 0, n_rays,
                                                                              rays_o, rays_d, target, n_sample, near, far, perturb, z_seed,
                                                                              z_offset, z, ray_blocks);
@@ -236,7 +236,7 @@ int nerf_sample_z(int64_t n_rays, int n_sample, float near, float far, int pertu
   if (!z || n_rays < 0 || n_sample <= 0) return NERF_ERR_ARG;
   const int64_t total = n_rays * n_sample;
   if (total == 0) return NERF_OK;
-  sample_z_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(total, n_sample, near, far, perturb,
+  sample_z_kernel<<<blocks_for((total + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(total, n_sample, near, far, perturb,
                                                                            t_rand, seed, offset, z);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
@@ -536,7 +536,7 @@ int nerf_train_step(const NerfTrainStep* c, int phases, void* stream) {
     return NERF_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t rows = c->n_rays * c->n_sample;
-  const unsigned ray_blocks = blocks_for(c->n_rays, 256), z_blocks = blocks_for(rows, 256);
+  const unsigned ray_blocks = blocks_for(c->n_rays, 256), z_blocks = blocks_for((rows + 3) / 4, 256);
   if (phases & NERF_STEP_FORWARD) {
   train_batch_kernel<<<ray_blocks + z_blocks, 256, 0, s>>>(c->step_state, (unsigned)c->world, (unsigned)c->rank, c->batch9, c->poses, c->fx,
                                                           c->fy, c->cx, c->cy, c->width, c->height, c->n_images, c->images, c->seed, 0,

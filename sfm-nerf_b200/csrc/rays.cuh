@@ -83,27 +83,43 @@ __device__ __forceinline__ float stratified_t(int s, int S, float u) {
   return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u));
 }
 
+// Four consecutive depths per thread: one Philox call yields the four uniforms of elements 4k .. 4k+3 (the mapping the
+// one-element form used: u(i) = word i & 3 of philox(seed, offset + (i >> 2))), one 16-byte store.  Same roundings as before.
+__device__ __forceinline__ void sample_z_quad(int64_t q, int64_t total, int S, float near, float far, int perturb,
+                                              const float* __restrict__ t_rand, uint64_t seed, uint64_t offset,
+                                              float* __restrict__ z) {
+  const int64_t i0 = 4 * q;
+  if (i0 >= total) return;
+  uint32_t r[4] = {0u, 0u, 0u, 0u};
+  if (perturb && t_rand == nullptr) philox4x32_10(seed, offset + (uint64_t)q, r);
+  const int s0 = (int)(i0 % S);
+  const float range = __fsub_rn(far, near);
+  float v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int s = (s0 + k) % S;
+    float t;
+    if (!perturb) {
+      t = linspace01(s, S);
+    } else {
+      const float u = (t_rand != nullptr) ? ((i0 + k < total) ? t_rand[i0 + k] : 0.0f) : u32_to_unit_float(r[k]);
+      t = stratified_t(s, S, u);
+    }
+    v[k] = __fadd_rn(near, __fmul_rn(range, t));   // train.py:217
+  }
+  if (i0 + 3 < total && (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
+    reinterpret_cast<float4*>(z)[q] = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (i0 + k < total) z[i0 + k] = v[k];
+  }
+}
+
 __global__ void sample_z_kernel(int64_t total, int S, float near, float far, int perturb,
                                 const float* __restrict__ t_rand, uint64_t seed, uint64_t offset,
                                 float* __restrict__ z) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int s = (int)(i % S);
-  float t;
-  if (!perturb) {
-    t = linspace01(s, S);
-  } else {
-    float u;
-    if (t_rand != nullptr) {
-      u = t_rand[i];
-    } else {
-      uint32_t r[4];
-      philox4x32_10(seed, offset + (uint64_t)(i >> 2), r);
-      u = u32_to_unit_float(r[i & 3]);
-    }
-    t = stratified_t(s, S, u);
-  }
-  z[i] = __fadd_rn(near, __fmul_rn(__fsub_rn(far, near), t));   // train.py:217
+  sample_z_quad((int64_t)blockIdx.x * blockDim.x + threadIdx.x, total, S, near, far, perturb, t_rand, seed, offset, z);
 }
 
 // generateBatch (train.py:104-127) + the depths of render (train.py:205-217) for one train step in ONE launch: the first
@@ -144,18 +160,8 @@ __global__ void train_batch_kernel(const unsigned long long* __restrict__ iter_p
 #pragma unroll
     for (int c = 0; c < 3; ++c) { rays_o[3 * i + c] = o[c]; rays_d[3 * i + c] = d[c]; target[3 * i + c] = __ldg(p + c); }
   } else {
-    const int64_t i = (int64_t)(blockIdx.x - ray_blocks) * blockDim.x + threadIdx.x;
-    if (i >= n_rays * S) return;
-    const int s = (int)(i % S);
-    float t;
-    if (!perturb) {
-      t = linspace01(s, S);
-    } else {
-      uint32_t r[4];
-      philox4x32_10(z_seed, z_offset + (uint64_t)(i >> 2), r);
-      t = stratified_t(s, S, u32_to_unit_float(r[i & 3]));
-    }
-    z[i] = __fadd_rn(near, __fmul_rn(__fsub_rn(far, near), t));
+    sample_z_quad((int64_t)(blockIdx.x - ray_blocks) * blockDim.x + threadIdx.x, n_rays * S, S, near, far, perturb, nullptr, z_seed,
+                  z_offset, z);
   }
 }
 

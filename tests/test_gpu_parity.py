@@ -119,6 +119,20 @@ def test_sample_z(pkg, orc, golden):
     assert torch.equal(a, b)
     assert bool((a[:, 1:] >= a[:, :-1]).all()) and float(a.min()) >= 2.0 and float(a.max()) <= 6.0
     assert not torch.equal(a[0], a[1])
+    # the kernel writes four depths per thread: ragged totals (33 * 7 = 231 = 4 * 57 + 3), rows that wrap inside a quad, an
+    # output pointer that is not 16-byte aligned, and the element -> random-word mapping (prefix property of the counter RNG)
+    E = pkg.engine
+    tr = torch.rand(33, 7)
+    np.testing.assert_allclose(E.sample_z(33, 7, 2.0, 6.0, "cuda", perturb=True, t_rand=tr.cuda()).cpu().numpy(),
+                               orc.sample_z(33, 7, 2.0, 6.0, tr).numpy(), rtol=0, atol=5e-7)
+    big = E.sample_z(40, 7, 2.0, 6.0, "cuda", perturb=True, seed=11, offset=100)
+    small = E.sample_z(33, 7, 2.0, 6.0, "cuda", perturb=True, seed=11, offset=100)
+    assert torch.equal(small.reshape(-1), big.reshape(-1)[:231])
+    buf = torch.zeros(231 + 1, device="cuda")
+    E.call("nerf_sample_z", 33, 7, 2.0, 6.0, 1, None, 11, 100, E.ptr(buf[1:]), E.stream_ptr())
+    assert torch.equal(buf[1:], small.reshape(-1)) and float(buf[0]) == 0.0
+    one = E.sample_z(5, 1, 2.0, 6.0, "cuda", perturb=True, seed=1)           # S == 1: t = 0 whatever the jitter
+    assert torch.equal(one, torch.full((5, 1), 2.0, device="cuda"))
 
 
 def test_encoding_matches_reference(pkg, golden):
