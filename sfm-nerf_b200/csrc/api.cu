@@ -420,8 +420,17 @@ int nerf_composite_forward(const float* sigma_rgb, const float* z, int64_t n_ray
   if (!sigma_rgb || !z || !rgb || n_rays < 0 || n_sample <= 0) return NERF_ERR_ARG;
   if (!nerf_aligned(sigma_rgb, 16)) return NERF_ERR_ALIGN;
   if (n_rays == 0) return NERF_OK;
-  composite_forward_kernel<<<blocks_for(n_rays, kCompWarpsPerBlock), kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(sigma_rgb), z, n_rays, n_sample, rgb, depth, acc);
+  const unsigned cf_blocks = blocks_for(n_rays, kCompWarpsPerBlock);
+  const float4* sr4 = reinterpret_cast<const float4*>(sigma_rgb);
+  cudaStream_t cs = (cudaStream_t)stream;
+  switch ((n_sample & 31) == 0 ? n_sample >> 5 : 0) {            // full-chunk ray lengths get the straight-line kernels
+    case 1: composite_forward_exact_kernel<1><<<cf_blocks, kCompWarpsPerBlock * 32, 0, cs>>>(sr4, z, n_rays, rgb, depth, acc); break;
+    case 2: composite_forward_exact_kernel<2><<<cf_blocks, kCompWarpsPerBlock * 32, 0, cs>>>(sr4, z, n_rays, rgb, depth, acc); break;
+    case 4: composite_forward_exact_kernel<4><<<cf_blocks, kCompWarpsPerBlock * 32, 0, cs>>>(sr4, z, n_rays, rgb, depth, acc); break;
+    case 6: composite_forward_exact_kernel<6><<<cf_blocks, kCompWarpsPerBlock * 32, 0, cs>>>(sr4, z, n_rays, rgb, depth, acc); break;
+    case 8: composite_forward_exact_kernel<8><<<cf_blocks, kCompWarpsPerBlock * 32, 0, cs>>>(sr4, z, n_rays, rgb, depth, acc); break;
+    default: composite_forward_kernel<<<cf_blocks, kCompWarpsPerBlock * 32, 0, cs>>>(sr4, z, n_rays, n_sample, rgb, depth, acc);
+  }
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
@@ -463,7 +472,13 @@ int nerf_composite_backward(const float* sigma_rgb, const float* z, const float*
     return NERF_ERR_ARG;
   if (!nerf_aligned(sigma_rgb, 16) || !nerf_aligned(d_sigma_rgb, 16)) return NERF_ERR_ALIGN;
   if (n_rays == 0) return NERF_OK;
-  composite_backward_kernel<<<blocks_for(n_rays, kCompWarpsPerBlock), kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+  // instances unrolled for 2 / 4 / 8 chunks of 32 samples: a 64-sample ray does not pay the registers of a 256-sample one
+  const unsigned cb_blocks = blocks_for(n_rays, kCompWarpsPerBlock);
+  if (n_sample <= 64) composite_backward_kernel<2><<<cb_blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(sigma_rgb), z, g_rgb, n_rays, n_sample, reinterpret_cast<float4*>(d_sigma_rgb));
+  else if (n_sample <= 128) composite_backward_kernel<4><<<cb_blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(sigma_rgb), z, g_rgb, n_rays, n_sample, reinterpret_cast<float4*>(d_sigma_rgb));
+  else composite_backward_kernel<8><<<cb_blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(sigma_rgb), z, g_rgb, n_rays, n_sample, reinterpret_cast<float4*>(d_sigma_rgb));
   NERF_LAUNCH_CHECK();
   return NERF_OK;
@@ -486,7 +501,13 @@ int nerf_composite_train(const float* sigma_rgb, const float* z, const float* ta
   const unsigned blocks = blocks_for(n_rays, kCompWarpsPerBlock);
   float* partial = static_cast<float*>(workspace);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + blocks);      /* zero before first use; the kernel re-zeroes it */
-  composite_train_kernel<<<blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+  if (n_sample <= 64) composite_train_kernel<2><<<blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(sigma_rgb), z, target, n_rays, n_sample, grad_scale, loss, partial, ticket,
+      reinterpret_cast<float4*>(d_sigma_rgb));
+  else if (n_sample <= 128) composite_train_kernel<4><<<blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(sigma_rgb), z, target, n_rays, n_sample, grad_scale, loss, partial, ticket,
+      reinterpret_cast<float4*>(d_sigma_rgb));
+  else composite_train_kernel<8><<<blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(sigma_rgb), z, target, n_rays, n_sample, grad_scale, loss, partial, ticket,
       reinterpret_cast<float4*>(d_sigma_rgb));
   NERF_LAUNCH_CHECK();

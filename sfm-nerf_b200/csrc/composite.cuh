@@ -31,15 +31,46 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// alpha_i = 1 - exp(-sigma_i * delta_i); delta_{S-1} = 1e-3 (train.py:248-254)
-__device__ __forceinline__ void sample_alpha(const float* __restrict__ zr, int s, int S, float sigma,
-                                             float& delta, float& alpha) {
+// Sums of four per-lane values over the warp with 6 shuffles instead of 20: after the xor-16 / xor-8 steps every lane keeps
+// one of the four partial sums; lanes 0-7 end with the total of a, 8-15 of b, 16-23 of c, 24-31 of d.
+__device__ __forceinline__ float warp_sum4_scatter(float a, float b, float c, float d, int lane) {
+  const bool up16 = (lane & 16) != 0;
+  float k0 = up16 ? c : a, k1 = up16 ? d : b;
+  k0 += __shfl_xor_sync(0xffffffffu, up16 ? a : c, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, up16 ? b : d, 16);
+  const bool up8 = (lane & 8) != 0;
+  float k = up8 ? k1 : k0;
+  k += __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
+}
+
+// alpha_i = 1 - exp(-sigma_i * delta_i); delta_{S-1} = 1e-3 (train.py:248-254).  z / z_next are the depths of samples s, s+1.
+__device__ __forceinline__ void sample_alpha(float z, float z_next, int s, int S, float sigma, float& delta, float& alpha) {
   // last delta = 1e-3 (train.py:250); with S == 1 the reference's `dists` is EMPTY (its ones_like of an
   // empty slice) and every output is 0 -- reproduced by a zero delta.
-  delta = (s < S - 1) ? __fsub_rn(zr[s + 1], zr[s]) : (S == 1 ? 0.0f : 1e-3f);
+  delta = (s < S - 1) ? __fsub_rn(z_next, z) : (S == 1 ? 0.0f : 1e-3f);
   alpha = __fsub_rn(1.0f, expf(-__fmul_rn(sigma, delta)));
 }
 
+// One 32-sample chunk of a ray as its warp holds it: lane l = sample c*32 + l (zeros past the end of the ray).  All chunks
+// of a ray (or of a 128-sample group) are loaded before any of them is used, so every warp keeps several 512-byte rows in
+// flight instead of one load -> scan -> load chain.
+struct CompChunk { float4 v; float z, zn; };
+__device__ __forceinline__ CompChunk load_chunk(const float4* __restrict__ sr, const float* __restrict__ zr, int s, int S) {
+  CompChunk c;
+  c.v = make_float4(0.f, 0.f, 0.f, 0.f); c.z = 0.f; c.zn = 0.f;
+  if (s < S) {
+    c.v = __ldg(sr + s);
+    c.z = __ldg(zr + s);
+    if (s < S - 1) c.zn = __ldg(zr + s + 1);
+  }
+  return c;
+}
+
+// Forward, any S: one warp per ray, groups of four chunks with the loads first.
 __global__ void __launch_bounds__(kCompWarpsPerBlock * 32)
 composite_forward_kernel(const float4* __restrict__ sigma_rgb, const float* __restrict__ z,
                          int64_t n_rays, int S, float* __restrict__ rgb, float* __restrict__ depth,
@@ -50,35 +81,134 @@ composite_forward_kernel(const float4* __restrict__ sigma_rgb, const float* __re
   const float4* sr = sigma_rgb + ray * S;
   const float* zr = z + ray * S;
   float carry = 1.0f, ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
-  for (int base = 0; base < S; base += 32) {
-    const int s = base + lane;
-    float om = 1.0f, alpha = 0.0f, zz = 0.0f;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (s < S) {
-      v = __ldg(sr + s);
-      zz = zr[s];
-      float delta;
-      sample_alpha(zr, s, S, v.x, delta, alpha);
-      om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);          // train.py:262
+  for (int base = 0; base < S; base += 128) {
+    CompChunk ck[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ck[k] = load_chunk(sr, zr, base + 32 * k + lane, S);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (base + 32 * k < S) {                                   // warp-uniform
+        const int s = base + 32 * k + lane;
+        float om = 1.0f, alpha = 0.0f;
+        if (s < S) {
+          float delta;
+          sample_alpha(ck[k].z, ck[k].zn, s, S, ck[k].v.x, delta, alpha);
+          om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);        // train.py:262
+        }
+        const float incl = warp_incl_prod(om, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float T = carry * excl;                             // exclusive cumprod (261-263)
+        const float w = alpha * T;                                // train.py:266
+        ar += w * ck[k].v.y; ag += w * ck[k].v.z; ab += w * ck[k].v.w; ad += w * ck[k].z; aa += w;
+        carry *= __shfl_sync(0xffffffffu, incl, 31);
+      }
     }
+  }
+  const float r = warp_sum4_scatter(ar, ag, ab, ad, lane);
+  aa = warp_sum(aa);
+  if ((lane & 7) == 0) {
+    if (lane < 24) rgb[3 * ray + (lane >> 3)] = r;               // train.py:269
+    else if (depth) depth[ray] = r;
+    if (lane == 0 && acc) acc[ray] = aa;
+  }
+}
+
+// Forward for S == 32 * NC (64, 128, 192, 256 samples per ray: every chunk is full).  ncu showed the generic kernels
+// ISSUE-bound, not memory-bound: 282 warp instructions per 64-sample ray of which ~165 were index arithmetic, bounds predicates
+// and branches (smsp issue active 62-80 % at 3.4 TB/s).  With the ray length a compile-time constant the loads are NC
+// unguarded 16-byte + 2 NC 4-byte loads from one base pointer and the loop body is straight-line code.
+template <int NC>
+__global__ void __launch_bounds__(kCompWarpsPerBlock * 32)
+composite_forward_exact_kernel(const float4* __restrict__ sigma_rgb, const float* __restrict__ z, int64_t n_rays,
+                               float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ acc) {
+  constexpr int S = 32 * NC;
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kCompWarpsPerBlock + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const float4* sr = sigma_rgb + ray * S + lane;
+  const float* zr = z + ray * S + lane;
+  float4 v[NC];
+  float zz[NC], zn[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) { v[k] = __ldg(sr + 32 * k); zz[k] = __ldg(zr + 32 * k); }
+#pragma unroll
+  for (int k = 0; k < NC - 1; ++k) zn[k] = __ldg(zr + 32 * k + 1);
+  zn[NC - 1] = __ldg(zr + 32 * (NC - 1) + (lane < 31 ? 1 : 0));   // the last sample has no successor: its delta is 1e-3
+  float carry = 1.0f, ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    float delta = __fsub_rn(zn[k], zz[k]);
+    if (k == NC - 1 && lane == 31) delta = 1e-3f;                 // train.py:250
+    const float alpha = __fsub_rn(1.0f, expf(-__fmul_rn(v[k].x, delta)));
+    const float om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);   // train.py:262
     const float incl = warp_incl_prod(om, lane);
     float excl = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) excl = 1.0f;
-    const float T = carry * excl;                               // exclusive cumprod (261-263)
-    const float w = alpha * T;                                  // train.py:266
-    ar += w * v.y; ag += w * v.z; ab += w * v.w; ad += w * zz; aa += w;
-    carry *= __shfl_sync(0xffffffffu, incl, 31);
+    const float w = alpha * (carry * excl);                       // train.py:261-266
+    ar += w * v[k].y; ag += w * v[k].z; ab += w * v[k].w; ad += w * zz[k]; aa += w;
+    if (k < NC - 1) carry *= __shfl_sync(0xffffffffu, incl, 31);
   }
-  ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad); aa = warp_sum(aa);
-  if (lane == 0) {
-    rgb[3 * ray + 0] = ar; rgb[3 * ray + 1] = ag; rgb[3 * ray + 2] = ab;   // train.py:269
-    if (depth) depth[ray] = ad;
-    if (acc) acc[ray] = aa;
+  const float r = warp_sum4_scatter(ar, ag, ab, ad, lane);
+  aa = warp_sum(aa);
+  if ((lane & 7) == 0) {
+    if (lane < 24) rgb[3 * ray + (lane >> 3)] = r;               // train.py:269
+    else if (depth) depth[ray] = r;
+    if (lane == 0 && acc) acc[ray] = aa;
   }
 }
 
 // Backward: with gc_i = g . c_i and suffix_i = sum_{j>i} w_j gc_j
 //   dL/dc_i = w_i g;  dL/dalpha_i = T_i gc_i - suffix_i / om_i;  dL/dsigma_i = delta_i (1-alpha_i) dL/dalpha_i
+// NC = chunks per ray this instance is unrolled for (S <= 32 * NC).
+struct CompState { float T, w, f, om; };
+template <int NC>
+__device__ __forceinline__ void composite_ray_forward(const CompChunk (&ck)[NC], int n_chunks, int lane, int S, CompState (&st)[NC],
+                                                      float& ar, float& ag, float& ab) {
+  float carry = 1.0f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c < n_chunks) {
+      const int s = c * 32 + lane;
+      float om = 1.0f, alpha = 0.0f, delta = 0.0f;
+      if (s < S) {
+        sample_alpha(ck[c].z, ck[c].zn, s, S, ck[c].v.x, delta, alpha);
+        om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+      }
+      const float incl = warp_incl_prod(om, lane);
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      st[c].T = carry * excl;
+      st[c].w = alpha * st[c].T;
+      st[c].f = delta * (1.0f - alpha);
+      st[c].om = om;
+      ar += st[c].w * ck[c].v.y; ag += st[c].w * ck[c].v.z; ab += st[c].w * ck[c].v.w;
+      carry *= __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+}
+template <int NC>
+__device__ __forceinline__ void composite_ray_backward(const CompChunk (&ck)[NC], const CompState (&st)[NC], int n_chunks, int lane, int S,
+                                                       float g0, float g1, float g2, float4* __restrict__ out) {
+  float tail = 0.0f;                                            // reverse pass: suffix sums of w*gc
+#pragma unroll
+  for (int c = NC - 1; c >= 0; --c) {
+    if (c < n_chunks) {
+      const int s = c * 32 + lane;
+      const float gc = g0 * ck[c].v.y + g1 * ck[c].v.z + g2 * ck[c].v.w;     // 0 past the end of the ray
+      const float incl = warp_incl_sum(st[c].w * gc, lane);
+      const float total = __shfl_sync(0xffffffffu, incl, 31);
+      const float suffix = tail + (total - incl);               // sum over j > i
+      if (s < S) {
+        const float dalpha = st[c].T * gc - suffix / st[c].om;
+        out[s] = make_float4(st[c].f * dalpha, st[c].w * g0, st[c].w * g1, st[c].w * g2);
+      }
+      tail += total;
+    }
+  }
+}
+
+template <int NC>
 __global__ void __launch_bounds__(kCompWarpsPerBlock * 32)
 composite_backward_kernel(const float4* __restrict__ sigma_rgb, const float* __restrict__ z,
                           const float* __restrict__ g_rgb, int64_t n_rays, int S,
@@ -88,55 +218,22 @@ composite_backward_kernel(const float4* __restrict__ sigma_rgb, const float* __r
   if (ray >= n_rays) return;
   const float4* sr = sigma_rgb + ray * S;
   const float* zr = z + ray * S;
-  const float g0 = g_rgb[3 * ray + 0], g1 = g_rgb[3 * ray + 1], g2 = g_rgb[3 * ray + 2];
-  float Tk[kCompMaxChunks], wk[kCompMaxChunks], gck[kCompMaxChunks], fk[kCompMaxChunks], omk[kCompMaxChunks];
-  float carry = 1.0f;
   const int n_chunks = (S + 31) >> 5;
+  CompChunk ck[NC];
 #pragma unroll
-  for (int c = 0; c < kCompMaxChunks; ++c) {
-    if (c < n_chunks) {
-      const int s = c * 32 + lane;
-      float om = 1.0f, alpha = 0.0f, delta = 0.0f, gc = 0.0f;
-      if (s < S) {
-        const float4 v = __ldg(sr + s);
-        sample_alpha(zr, s, S, v.x, delta, alpha);
-        om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
-        gc = g0 * v.y + g1 * v.z + g2 * v.w;
-      }
-      const float incl = warp_incl_prod(om, lane);
-      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-      if (lane == 0) excl = 1.0f;
-      Tk[c] = carry * excl;
-      wk[c] = alpha * Tk[c];
-      gck[c] = gc;
-      fk[c] = delta * (1.0f - alpha);
-      omk[c] = om;
-      carry *= __shfl_sync(0xffffffffu, incl, 31);
-    }
-  }
-  // reverse pass: suffix sums of w*gc
-  float tail = 0.0f;
-#pragma unroll
-  for (int c = kCompMaxChunks - 1; c >= 0; --c) {
-    if (c < n_chunks) {
-      const int s = c * 32 + lane;
-      const float wgc = wk[c] * gck[c];
-      const float incl = warp_incl_sum(wgc, lane);
-      const float total = __shfl_sync(0xffffffffu, incl, 31);
-      const float suffix = tail + (total - incl);               // sum over j > i
-      if (s < S) {
-        const float dalpha = Tk[c] * gck[c] - suffix / omk[c];
-        d_sigma_rgb[ray * S + s] = make_float4(fk[c] * dalpha, wk[c] * g0, wk[c] * g1, wk[c] * g2);
-      }
-      tail += total;
-    }
-  }
+  for (int c = 0; c < NC; ++c) ck[c] = load_chunk(sr, zr, c * 32 + lane, S);
+  const float g0 = g_rgb[3 * ray + 0], g1 = g_rgb[3 * ray + 1], g2 = g_rgb[3 * ray + 2];
+  CompState st[NC];
+  float ar = 0.f, ag = 0.f, ab = 0.f;
+  composite_ray_forward<NC>(ck, n_chunks, lane, S, st, ar, ag, ab);
+  composite_ray_backward<NC>(ck, st, n_chunks, lane, S, g0, g1, g2, d_sigma_rgb + ray * S);
 }
 
 // Training form: compositing forward + MSE (train.py:460) + its gradient + compositing backward in ONE launch.  One warp
-// per ray runs the forward pass, forms g = dL/d rgb of its ray, then the backward pass (the second read of the ray's
-// samples hits L1/L2).  The loss is reduced deterministically: per-block partial sums go to `partial`, the last block to
+// per ray loads the ray once, runs the forward pass, forms g = dL/d rgb of its ray, then the backward pass from the same
+// registers.  The loss is reduced deterministically: per-block partial sums go to `partial`, the last block to
 // finish (ticket counter behind `partial`) adds them in index order and resets the counter.
+template <int NC>
 __global__ void __launch_bounds__(kCompWarpsPerBlock * 32)
 composite_train_kernel(const float4* __restrict__ sigma_rgb, const float* __restrict__ z, const float* __restrict__ target,
                        int64_t n_rays, int S, float grad_scale, float* __restrict__ loss, float* __restrict__ partial,
@@ -150,53 +247,19 @@ composite_train_kernel(const float4* __restrict__ sigma_rgb, const float* __rest
   if (ray < n_rays) {
     const float4* sr = sigma_rgb + ray * S;
     const float* zr = z + ray * S;
-    float Tk[kCompMaxChunks], wk[kCompMaxChunks], fk[kCompMaxChunks], omk[kCompMaxChunks];
-    float carry = 1.0f, ar = 0.f, ag = 0.f, ab = 0.f;
+    CompChunk ck[NC];
 #pragma unroll
-    for (int c = 0; c < kCompMaxChunks; ++c) {
-      if (c < n_chunks) {
-        const int s = c * 32 + lane;
-        float om = 1.0f, alpha = 0.0f, delta = 0.0f;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s < S) {
-          v = __ldg(sr + s);
-          sample_alpha(zr, s, S, v.x, delta, alpha);
-          om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
-        }
-        const float incl = warp_incl_prod(om, lane);
-        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) excl = 1.0f;
-        Tk[c] = carry * excl;
-        wk[c] = alpha * Tk[c];
-        fk[c] = delta * (1.0f - alpha);
-        omk[c] = om;
-        ar += wk[c] * v.y; ag += wk[c] * v.z; ab += wk[c] * v.w;
-        carry *= __shfl_sync(0xffffffffu, incl, 31);
-      }
-    }
-    ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab);
-    const float d0 = ar - target[3 * ray + 0], d1 = ag - target[3 * ray + 1], d2 = ab - target[3 * ray + 2];
+    for (int c = 0; c < NC; ++c) ck[c] = load_chunk(sr, zr, c * 32 + lane, S);
+    const float t0 = target[3 * ray + 0], t1 = target[3 * ray + 1], t2 = target[3 * ray + 2];
+    CompState st[NC];
+    float ar = 0.f, ag = 0.f, ab = 0.f;
+    composite_ray_forward<NC>(ck, n_chunks, lane, S, st, ar, ag, ab);
+    const float r = warp_sum4_scatter(ar, ag, ab, 0.0f, lane);
+    ar = __shfl_sync(0xffffffffu, r, 0); ag = __shfl_sync(0xffffffffu, r, 8); ab = __shfl_sync(0xffffffffu, r, 16);
+    const float d0 = ar - t0, d1 = ag - t1, d2 = ab - t2;
     sq = d0 * d0 + d1 * d1 + d2 * d2;
     const float gs = grad_scale * 2.0f / (float)(3 * n_rays);
-    const float g0 = gs * d0, g1 = gs * d1, g2 = gs * d2;
-    float tail = 0.0f;
-#pragma unroll
-    for (int c = kCompMaxChunks - 1; c >= 0; --c) {
-      if (c < n_chunks) {
-        const int s = c * 32 + lane;
-        float gc = 0.0f;
-        if (s < S) { const float4 v = __ldg(sr + s); gc = g0 * v.y + g1 * v.z + g2 * v.w; }
-        const float wgc = wk[c] * gc;
-        const float incl = warp_incl_sum(wgc, lane);
-        const float total = __shfl_sync(0xffffffffu, incl, 31);
-        const float suffix = tail + (total - incl);
-        if (s < S) {
-          const float dalpha = Tk[c] * gc - suffix / omk[c];
-          d_sigma_rgb[ray * S + s] = make_float4(fk[c] * dalpha, wk[c] * g0, wk[c] * g1, wk[c] * g2);
-        }
-        tail += total;
-      }
-    }
+    composite_ray_backward<NC>(ck, st, n_chunks, lane, S, gs * d0, gs * d1, gs * d2, d_sigma_rgb + ray * S);
   }
   if (lane == 0) red[wib] = sq;
   __syncthreads();
