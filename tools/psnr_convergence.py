@@ -37,15 +37,16 @@ for it in range(steps):
     k, x, y = rng.integers(0, n_train, n_rays), rng.integers(0, W, n_rays), rng.integers(0, W, n_rays)
     rays = orc.rays_from_indices(images, poses, cam, k, x, y)
     o, d, t = (torch.tensor(rays[:, i:i + 3]) for i in (0, 3, 6))
-    tr.step(rays=(o.cuda(), d.cuda(), t.cuda()))
+    tr.step(rays=torch.tensor(np.asarray(rays, dtype=np.float32)).cuda())   # [N,9] array: nerf_train_step, CUDA-graph replay
     loss, grads = orc.loss_and_grads(sd, o, d, t, S)
     sd = opt.step(sd, grads)
-    tr2.step(rays=(o.cuda(), d.cuda(), t.cuda()))
+    tr2.step(rays=(o.cuda(), d.cuda(), t.cuda()))                            # three tensors: the per-kernel sequence
     for j in range(n_pert):
         loss2, grads2 = orc.loss_and_grads(sds[j], o, d, t, S)
         sds[j] = opts[j].step(sds[j], grads2)
     if it % 250 == 0:
         print(it, "loss cuda", float(tr.loss.item()), "oracle", float(loss), "oracle'", float(loss2), f"{time.time()-t0:.0f}s", flush=True)
+print("first CUDA trainer: cuda graphs", len(tr._graphs), tr.graph_error, "| second: per-kernel path, graphs", len(tr2._graphs), flush=True)
 tr.close(); tr2.close()
 args = argparse.Namespace(n_sample=S, perturb=False, chunk_size=32768, n_rays_batch=W * W, near=2.0, far=6.0)
 psnr = lambda mse: -10 * np.log10(mse)
