@@ -111,6 +111,13 @@ int launch_forward(const void* packed, int layout, const float* pos, const float
   return NERF_OK;
 }
 
+void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
+                 float bc2_sqrt, float grad_scale, AdamSchedule sched, cudaStream_t s) {
+  const bool vec = (n & 3) == 0 && nerf_aligned(p, 16) && nerf_aligned(g, 16) && nerf_aligned(m, 16) && nerf_aligned(v, 16);
+  if (vec) adam_kernel<4><<<blocks_for(n / 4, 256), 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale, sched);
+  else adam_kernel<1><<<blocks_for(n, 256), 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale, sched);
+}
+
 }  // namespace
 
 extern "C" {
@@ -535,8 +542,8 @@ int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
   if (n == 0) return NERF_OK;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  adam_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                                    eps, (float)bc1, (float)sqrt(bc2), grad_scale, AdamSchedule{});
+  launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale, AdamSchedule{},
+              (cudaStream_t)stream);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
@@ -589,8 +596,8 @@ int nerf_train_step(const NerfTrainStep* c, int phases, void* stream) {
                                                                         c->exp_avg_sq, m->n_params / 4, 0.f, c->beta1, c->beta2, c->eps,
                                                                         1.f, 1.f, c->grad_scale, sched);
   } else {
-    adam_kernel<<<blocks_for(m->n_params, 256), 256, 0, s>>>(c->params, c->grads, c->exp_avg, c->exp_avg_sq, m->n_params, 0.f, c->beta1,
-                                                             c->beta2, c->eps, 1.f, 1.f, c->grad_scale, sched);
+    launch_adam(c->params, c->grads, c->exp_avg, c->exp_avg_sq, m->n_params, 0.f, c->beta1, c->beta2, c->eps, 1.f, 1.f, c->grad_scale,
+                sched, s);
   }
   NERF_LAUNCH_CHECK();
   return launch_pack(c->params, c->layout, c->packed, c->step_state, stream);

@@ -321,19 +321,39 @@ __device__ __forceinline__ void adam_device_schedule(const AdamSchedule& sched, 
   lr = sh[0]; bc1 = sh[1]; bc2_sqrt = sh[2];
 }
 
-// torch.optim.Adam (train.py:401) over the flat parameter vector.
+// torch.optim.Adam (train.py:401) over the flat parameter vector, four elements per thread (16-byte loads / stores; the
+// flat vectors are 16-byte aligned and both parameter counts are multiples of 4 -- the API falls back to VEC = 1 otherwise).
+template <int VEC>
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                             float bc1, float bc2_sqrt, float grad_scale, AdamSchedule sched) {
   adam_device_schedule(sched, b1, b2, lr, bc1, bc2_sqrt);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float gi = g[i] * grad_scale;
-  const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
-  const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
-  m[i] = mi; v[i] = vi;
-  const float denom = sqrtf(vi) / bc2_sqrt + eps;
-  p[i] = p[i] - (lr / bc1) * (mi / denom);
+  if (i * VEC >= n) return;
+  float pi[VEC], gi[VEC], mi[VEC], vi[VEC];
+  if (VEC == 4) {
+    *reinterpret_cast<float4*>(pi) = reinterpret_cast<const float4*>(p)[i];
+    *reinterpret_cast<float4*>(gi) = reinterpret_cast<const float4*>(g)[i];
+    *reinterpret_cast<float4*>(mi) = reinterpret_cast<const float4*>(m)[i];
+    *reinterpret_cast<float4*>(vi) = reinterpret_cast<const float4*>(v)[i];
+  } else {
+    pi[0] = p[i]; gi[0] = g[i]; mi[0] = m[i]; vi[0] = v[i];
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const float gk = gi[k] * grad_scale;
+    mi[k] = mi[k] + (gk - mi[k]) * (1.0f - b1);
+    vi[k] = vi[k] * b2 + (1.0f - b2) * gk * gk;
+    const float denom = sqrtf(vi[k]) / bc2_sqrt + eps;
+    pi[k] = pi[k] - (lr / bc1) * (mi[k] / denom);
+  }
+  if (VEC == 4) {
+    reinterpret_cast<float4*>(p)[i] = *reinterpret_cast<float4*>(pi);
+    reinterpret_cast<float4*>(m)[i] = *reinterpret_cast<float4*>(mi);
+    reinterpret_cast<float4*>(v)[i] = *reinterpret_cast<float4*>(vi);
+  } else {
+    p[i] = pi[0]; m[i] = mi[0]; v[i] = vi[0];
+  }
 }
 
 // Data-parallel Adam with the gradient exchange FUSED into the optimiser kernel: every rank's wgrad has written its local

@@ -374,6 +374,26 @@ def test_adam_step_matches_reference_golden(pkg, golden, sd_pe256):
         assert np.abs(upd).max() <= 5.0e-4 * 1.001
 
 
+def test_adam_vector_and_scalar_paths_agree(pkg):
+    """nerf_adam_step uses 16-byte accesses when the vectors allow it and a scalar kernel otherwise (length not a multiple
+    of 4, or unaligned views): both give the same bits."""
+    E = pkg.engine
+    torch.manual_seed(3)
+    n = 1024
+    base = [torch.randn(n + 1, device="cuda") for _ in range(2)] + [torch.rand(n + 1, device="cuda") * 1e-3 for _ in range(2)]
+    outs = []
+    for off, cnt in ((0, n), (1, n - 1), (0, n - 3)):          # aligned x4 -> vector kernel; offset view / odd length -> scalar kernel
+        p, g, m, v = (t.clone() for t in base)
+        E.call("nerf_adam_step", E.ptr(p[off:]), E.ptr(g[off:]), E.ptr(m[off:]), E.ptr(v[off:]), cnt, 5e-4, 0.9, 0.999, 1e-8, 3, 0.5,
+               E.stream_ptr())
+        outs.append((p, m, v))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a[1:n], b[1:n])
+    for a, b in zip(outs[0], outs[2]):
+        assert torch.equal(a[:n - 3], b[:n - 3])
+    assert torch.equal(outs[2][0][n - 3:], base[0][n - 3:])      # elements past the count are untouched
+
+
 def test_ragged_and_empty_inputs(pkg, model_pe):
     st = model_pe.kernel_state()
     empty = torch.empty((0, 3), device="cuda")
