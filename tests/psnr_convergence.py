@@ -2,7 +2,7 @@
 on IDENTICAL ray batches, initial weights and deterministic depths.  Training is chaotic, so a second fp32 oracle
 trajectory started from weights perturbed by 1e-7 (relative) measures how far two fp32 runs drift apart by themselves;
 PSNR is averaged over several training views and several held-out views.
-    python tools/psnr_convergence.py [steps=2000] [rays=512] [samples=48] [scene=textured|dense]"""
+    python tests/psnr_convergence.py [steps=2000] [rays=512] [samples=48] [scene=textured|dense]"""
 import os, sys, time, json, argparse, copy
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
