@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NERF_ABI_VERSION 1
+#define NERF_ABI_VERSION 2
 
 enum {
   NERF_OK = 0,
@@ -173,10 +173,13 @@ int nerf_mse_loss(const float* rgb, const float* target, int64_t n_rays, float g
 /* ---------------------------------------------------------------------------------------
  * Optimizer -- torch.optim.Adam defaults of train.py:401 over the flat vectors (one launch
  * instead of 26).  step is 1-based; grads are multiplied by grad_scale first (1/world for
- * data-parallel sums).
+ * data-parallel sums).  lr / beta1 / beta2 / eps are doubles like torch's Python scalars: the per-step
+ * scalars (1 - beta1, 1 - beta2, lr / (1 - beta1^t), sqrt(1 - beta2^t)) are formed in fp64 and rounded
+ * to fp32 once, exactly where torch.optim.Adam rounds them, and each element follows torch's
+ * operation order -- parameters and moments agree with torch.optim.Adam to <= 2e-7 over a run.
  * ------------------------------------------------------------------------------------- */
 int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                   int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
+                   int64_t n, double lr, double beta1, double beta2, double eps, int64_t step,
                    float grad_scale, void* stream);
 
 /* Data-parallel form of nerf_adam_step (train.py:401, 456-465 on N GPUs): the gradient exchange is fused into the optimiser
@@ -187,7 +190,7 @@ int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
  * grad_scale (= 1/n_ranks for the mean).  n must be a multiple of 4 and all pointers 16-byte aligned.  Every rank gets
  * bit-identical parameters. */
 int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, int n_ranks, const float* multicast_grads,
-                          float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                          float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2, double eps,
                           int64_t step, float grad_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -227,7 +230,8 @@ typedef struct NerfTrainStep {
   uint64_t seed, z_seed;
   double lr0, lr_decay;
   int64_t lr_decay_steps;
-  float beta1, beta2, eps, grad_scale;
+  double beta1, beta2, eps;
+  float grad_scale, pad_;
   const double* poses;
   const float* images;
   const float* batch9;

@@ -62,7 +62,7 @@ class NerfTrainStep(C.Structure):
     """Mirror of `struct NerfTrainStep` (include/nerf_b200.h); struct_bytes guards against drift."""
     _fields_ = [("struct_bytes", _L)] + [(n, C.c_int32) for n in ("layout", "n_sample", "perturb", "world", "rank", "n_images", "width", "height")] + \
         [("n_rays", _L), ("fx", _D), ("fy", _D), ("cx", _D), ("cy", _D), ("near", _F), ("far", _F), ("seed", _U), ("z_seed", _U),
-         ("lr0", _D), ("lr_decay", _D), ("lr_decay_steps", _L), ("beta1", _F), ("beta2", _F), ("eps", _F), ("grad_scale", _F)] + \
+         ("lr0", _D), ("lr_decay", _D), ("lr_decay_steps", _L), ("beta1", _D), ("beta2", _D), ("eps", _D), ("grad_scale", _F), ("pad_", _F)] + \
         [(n, _P) for n in ("poses", "images", "batch9", "rays_o", "rays_d", "target", "z", "sigma_rgb", "d_sigma_rgb", "loss",
                            "composite_ws", "stash", "dstash", "packed", "params", "grads", "exp_avg", "exp_avg_sq", "step_state")] + \
         [("peer_grads", _P * 8), ("multicast_grads", _P)]
@@ -94,11 +94,11 @@ PROTOTYPES = {
     "nerf_composite_forward": (_I, [_P, _P, _L, _I, _P, _P, _P, _P]),
     "nerf_composite_backward": (_I, [_P, _P, _P, _L, _I, _P, _P]),
     "nerf_debug_umma_rate": (_I, [_I, _I, _P]),
-    "nerf_adam_step_reduce": (_I, [_P, _P, _I, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
+    "nerf_adam_step_reduce": (_I, [_P, _P, _I, _P, _P, _P, _L, _D, _D, _D, _D, _L, _F, _P]),
     "nerf_composite_train_workspace_bytes": (_L, [_L]),
     "nerf_composite_train": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P, _P]),
     "nerf_mse_loss": (_I, [_P, _P, _L, _F, _P, _P, _P]),
-    "nerf_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
+    "nerf_adam_step": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _L, _F, _P]),
     "nerf_render_workspace_bytes": (_L, [_L, _I]),
     "nerf_render_image": (_I, [_P, _I, _P, _I, _D, _D, _D, _D, _I, _I, _L, _L, _I, _F, _F, _I, _U, _U, _P, _P, _P, _P, _P]),
     "nerf_train_step": (_I, [C.POINTER(NerfTrainStep), _I, _P]),

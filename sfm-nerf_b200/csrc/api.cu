@@ -111,11 +111,10 @@ int launch_forward(const void* packed, int layout, const float* pos, const float
   return NERF_OK;
 }
 
-void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
-                 float bc2_sqrt, float grad_scale, AdamSchedule sched, cudaStream_t s) {
+void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, AdamCoef c, float grad_scale, AdamSchedule sched, cudaStream_t s) {
   const bool vec = (n & 3) == 0 && nerf_aligned(p, 16) && nerf_aligned(g, 16) && nerf_aligned(m, 16) && nerf_aligned(v, 16);
-  if (vec) adam_kernel<4><<<blocks_for(n / 4, 256), 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale, sched);
-  else adam_kernel<1><<<blocks_for(n, 256), 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale, sched);
+  if (vec) adam_kernel<4><<<blocks_for(n / 4, 256), 256, 0, s>>>(p, g, m, v, n, c, grad_scale, sched);
+  else adam_kernel<1><<<blocks_for(n, 256), 256, 0, s>>>(p, g, m, v, n, c, grad_scale, sched);
 }
 
 }  // namespace
@@ -533,16 +532,14 @@ int nerf_mse_loss(const float* rgb, const float* target, int64_t n_rays, float g
 }
 
 // ------------------------------------------------------------------------------------ optimizer
-int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                   float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream) {
+int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                   double beta1, double beta2, double eps, int64_t step, float grad_scale, void* stream) {
   DeviceInfo* dev;
   int rc = device_info(&dev);
   if (rc != NERF_OK) return rc;
   if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return NERF_ERR_ARG;
   if (n == 0) return NERF_OK;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale, AdamSchedule{},
+  launch_adam(params, grads, exp_avg, exp_avg_sq, n, adam_coef(lr, beta1, beta2, eps, (double)step), grad_scale, AdamSchedule{},
               (cudaStream_t)stream);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
@@ -581,7 +578,7 @@ int nerf_train_step(const NerfTrainStep* c, int phases, void* stream) {
     if ((rc = nerf_mlp_wgrad(c->layout, c->stash, c->dstash, rows, c->grads, 0, stream))) return rc;
   }
   if (!(phases & NERF_STEP_UPDATE)) return NERF_OK;
-  const AdamSchedule sched{c->step_state, c->lr0, c->lr_decay, (long long)c->lr_decay_steps};
+  const AdamSchedule sched{c->step_state, c->lr0, c->lr_decay, c->beta1, c->beta2, c->eps, (long long)c->lr_decay_steps};
   if (c->world > 1 && (c->multicast_grads || c->peer_grads[0])) {
     // data parallel: the gradient sum over ranks is read through NVLink inside the optimiser kernel (nerf_adam_step_reduce)
     if (c->world > 8 || (m->n_params & 3) || !nerf_aligned(c->params, 16) || !nerf_aligned(c->exp_avg, 16) ||
@@ -593,18 +590,16 @@ int nerf_train_step(const NerfTrainStep* c, int phases, void* stream) {
       peers.ptr[r] = c->peer_grads[r];
     }
     adam_reduce_kernel<<<blocks_for(m->n_params / 4, 256), 256, 0, s>>>(c->params, peers, c->world, c->multicast_grads, c->exp_avg,
-                                                                        c->exp_avg_sq, m->n_params / 4, 0.f, c->beta1, c->beta2, c->eps,
-                                                                        1.f, 1.f, c->grad_scale, sched);
+                                                                        c->exp_avg_sq, m->n_params / 4, AdamCoef{}, c->grad_scale, sched);
   } else {
-    launch_adam(c->params, c->grads, c->exp_avg, c->exp_avg_sq, m->n_params, 0.f, c->beta1, c->beta2, c->eps, 1.f, 1.f, c->grad_scale,
-                sched, s);
+    launch_adam(c->params, c->grads, c->exp_avg, c->exp_avg_sq, m->n_params, AdamCoef{}, c->grad_scale, sched, s);
   }
   NERF_LAUNCH_CHECK();
   return launch_pack(c->params, c->layout, c->packed, c->step_state, stream);
 }
 
 int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, int n_ranks, const float* multicast_grads,
-                          float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
+                          float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2, double eps, int64_t step,
                           float grad_scale, void* stream) {
   DeviceInfo* dev;
   int rc = device_info(&dev);
@@ -620,10 +615,8 @@ int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, in
       (multicast_grads && !nerf_aligned(multicast_grads, 16)))
     return NERF_ERR_ALIGN;
   if (n == 0) return NERF_OK;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_reduce_kernel<<<blocks_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(params, peers, n_ranks, multicast_grads, exp_avg, exp_avg_sq,
-                                                                             n / 4, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2),
+                                                                             n / 4, adam_coef(lr, beta1, beta2, eps, (double)step),
                                                                              grad_scale, AdamSchedule{});
   NERF_LAUNCH_CHECK();
   return NERF_OK;

@@ -302,32 +302,51 @@ mse_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ target,
   }
 }
 
+// torch.optim.Adam's per-step scalars (torch/optim/adam.py, _single_tensor_adam): formed in fp64 and rounded to fp32 once,
+// exactly where torch rounds them -- lerp weight 1 - beta1, beta2 and 1 - beta2 of the second-moment update,
+// step_size = lr / (1 - beta1^t), sqrt(1 - beta2^t), eps.
+struct AdamCoef { float step_size, b2, w1, w2, eps, bc2_sqrt; };
+__host__ __device__ inline AdamCoef adam_coef(double lr, double beta1, double beta2, double eps, double step) {
+  AdamCoef c;
+  c.step_size = (float)(lr / (1.0 - pow(beta1, step)));
+  c.b2 = (float)beta2; c.w1 = (float)(1.0 - beta1); c.w2 = (float)(1.0 - beta2);
+  c.eps = (float)eps;
+  c.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, step));
+  return c;
+}
+
 // Device-side schedule of a graph-replayable step (nerf_train_step): iteration counter in device memory; the step size
 // follows StepLR (train.py:403-404, lr0 * gamma^(iteration / decay_steps)) and the bias corrections follow torch.optim.Adam,
 // evaluated in fp64 like the host path of nerf_adam_step and rounded to fp32 once.
-struct AdamSchedule { const unsigned long long* iter_ptr; double lr0, gamma; long long decay_steps; };
+struct AdamSchedule { const unsigned long long* iter_ptr; double lr0, gamma, beta1, beta2, eps; long long decay_steps; };
 
-__device__ __forceinline__ void adam_device_schedule(const AdamSchedule& sched, float b1, float b2, float& lr, float& bc1, float& bc2_sqrt) {
+__device__ __forceinline__ void adam_device_schedule(const AdamSchedule& sched, AdamCoef& c) {
   if (sched.iter_ptr == nullptr) return;                 // block-uniform
-  __shared__ float sh[3];
+  __shared__ AdamCoef sh;
   if (threadIdx.x == 0) {
     const unsigned long long it = *sched.iter_ptr;
-    const double step = (double)(it + 1ull);
-    sh[0] = (float)(sched.lr0 * pow(sched.gamma, (double)(it / (unsigned long long)sched.decay_steps)));
-    sh[1] = (float)(1.0 - pow((double)b1, step));
-    sh[2] = (float)sqrt(1.0 - pow((double)b2, step));
+    const double lr = sched.lr0 * pow(sched.gamma, (double)(it / (unsigned long long)sched.decay_steps));
+    sh = adam_coef(lr, sched.beta1, sched.beta2, sched.eps, (double)(it + 1ull));
   }
   __syncthreads();
-  lr = sh[0]; bc1 = sh[1]; bc2_sqrt = sh[2];
+  c = sh;
 }
 
-// torch.optim.Adam (train.py:401) over the flat parameter vector, four elements per thread (16-byte loads / stores; the
+// one element of torch.optim.Adam (train.py:401), in torch's operation order:
+//   m = lerp(m, g, 1 - b1);  v = v * b2 + (1 - b2) * (g * g);  p += (-step_size * m) / (sqrt(v) / sqrt(bc2) + eps)
+__device__ __forceinline__ void adam_element(float& p, float g, float& m, float& v, const AdamCoef& c) {
+  m = m + c.w1 * (g - m);
+  v = __fmaf_rn(c.w2, __fmul_rn(g, g), __fmul_rn(v, c.b2));
+  const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), c.bc2_sqrt), c.eps);
+  p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-c.step_size, m), denom));
+}
+
+// torch.optim.Adam over the flat parameter vector, four elements per thread (16-byte loads / stores; the
 // flat vectors are 16-byte aligned and both parameter counts are multiples of 4 -- the API falls back to VEC = 1 otherwise).
 template <int VEC>
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                            float bc1, float bc2_sqrt, float grad_scale, AdamSchedule sched) {
-  adam_device_schedule(sched, b1, b2, lr, bc1, bc2_sqrt);
+                            float* __restrict__ v, int64_t n, AdamCoef c, float grad_scale, AdamSchedule sched) {
+  adam_device_schedule(sched, c);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i * VEC >= n) return;
   float pi[VEC], gi[VEC], mi[VEC], vi[VEC];
@@ -340,13 +359,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     pi[0] = p[i]; gi[0] = g[i]; mi[0] = m[i]; vi[0] = v[i];
   }
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    const float gk = gi[k] * grad_scale;
-    mi[k] = mi[k] + (gk - mi[k]) * (1.0f - b1);
-    vi[k] = vi[k] * b2 + (1.0f - b2) * gk * gk;
-    const float denom = sqrtf(vi[k]) / bc2_sqrt + eps;
-    pi[k] = pi[k] - (lr / bc1) * (mi[k] / denom);
-  }
+  for (int k = 0; k < VEC; ++k) adam_element(pi[k], gi[k] * grad_scale, mi[k], vi[k], c);
   if (VEC == 4) {
     reinterpret_cast<float4*>(p)[i] = *reinterpret_cast<float4*>(pi);
     reinterpret_cast<float4*>(m)[i] = *reinterpret_cast<float4*>(mi);
@@ -364,9 +377,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // operation on the same operands in the same order), so the replicated weights stay bit-identical.  4 elements per thread.
 struct PeerGrads { const float* ptr[8]; };
 __global__ void adam_reduce_kernel(float* __restrict__ p, PeerGrads peers, int n_ranks, const float* mc_grads, float* __restrict__ m,
-                                   float* __restrict__ v, int64_t n4, float lr, float b1, float b2, float eps, float bc1,
-                                   float bc2_sqrt, float grad_scale, AdamSchedule sched) {
-  adam_device_schedule(sched, b1, b2, lr, bc1, bc2_sqrt);
+                                   float* __restrict__ v, int64_t n4, AdamCoef c, float grad_scale, AdamSchedule sched) {
+  adam_device_schedule(sched, c);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 g;
@@ -384,11 +396,7 @@ __global__ void adam_reduce_kernel(float* __restrict__ p, PeerGrads peers, int n
   const float gg[4] = {g.x * grad_scale, g.y * grad_scale, g.z * grad_scale, g.w * grad_scale};
   float* pp = &pi.x; float* mm = &mi.x; float* vv = &vi.x;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    mm[k] = mm[k] + (gg[k] - mm[k]) * (1.0f - b1);
-    vv[k] = vv[k] * b2 + (1.0f - b2) * gg[k] * gg[k];
-    pp[k] = pp[k] - (lr / bc1) * (mm[k] / (sqrtf(vv[k]) / bc2_sqrt + eps));
-  }
+  for (int k = 0; k < 4; ++k) adam_element(pp[k], gg[k], mm[k], vv[k], c);
   reinterpret_cast<float4*>(p)[i] = pi; reinterpret_cast<float4*>(m)[i] = mi; reinterpret_cast<float4*>(v)[i] = vi;
 }
 

@@ -371,6 +371,14 @@ class Trainer:
     def lr(self):
         return self.lr0 * self.lr_decay ** (self.iteration // self.lr_decay_steps)
 
+    def _check_batch(self, n_rays):
+        """The activation / gradient stashes were sized for ``self.n_rays`` rays in __init__: a larger batch would run the MLP
+        kernels past their end."""
+        if n_rays > self.n_rays:
+            raise _lib.NerfB200Error(f"batch of {n_rays} rays exceeds the {self.n_rays} rays this Trainer was built for")
+        if n_rays <= 0:
+            raise _lib.NerfB200Error("empty ray batch")
+
     def close(self):
         self.st.frozen = False
 
@@ -500,6 +508,7 @@ class Trainer:
         if rays is None or (torch.is_tensor(rays) and rays.dim() == 2 and rays.shape[1] == 9):
             # one launch: draw + ray generation + target gather (or the split of a generateBatch() [N,9] array) + depths
             n_rays = self.n_rays if rays is None else int(rays.shape[0])
+            self._check_batch(n_rays)
             odt = torch.empty((3, n_rays, 3), dtype=torch.float32, device=dev)
             o, d, tgt = odt[0], odt[1], odt[2]
             z = torch.empty((n_rays, S), dtype=torch.float32, device=dev)
@@ -515,8 +524,12 @@ class Trainer:
                      1 if self.perturb else 0, z_seed, z_off, ptr(z), stream_ptr())
             launches += 1
         else:
-            o, d, tgt = rays
+            o, d, tgt = (_f32c(t) for t in rays)
+            _need_cuda(o, d, tgt)
             n_rays = o.shape[0]
+            if d.shape != o.shape or tgt.shape != o.shape or o.dim() != 2 or o.shape[1] != 3:
+                raise _lib.NerfB200Error("rays must be three [n,3] tensors (origins, directions, target colours)")
+            self._check_batch(n_rays)
             z = sample_z(n_rays, S, self.near, self.far, dev, perturb=self.perturb, seed=z_seed, offset=ctr * ((n_rays * S + 3) // 4))
             launches += 1
         with _timed(timers, "mlp_fwd"):

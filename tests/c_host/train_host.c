@@ -63,7 +63,7 @@ int main(int argc, char** argv) {
   c.near = 2.0f; c.far = 6.0f;
   c.seed = (uint64_t)seed; c.z_seed = (uint64_t)seed ^ 0x5bd1e995ull;
   c.lr0 = 5e-4; c.lr_decay = 0.1; c.lr_decay_steps = 50000;                   /* train.py:401-404 */
-  c.beta1 = 0.9f; c.beta2 = 0.999f; c.eps = 1e-8f; c.grad_scale = 1.0f;
+  c.beta1 = 0.9; c.beta2 = 0.999; c.eps = 1e-8; c.grad_scale = 1.0f;
   c.poses = poses; c.images = images; c.batch9 = NULL;
   c.rays_o = (float*)dmalloc((size_t)n_rays * 12, 0); c.rays_d = (float*)dmalloc((size_t)n_rays * 12, 0);
   c.target = (float*)dmalloc((size_t)n_rays * 12, 0); c.z = (float*)dmalloc((size_t)rows * 4, 0);

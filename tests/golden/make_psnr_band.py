@@ -1,0 +1,122 @@
+"""PSNR-after-2k-steps band of the UNMODIFIED reference (north_star: "PSNR after 2k training steps on a synthetic scene is
+within 0.2 dB").  Run in the build container (the reference does not travel to the GPU box):
+
+    python tests/golden/make_psnr_band.py scene                 # writes psnr_scene.npz (uint8 views of the synthetic scene)
+    python tests/golden/make_psnr_band.py run SEED [SEED ...]   # one fp32 CPU trajectory per seed -> psnr_runs/seed_<s>.json
+    python tests/golden/make_psnr_band.py merge                 # -> psnr_band.json (per-seed PSNRs, mean, std)
+
+Each trajectory is the reference's own loop body (train.py:447-465): `generateBatch` (Python `random`, seeded per
+trajectory) -> `render` (deterministic depths) -> `nn.MSELoss` -> `backward` -> `torch.optim.Adam.step` -> `StepLR.step`,
+on `NeRFmodel()` initialised under `torch.manual_seed(seed)`; PSNR comes from the reference's `test_image` on 4 training
+and 4 held-out views.  tests/test_gpu_parity.py::test_psnr_after_2k_steps_matches_reference_band trains the CUDA path
+from the same initial weights on the same batches and compares the mean PSNR over the seeds.
+"""
+import argparse
+import json
+import os
+import random
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+# the configuration both sides run (the GPU test reads it from psnr_band.json)
+CFG = {"steps": 2000, "n_rays_batch": 256, "n_sample": 32, "width": 48, "n_train": 12, "n_test": 4, "near": 2.0, "far": 6.0,
+       "lrate": 5e-4, "lrate_decay_steps": 500, "lrate_decay": 0.5, "batch_seed_base": 1000,
+       "eval_train_views": [0, 3, 6, 9], "scene": "textured_field, uint8-quantised views"}
+
+
+def make_scene():
+    import sfmnerf_b200 as s                                   # data generation only (analytic scene -> images), CPU torch
+    W = CFG["width"]
+    cam = s.synthetic.make_camera_info(W, W)
+    poses = s.synthetic.sphere_poses(CFG["n_train"] + CFG["n_test"], seed=0)
+    images = s.synthetic.render_lego_images(poses, cam, n_sample=128, device="cpu", field=s.synthetic.textured_field).numpy()
+    u8 = np.clip(np.rint(images * 255.0), 0, 255).astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "psnr_scene.npz"), images_u8=u8, poses=poses, K=cam["camera_matrix"])
+    print("scene written:", u8.shape, "mean", u8.mean())
+
+
+def load_scene():
+    z = np.load(os.path.join(HERE, "psnr_scene.npz"))
+    images = z["images_u8"].astype(np.float64) / 255.0           # what loadDataset returns (train.py:44-46)
+    W = images.shape[2]
+    return images, z["poses"], {"width": W, "height": images.shape[1], "camera_matrix": z["K"]}
+
+
+def run_seed(seed, steps=None, threads=1):
+    from make_golden import import_reference
+    ref = import_reference()
+    torch.set_num_threads(threads)
+    images, poses, cam = load_scene()
+    nt = CFG["n_train"]
+    steps = steps or CFG["steps"]
+    args = argparse.Namespace(n_sample=CFG["n_sample"], perturb=False, chunk_size=32768, n_rays_batch=CFG["n_rays_batch"],
+                              near=CFG["near"], far=CFG["far"])
+    torch.manual_seed(seed)
+    model = ref.NeRFmodel()
+    optimizer = torch.optim.Adam(model.parameters(), lr=CFG["lrate"])                                  # train.py:401
+    scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=CFG["lrate_decay_steps"], gamma=CFG["lrate_decay"])  # :404
+    random.seed(CFG["batch_seed_base"] + seed)
+    t0 = time.time()
+    losses = []
+    for it in range(steps):
+        rays_batch = torch.tensor(ref.generateBatch(images[:nt], poses[:nt], cam, args))             # train.py:447-448
+        optimizer.zero_grad()
+        rendered = ref.render(model, rays_batch[:, :3], rays_batch[:, 3:6], args, near=args.near, far=args.far)
+        loss = torch.nn.MSELoss()(rendered, rays_batch[:, 6:9])
+        loss.backward()
+        optimizer.step()
+        scheduler.step()
+        losses.append(loss.item())
+        if it % 250 == 0:
+            print(f"seed {seed} it {it} loss {losses[-1]:.5f} {time.time() - t0:.0f}s", flush=True)
+    args_eval = argparse.Namespace(n_sample=CFG["n_sample"], perturb=False, chunk_size=32768, n_rays_batch=CFG["width"] ** 2,
+                                   near=CFG["near"], far=CFG["far"])
+    psnr = lambda mse: float(-10.0 * np.log10(mse))
+    tv = CFG["eval_train_views"]
+    hv = list(range(nt, nt + CFG["n_test"]))
+    mse_t = [ref.test_image(model, images[i], poses[i], cam, args_eval)[1] for i in tv]
+    mse_h = [ref.test_image(model, images[i], poses[i], cam, args_eval)[1] for i in hv]
+    out = {"seed": seed, "steps": steps, "psnr_train_views": psnr(np.mean(mse_t)), "psnr_held_out_views": psnr(np.mean(mse_h)),
+           "loss_first": losses[0], "loss_last100_mean": float(np.mean(losses[-100:])), "seconds": time.time() - t0}
+    os.makedirs(os.path.join(HERE, "psnr_runs"), exist_ok=True)
+    with open(os.path.join(HERE, "psnr_runs", f"seed_{seed}.json"), "w") as f:
+        json.dump(out, f)
+    print(json.dumps(out), flush=True)
+
+
+def merge():
+    runs = []
+    d = os.path.join(HERE, "psnr_runs")
+    for name in sorted(os.listdir(d), key=lambda n: int(n.split("_")[1].split(".")[0])):
+        r = json.load(open(os.path.join(d, name)))
+        if r["steps"] == CFG["steps"]:
+            runs.append(r)
+    band = {"config": CFG, "source": "unmodified reference (Phase2/train.py generateBatch/render/test_image + torch.optim.Adam + StepLR), "
+            "fp32 CPU, torch %s" % torch.__version__, "seeds": [r["seed"] for r in runs]}
+    for key in ("psnr_train_views", "psnr_held_out_views"):
+        v = np.array([r[key] for r in runs])
+        band[key] = {"per_seed": v.tolist(), "mean": float(v.mean()), "std": float(v.std(ddof=1)) if len(v) > 1 else None}
+    band["loss_first"] = [r["loss_first"] for r in runs]
+    with open(os.path.join(HERE, "psnr_band.json"), "w") as f:
+        json.dump(band, f, indent=1)
+    print(json.dumps({k: band[k] for k in ("seeds", "psnr_train_views", "psnr_held_out_views")}, indent=1))
+
+
+if __name__ == "__main__":
+    cmd = sys.argv[1]
+    if cmd == "scene":
+        make_scene()
+    elif cmd == "run":
+        steps = int(os.environ.get("PSNR_STEPS", 0)) or None
+        for s in sys.argv[2:]:
+            run_seed(int(s), steps, int(os.environ.get("PSNR_THREADS", 1)))
+    elif cmd == "merge":
+        merge()

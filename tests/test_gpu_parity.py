@@ -268,32 +268,56 @@ def test_render_matches_reference_golden(pkg, orc, model_pe, sd_pe256, golden):
     assert float(np.abs(rgb_j.cpu().numpy() - g["rgb_jit"]).max()) < RGB_TOL
 
 
-def test_gradients_match_reference_golden(pkg, model_pe, golden):
-    """Per-layer gradients against the reference's autograd (golden): norm within 2 %, direction
-    (cosine on the recorded samples) > 0.99.  Element-wise rel-L2 of a bf16-operand evaluation against
-    the fp32 reference is 1-6 % in the early layers whatever the implementation (ReLU masks of
-    near-zero pre-activations flip; DESIGN.md "Numerics"), so the element-wise check is made against
-    the bf16-operand restatement in test_gradients_full_tensors_vs_oracle."""
-    g = golden("render_pe256")
-    o, d, target = (torch.tensor(g[k]).cuda() for k in ("o", "d", "target"))
+# Per-tensor rel-L2 bounds against the reference's fp32 gradients (tests/golden/grads_*.npz).  What limits them is stated in
+# DESIGN.md "Numerics" and measured by tests/grad_error_study.py: rounding ONLY the weights to bf16 (activations fp32) already
+# gives 5 % on fc1.weight, whose high-frequency encoding columns are random-walk sums over samples (no averaging of the
+# per-sample error); every coherent sum (biases, 256-wide layers) averages its error down with the batch size.
+GRAD_REL_L2_BOUNDS = {
+    # 48-ray batch of render_pe256.npz (3,072 rows: the hardest case, least averaging)
+    "grads_pe256": {"fc1.weight": 0.105, "fc1.bias": 0.040, "fc_layers.0.weight": 0.048, "fc_layers.0.bias": 0.030,
+                    "fc_layers.1.weight": 0.030, "fc_layers.1.bias": 0.022, "skip_layer.weight": 0.048},
+    # 1024 rays from four poses (65,536 rows, a quarter of the C2 batch)
+    "grads_pe256_b1024": {"fc1.weight": 0.070, "skip_layer.weight": 0.028},
+}
+
+
+@pytest.mark.parametrize("name", ["grads_pe256", "grads_pe256_b1024"])
+def test_gradients_match_reference_golden(pkg, model_pe, golden, name):
+    """All 26 gradient tensors against the reference's fp32 autograd (full tensors recorded from the unmodified reference):
+      * per-layer gradient NORM within 2 % (north_star "per-layer gradients match within 2 % relative error", reading 1),
+      * rel-L2 of the whole 661,636-element gradient within 2 % (reading 2),
+      * per-tensor element-wise rel-L2 within 2 % for every tensor except the few listed in GRAD_REL_L2_BOUNDS, which are
+        asserted at the bound a bf16-operand evaluation achieves (reading 3; see the comment above the table)."""
+    import json, os
+    g = golden(name)
+    r = golden("render_pe256") if name == "grads_pe256" else g
+    o, d, target = (torch.tensor(r[k]).cuda() for k in ("o", "d", "target"))
     args = _ns(n_sample=64, perturb=False, chunk_size=32768)
     model_pe.zero_grad()
     loss = pkg.loss(pkg.render(model_pe, o, d, args), target)
     assert abs(loss.item() - float(g["loss"])) < 1e-3
     loss.backward()
-    for name, p in model_pe.named_parameters():
-        key = name.replace(".", "__")
-        gn = float(g[key + "__gnorm"])
-        assert p.grad is not None and p.grad.shape == p.shape
-        mine = p.grad.flatten()[:: max(1, p.numel() // 64)][:64].cpu().numpy()
-        ref = g[key + "__g"]
-        rel_norm = abs(float(p.grad.norm()) - gn) / (gn + 1e-30)
-        denom = np.linalg.norm(ref) * np.linalg.norm(mine)
-        cos = float(np.dot(mine, ref) / denom) if denom > 0 else 1.0
-        print(f"{name:28s} |g| ref {gn:.3e} rel-norm-err {rel_norm:.2e} sample cosine {cos:.5f}")
-        assert rel_norm < GRAD_REL_TOL, (name, rel_norm)
-        assert cos > 0.99, (name, cos)
+    report, num, den = {}, 0.0, 0.0
+    for pname, p in model_pe.named_parameters():
+        ref = torch.tensor(g[pname.replace(".", "__")])
+        mine = p.grad.detach().cpu()
+        assert mine.shape == ref.shape
+        rel_l2 = float((mine - ref).norm() / ref.norm())
+        rel_norm = abs(float(mine.norm() - ref.norm())) / float(ref.norm())
+        cos = float((mine * ref).sum() / (mine.norm() * ref.norm()))
+        report[pname] = {"rel_l2": rel_l2, "rel_norm": rel_norm, "cosine": cos, "bound": GRAD_REL_L2_BOUNDS[name].get(pname, GRAD_REL_TOL)}
+        num += float((mine - ref).norm() ** 2); den += float(ref.norm() ** 2)
+        print(f"{pname:24s} rel-L2 {rel_l2:.3e} (bound {report[pname]['bound']:.3f})  norm err {rel_norm:.2e}  cosine {cos:.6f}")
+    whole = (num / den) ** 0.5
+    print(f"whole gradient rel-L2 {whole:.3e}")
+    if os.path.isdir("gpurun_out"):
+        with open(os.path.join("gpurun_out", f"gradient_parity_{name}.json"), "w") as f:
+            json.dump({"batch": name, "loss": loss.item(), "loss_ref": float(g["loss"]), "whole_gradient_rel_l2": whole, "tensors": report}, f, indent=1)
     model_pe.zero_grad()
+    for pname, rpt in report.items():
+        assert rpt["rel_norm"] < GRAD_REL_TOL, (pname, rpt)
+        assert rpt["rel_l2"] < rpt["bound"], (pname, rpt)
+    assert whole < GRAD_REL_TOL
 
 
 def test_gradients_full_tensors_vs_oracle(pkg, orc, model_pe, sd_pe256):
@@ -356,8 +380,63 @@ def test_same_seed_same_init_as_reference(pkg, sd_pe256):
     assert list(m.state_dict().keys()) == list(sd_pe256.keys())
 
 
+def test_adam_matches_torch_optim_across_steplr_boundary(pkg, sd_pe256):
+    """nerf_adam_step (host-side scalars) and the UPDATE phase of nerf_train_step (device-side iteration counter, StepLR and
+    bias corrections) against torch.optim.Adam + StepLR (train.py:401-404, 464-465) on IDENTICAL gradients: 8 steps across
+    two decay boundaries (step_size 3, gamma 0.1), parameters and both moment vectors within 2e-7."""
+    import ctypes
+    E = pkg.engine
+    steps, step_size, gamma, lr0 = 8, 3, 0.1, 5e-4
+    gen = torch.Generator().manual_seed(12)
+    m = pkg.NeRFmodel().cuda()
+    m.load_state_dict(sd_pe256)
+    names = [k for k, _ in m.named_parameters()]
+    # gradients with a wide dynamic range (1e-9 .. 1e-1): exercises eps in the denominator
+    grads = [{k: torch.randn(sd_pe256[k].shape, generator=gen) * 10.0 ** float(torch.randint(-9, 0, (1,), generator=gen)) for k in names}
+             for _ in range(steps)]
+    # reference: torch.optim.Adam + StepLR on CPU fp32, single-tensor implementation
+    ref_p = [torch.nn.Parameter(sd_pe256[k].clone()) for k in names]
+    opt = torch.optim.Adam(ref_p, lr=lr0, foreach=False)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=step_size, gamma=gamma)
+    for i in range(steps):
+        for p, k in zip(ref_p, names):
+            p.grad = grads[i][k].clone()
+        opt.step(); sched.step()
+    ref_flat = torch.cat([p.detach().flatten() for p in ref_p])
+    ref_m = torch.cat([opt.state[p]["exp_avg"].flatten() for p in ref_p])
+    ref_v = torch.cat([opt.state[p]["exp_avg_sq"].flatten() for p in ref_p])
+    flat_grads = [torch.cat([g[k].flatten() for k in names]).cuda() for g in grads]
+
+    # (a) nerf_adam_step, scalars from the host
+    st = m.kernel_state()
+    n = st.n_params
+    p = st.flat.detach().clone(); ea = torch.zeros(n, device="cuda"); eq = torch.zeros(n, device="cuda")
+    for i in range(steps):
+        E.call("nerf_adam_step", E.ptr(p), E.ptr(flat_grads[i]), E.ptr(ea), E.ptr(eq), n, lr0 * gamma ** (i // step_size), 0.9, 0.999, 1e-8,
+               i + 1, 1.0, E.stream_ptr())
+    for mine, ref, what in ((p, ref_flat, "params"), (ea, ref_m, "exp_avg"), (eq, ref_v, "exp_avg_sq")):
+        err = float((mine.cpu() - ref).abs().max())
+        print(f"nerf_adam_step        {what:10s} max |diff| vs torch.optim.Adam {err:.2e}")
+        assert err <= 2e-7, (what, err)
+
+    # (b) the UPDATE phase of nerf_train_step: iteration counter, StepLR step size and bias corrections on the device
+    cam = {"width": 8, "height": 8, "camera_matrix": np.eye(3)}
+    tr = E.Trainer(m, None, None, cam, 128, 32, perturb=False, lr=lr0, lr_decay_steps=step_size, lr_decay=gamma)
+    cfg = tr._train_step_cfg(True, 0)
+    for i in range(steps):
+        tr.grads.copy_(flat_grads[i])
+        E.call("nerf_train_step", ctypes.byref(cfg), 4, E.stream_ptr())
+    assert int(tr.step_state.item()) == steps
+    for mine, ref, what in ((tr.st.flat, ref_flat, "params"), (tr.exp_avg, ref_m, "exp_avg"), (tr.exp_avg_sq, ref_v, "exp_avg_sq")):
+        err = float((mine.detach().cpu() - ref).abs().max())
+        print(f"nerf_train_step UPDATE {what:10s} max |diff| vs torch.optim.Adam {err:.2e}")
+        assert err <= 2e-7, (what, err)
+    tr.close()
+
+
 def test_adam_step_matches_reference_golden(pkg, golden, sd_pe256):
-    """One fused train step (render + MSE + backward + Adam) against the reference's torch.optim.Adam."""
+    """One fused train step (render + MSE + backward + Adam) against the weights the reference's torch.optim.Adam step
+    produced (recorded samples): the update direction of every well-conditioned entry and the step size."""
     g = golden("render_pe256")
     m = pkg.NeRFmodel().cuda()
     m.load_state_dict(sd_pe256)
@@ -815,3 +894,65 @@ def test_train_and_test_drivers_end_to_end(pkg, tmp_path):
     res = pkg.test(ims, ps, ci, args3)
     assert len(res) == 5 and all(np.isfinite(r[1]) for r in res)
     assert (tmp_path / "img" / "test_0.png").exists()
+
+
+def test_psnr_after_2k_steps_matches_reference_band(pkg):
+    """north_star: "PSNR after 2k training steps on a synthetic scene is within 0.2 dB".  tests/golden/psnr_band.json holds
+    the PSNRs the UNMODIFIED reference reaches (its own generateBatch / render / MSELoss / Adam / StepLR loop, fp32 CPU, one
+    trajectory per seed; tests/golden/make_psnr_band.py).  Here the CUDA path trains from the SAME initial weights
+    (torch.manual_seed(seed)) on the SAME batches (Python `random` seeded like the reference run, drawn in generateBatch's
+    order) for the same 2,000 steps -- graph-replayed nerf_train_step, StepLR on the device -- and is evaluated with
+    test_image on the same views.  Training is chaotic (two fp32 runs differ by several tenths of a dB), so the criterion is
+    on the MEAN over all seeds: |mean PSNR (CUDA) - mean PSNR (reference)| <= 0.2 dB, for training and held-out views."""
+    import json, os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    band = json.load(open(os.path.join(gdir, "psnr_band.json")))
+    cfg = band["config"]
+    z = np.load(os.path.join(gdir, "psnr_scene.npz"))
+    images = z["images_u8"].astype(np.float64) / 255.0
+    poses_np = z["poses"]
+    W, nt, S, n_rays, steps = cfg["width"], cfg["n_train"], cfg["n_sample"], cfg["n_rays_batch"], cfg["steps"]
+    cam = {"width": W, "height": W, "camera_matrix": z["K"]}
+    E = pkg.engine
+    poses_dev = E.poses_to_device(poses_np[:nt], "cuda")
+    images_dev = torch.tensor(images[:nt], dtype=torch.float32).cuda()
+    args_eval = _ns(n_sample=S, perturb=False, chunk_size=32768, n_rays_batch=W * W, near=cfg["near"], far=cfg["far"])
+    psnr = lambda mse: float(-10.0 * np.log10(mse))
+    out = {"train": [], "held_out": []}
+    for seed in band["seeds"]:
+        torch.manual_seed(seed)
+        m = pkg.NeRFmodel().cuda()
+        random.seed(cfg["batch_seed_base"] + seed)
+        idx = np.empty((steps * n_rays, 3), dtype=np.int32)
+        for i in range(steps * n_rays):                     # generateBatch's draw order (train.py:120-121): image, x, y per ray
+            idx[i, 0] = random.randint(0, nt - 1); idx[i, 1] = random.randint(0, W - 1); idx[i, 2] = random.randint(0, W - 1)
+        idx_dev = torch.from_numpy(idx).cuda()
+        o, d, t = E.raygen_batch(poses_dev, cam, idx_dev[:, 0].contiguous(), idx_dev[:, 1].contiguous(), idx_dev[:, 2].contiguous(), images_dev)
+        batches = torch.cat([o, d, t], 1).reshape(steps, n_rays, 9)
+        tr = E.Trainer(m, None, None, cam, n_rays, S, near=cfg["near"], far=cfg["far"], perturb=False, lr=cfg["lrate"],
+                       lr_decay_steps=cfg["lrate_decay_steps"], lr_decay=cfg["lrate_decay"])
+        first = None
+        for it in range(steps):
+            loss = tr.step(rays=batches[it])
+            if it == 0:
+                first = float(loss.item())
+        assert tr.graph_error == "" and len(tr._graphs) == 1, tr.graph_error       # the graph-replayed whole-step path ran
+        tr.close()
+        ref_first = band["loss_first"][band["seeds"].index(seed)]
+        assert abs(first - ref_first) < 2e-3, (seed, first, ref_first)                # same init, same first batch
+        mse_t = [pkg.test_image(m, images[i], poses_np[i], cam, args_eval)[1] for i in cfg["eval_train_views"]]
+        mse_h = [pkg.test_image(m, images[i], poses_np[i], cam, args_eval)[1] for i in range(nt, nt + cfg["n_test"])]
+        out["train"].append(psnr(np.mean(mse_t))); out["held_out"].append(psnr(np.mean(mse_h)))
+    report = {"config": cfg, "seeds": band["seeds"]}
+    for key, bkey in (("train", "psnr_train_views"), ("held_out", "psnr_held_out_views")):
+        mine, ref = np.array(out[key]), np.array(band[bkey]["per_seed"])
+        report[key] = {"cuda_per_seed": mine.tolist(), "reference_per_seed": ref.tolist(), "cuda_mean": float(mine.mean()),
+                       "reference_mean": float(ref.mean()), "delta_db": float(mine.mean() - ref.mean()),
+                       "cuda_std": float(mine.std(ddof=1)), "reference_std": float(ref.std(ddof=1))}
+        print(f"PSNR {key:9s}: CUDA {mine.mean():.3f} +- {mine.std(ddof=1):.3f} dB, reference {ref.mean():.3f} +- {ref.std(ddof=1):.3f} dB "
+              f"({len(mine)} seeds), delta {mine.mean() - ref.mean():+.3f} dB")
+    if os.path.isdir("gpurun_out"):
+        with open(os.path.join("gpurun_out", "psnr_gate.json"), "w") as f:
+            json.dump(report, f, indent=1)
+    for key in ("train", "held_out"):
+        assert abs(report[key]["delta_db"]) <= 0.2, report[key]

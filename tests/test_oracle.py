@@ -96,6 +96,20 @@ def test_gradients_and_adam_match_reference(golden, sd_pe256):
         np.testing.assert_allclose(samp, g[k.replace(".", "__") + "__w1"], rtol=0, atol=2e-7)
 
 
+@pytest.mark.parametrize("name", ["grads_pe256", "grads_pe256_b1024"])
+def test_full_gradient_tensors_match_reference(golden, sd_pe256, name):
+    """All 26 gradient tensors of the reference train step (tests/golden/make_golden_grads.py), element-wise."""
+    g = golden(name)
+    r = golden("render_pe256") if name == "grads_pe256" else g
+    loss, grads = orc.loss_and_grads(sd_pe256, torch.tensor(r["o"]), torch.tensor(r["d"]), torch.tensor(r["target"]), 64)
+    assert abs(loss.item() - float(g["loss"])) < 1e-7
+    for k, gr in grads.items():
+        ref = torch.tensor(g[k.replace(".", "__")])
+        assert gr.shape == ref.shape
+        rel = float((gr - ref).norm() / ref.norm())
+        assert rel < 1e-4, (k, rel)                 # two fp32 CPU evaluations: summation order only
+
+
 def test_nope_variant_matches_reference(golden):
     g = golden("render_nope256")
     r = golden("render_pe256")
