@@ -28,7 +28,7 @@ sys.path.insert(0, HERE)
 
 # the configuration both sides run (the GPU test reads it from psnr_band.json)
 CFG = {"steps": 2000, "n_rays_batch": 256, "n_sample": 32, "width": 48, "n_train": 12, "n_test": 4, "near": 2.0, "far": 6.0,
-       "lrate": 5e-4, "lrate_decay_steps": 500, "lrate_decay": 0.5, "batch_seed_base": 1000,
+       "lrate": 5e-4, "lrate_decay_steps": 1500, "lrate_decay": 0.1, "batch_seed_base": 1000,
        "eval_train_views": [0, 3, 6, 9], "scene": "textured_field, uint8-quantised views"}
 
 

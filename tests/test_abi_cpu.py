@@ -143,3 +143,21 @@ def test_reference_python_surface_names_and_signatures():
     assert inspect.signature(pkg.Wrapper.render).parameters["near"].default == 1.0       # Wrapper.py:129
     assert inspect.signature(importlib.import_module("sfm-nerf_b200.train").render).parameters["far"].default == 6.0   # train.py:187
     assert pkg.Wrapper.configParser().parse_args([]).max_iters == 100001
+
+
+def test_vendored_reference_is_unmodified():
+    """oracle/_ref (git-ignored, built by oracle/make_ref.py / build()) holds byte-identical copies of the reference sources the
+    CPU arm of bench.py times; when the live reference is present the copies are compared with it."""
+    import hashlib, json
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not vendored (run python oracle/make_ref.py in the build container)")
+    man = json.load(open(os.path.join(ROOT, "oracle", "_ref", "MANIFEST.json")))
+    for rel, digest in man["sha256"].items():
+        data = open(os.path.join(ROOT, "oracle", "_ref", rel), "rb").read()
+        assert hashlib.sha256(data).hexdigest() == digest, rel
+        live = os.path.join("/root/reference", rel)
+        if os.path.exists(live):
+            assert open(live, "rb").read() == data, rel
+    ref = ref_loader.import_reference()
+    assert callable(ref.render) and callable(ref.generateBatch) and callable(ref.test_image)
