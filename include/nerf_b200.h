@@ -12,7 +12,9 @@
  *     (sizes of opaque buffers come from the *_bytes() queries);
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden syncs;
  *   - return value: 0 = success, <0 = NERF_ERR_* argument/state error, >0 = cudaError_t;
- *   - stateless and re-entrant; one device (the current one) per call;
+ *   - re-entrant and thread-safe: no state is shared between host threads (the only cached state -- device attributes, one
+ *     helper stream + two events per device -- is per thread and released when the thread exits; the layout tables are
+ *     immutable after a thread-safe one-time initialisation); one device (the current one) per call;
  *   - there is no CPU fallback: on a device that is not sm_100 every compute entry point
  *     returns NERF_ERR_ARCH.
  */
@@ -160,7 +162,7 @@ int nerf_composite_backward(const float* sigma_rgb, const float* z, const float*
  * compositing backward in ONE launch: loss[0] = mean((rgb - target)^2), d_sigma_rgb[n,4] = grad_scale * dL/d(sigma, r, g, b).
  * The loss is reduced deterministically (per-block partial sums, last block adds them in order).  workspace:
  * nerf_composite_train_workspace_bytes(n_rays) bytes, zero-filled before the FIRST use (the kernel leaves it ready for the
- * next call).  n_sample <= 256. */
+ * next call).  Any n_sample (rays of up to 256 samples are kept in registers between the passes; longer rays are read twice). */
 int64_t nerf_composite_train_workspace_bytes(int64_t n_rays);
 int nerf_composite_train(const float* sigma_rgb, const float* z, const float* target, int64_t n_rays, int n_sample,
                          float grad_scale, float* loss, float* d_sigma_rgb, void* workspace, void* stream);
@@ -260,9 +262,10 @@ int nerf_train_step(const NerfTrainStep* cfg, int phases, void* stream);
  * Self tests (device): exercise the tcgen05 descriptor encodings used by K4 on a small GEMM.
  * variant selects the operand layout hypothesis; result_host[0..3] receives max-abs-error
  * and diagnostics.  Returns 0 when the variant reproduces the fp32 reference product.
- * Diagnostics only: synchronises the device and is the one entry point that allocates.
+ * Not part of the hot path: synchronises the device and is the one entry point that allocates.
  * ------------------------------------------------------------------------------------- */
 int nerf_selftest_umma(int variant, float* result_host);
+#ifdef NERF_DIAGNOSTICS   /* only in libnerf_b200_diag.so (built with -DNERF_DIAGNOSTICS for tools/); not in the product library */
 /* Diagnostics: when device_buffer != NULL, CTA 0 (the leader of cluster 0) of the fused MLP kernels writes clock64 stamps
  * [cluster iteration][step 0..11][tile slot 0..1][4] = (MMA issue start, MMA issue end, accumulator ready seen by the
  * epilogue, next-layer release) into it (int64; 8 iterations fit in 8*12*2*4 entries).  NULL disables.  tools/trace_mlp.py. */
@@ -272,6 +275,8 @@ int nerf_debug_trace(void* device_buffer);
  * 4 two threads / same accumulator).  cycles_host[0] = SM cycles for n_mma MMAs, cycles_host[1] = n_mma.
  * Synchronises the device and allocates; not part of the hot path. */
 int nerf_debug_umma_rate(int variant, int n_mma, long long* cycles_host);
+
+#endif
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libnerf_b200.so")
+DIAG_LIB_PATH = os.path.join(HERE, "libnerf_b200_diag.so")    # the same sources with -DNERF_DIAGNOSTICS (tools/ only)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -32,21 +33,25 @@ def _sources():
         [os.path.join(os.path.dirname(HERE), "include", "nerf_b200.h")]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, diagnostics: bool = False) -> str:
     """Compile csrc/api.cu -> libnerf_b200.so in-tree with nvcc for sm_100a (cross-compiles
-    without a GPU).  Rebuilds only when a source is newer than the library."""
-    if not force and os.path.exists(LIB_PATH):
+    without a GPU).  Rebuilds only when a source is newer than the library.  ``diagnostics``: the same sources with
+    -DNERF_DIAGNOSTICS -> libnerf_b200_diag.so (clock-stamp trace of the fused MLP kernels, UMMA issue-rate microbenchmarks;
+    used by tools/ through NERF_B200_LIB, never by the product path)."""
+    out = DIAG_LIB_PATH if diagnostics else LIB_PATH
+    if not force and os.path.exists(out):
         newest = max(os.path.getmtime(p) for p in _sources())
-        if os.path.getmtime(LIB_PATH) >= newest:
-            return LIB_PATH
+        if os.path.getmtime(out) >= newest:
+            return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "api.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-DNERF_DIAGNOSTICS"] if diagnostics else []) + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", out, os.path.join(CSRC, "api.cu")]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise NerfB200Error("nvcc failed:\n" + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return out
 
 
 _P = C.c_void_p
@@ -93,7 +98,6 @@ PROTOTYPES = {
     "nerf_mlp_wgrad": (_I, [_I, _P, _P, _L, _P, _I, _P]),
     "nerf_composite_forward": (_I, [_P, _P, _L, _I, _P, _P, _P, _P]),
     "nerf_composite_backward": (_I, [_P, _P, _P, _L, _I, _P, _P]),
-    "nerf_debug_umma_rate": (_I, [_I, _I, _P]),
     "nerf_adam_step_reduce": (_I, [_P, _P, _I, _P, _P, _P, _L, _D, _D, _D, _D, _L, _F, _P]),
     "nerf_composite_train_workspace_bytes": (_L, [_L]),
     "nerf_composite_train": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P, _P]),
@@ -103,6 +107,10 @@ PROTOTYPES = {
     "nerf_render_image": (_I, [_P, _I, _P, _I, _D, _D, _D, _D, _I, _I, _L, _L, _I, _F, _F, _I, _U, _U, _P, _P, _P, _P, _P]),
     "nerf_train_step": (_I, [C.POINTER(NerfTrainStep), _I, _P]),
     "nerf_selftest_umma": (_I, [_I, _P]),
+}
+# only exported by libnerf_b200_diag.so (-DNERF_DIAGNOSTICS)
+DIAG_PROTOTYPES = {
+    "nerf_debug_umma_rate": (_I, [_I, _I, _P]),
     "nerf_debug_trace": (_I, [_P]),
 }
 
@@ -119,8 +127,8 @@ def load():
             f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU / eager fallback for the sm_100a kernels)")
     lib = C.CDLL(os.environ.get("NERF_B200_LIB", LIB_PATH))     # override: A/B runs of two builds of the same ABI
-    for name, (res, args) in PROTOTYPES.items():
-        if not hasattr(lib, name) and name.startswith("nerf_debug"):
+    for name, (res, args) in list(PROTOTYPES.items()) + list(DIAG_PROTOTYPES.items()):
+        if name in DIAG_PROTOTYPES and not hasattr(lib, name):
             continue
         fn = getattr(lib, name)
         fn.restype = res

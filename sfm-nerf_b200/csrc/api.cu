@@ -1,5 +1,6 @@
 // api.cu -- the C ABI of libnerf_b200.so (include/nerf_b200.h).  Argument checking, launch
 // geometry and nothing else: every entry point enqueues sm_100a kernels on the caller's stream.
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -21,18 +22,34 @@ struct DeviceInfo {
   // fork/join helpers of nerf_mlp_wgrad: the CUDA-core head-gradient kernel runs beside the tcgen05 kernel (stream-ordered)
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
-thread_local DeviceInfo g_dev;
-long long* g_trace = nullptr;      // diagnostics only (nerf_debug_trace)
+// Per host thread, one slot per device (indexed by device id): nothing is shared between host threads, so concurrent calls
+// -- also first calls -- do not race, and switching the current device keeps the other devices' slots.  The side stream and
+// the two events of a slot are destroyed when the thread exits.
+constexpr int kMaxDevices = 64;
+struct DeviceTable {
+  DeviceInfo slot[kMaxDevices];
+  ~DeviceTable() {
+    for (DeviceInfo& d : slot) {
+      if (d.ev_fork) (void)cudaEventDestroy(d.ev_fork);
+      if (d.ev_join) (void)cudaEventDestroy(d.ev_join);
+      if (d.side) (void)cudaStreamDestroy(d.side);      // errors (e.g. the runtime is already unloading at process exit) are ignored
+    }
+  }
+};
+thread_local DeviceTable g_devs;
+#ifdef NERF_DIAGNOSTICS
+std::atomic<long long*> g_trace{nullptr};      // nerf_debug_trace
+#endif
 
 int device_info(DeviceInfo** out) {
   int dev = 0;
   NERF_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return NERF_ERR_ARG;
+  DeviceInfo& g_dev = g_devs.slot[dev];
   if (g_dev.device != dev) {
-    DeviceInfo d;
-    d.device = dev;
-    NERF_CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
-    NERF_CUDA_TRY(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
-    g_dev = d;
+    NERF_CUDA_TRY(cudaDeviceGetAttribute(&g_dev.sms, cudaDevAttrMultiProcessorCount, dev));
+    NERF_CUDA_TRY(cudaDeviceGetAttribute(&g_dev.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    g_dev.device = dev;
   }
   if (g_dev.cc_major != 10) return NERF_ERR_ARCH;
   if (!g_dev.attrs_set) {
@@ -67,12 +84,15 @@ inline int mlp_grid(const DeviceInfo& dev, int n_tiles) {
 
 inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
+// every layout is built once, under the thread-safe initialisation of a function-local static (C++11)
+struct LayoutCache {
+  ModelLayout m[kNumLayouts];
+  LayoutCache() { for (int i = 0; i < kNumLayouts; ++i) build_model_layout(i, m[i]); }
+};
 const ModelLayout* get_layout(int layout) {
-  static ModelLayout cache[kNumLayouts];
-  static bool ready[kNumLayouts] = {};
+  static const LayoutCache cache;
   if (layout < 0 || layout >= kNumLayouts) return nullptr;
-  if (!ready[layout]) { build_model_layout(layout, cache[layout]); ready[layout] = true; }
-  return &cache[layout];
+  return &cache.m[layout];
 }
 
 void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t n_rows) {
@@ -84,7 +104,9 @@ void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t
   a.n_rows = n_rows;
   a.n_tiles = (int)((n_rows + 127) / 128);
   a.stash_tile_bytes = m.stash_tile_bytes; a.dstash_tile_bytes = m.dstash_tile_bytes;
-  a.trace = g_trace;
+#ifdef NERF_DIAGNOSTICS
+  a.trace = g_trace.load(std::memory_order_relaxed);
+#endif
   a.st_pe = m.st_pe; a.st_de = m.st_de; a.st_r1 = m.st_r1; a.st_mask = m.st_mask; a.ds_y10 = m.ds_y[10]; a.ds_sr = m.ds_sr;
 }
 
@@ -474,8 +496,7 @@ int nerf_composite_backward(const float* sigma_rgb, const float* z, const float*
   DeviceInfo* dev;
   int rc = device_info(&dev);
   if (rc != NERF_OK) return rc;
-  if (!sigma_rgb || !z || !g_rgb || !d_sigma_rgb || n_rays < 0 || n_sample <= 0 || n_sample > 32 * kCompMaxChunks)
-    return NERF_ERR_ARG;
+  if (!sigma_rgb || !z || !g_rgb || !d_sigma_rgb || n_rays < 0 || n_sample <= 0) return NERF_ERR_ARG;
   if (!nerf_aligned(sigma_rgb, 16) || !nerf_aligned(d_sigma_rgb, 16)) return NERF_ERR_ALIGN;
   if (n_rays == 0) return NERF_OK;
   // instances unrolled for 2 / 4 / 8 chunks of 32 samples: a 64-sample ray does not pay the registers of a 256-sample one
@@ -484,8 +505,10 @@ int nerf_composite_backward(const float* sigma_rgb, const float* z, const float*
       reinterpret_cast<const float4*>(sigma_rgb), z, g_rgb, n_rays, n_sample, reinterpret_cast<float4*>(d_sigma_rgb));
   else if (n_sample <= 128) composite_backward_kernel<4><<<cb_blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(sigma_rgb), z, g_rgb, n_rays, n_sample, reinterpret_cast<float4*>(d_sigma_rgb));
-  else composite_backward_kernel<8><<<cb_blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+  else if (n_sample <= 32 * kCompMaxChunks) composite_backward_kernel<8><<<cb_blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(sigma_rgb), z, g_rgb, n_rays, n_sample, reinterpret_cast<float4*>(d_sigma_rgb));
+  else composite_backward_long_kernel<false><<<cb_blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(       /* two-pass form: any ray length */
+      reinterpret_cast<const float4*>(sigma_rgb), z, g_rgb, n_rays, n_sample, 1.0f, nullptr, nullptr, nullptr, reinterpret_cast<float4*>(d_sigma_rgb));
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
@@ -500,9 +523,7 @@ int nerf_composite_train(const float* sigma_rgb, const float* z, const float* ta
   DeviceInfo* dev;
   int rc = device_info(&dev);
   if (rc != NERF_OK) return rc;
-  if (!sigma_rgb || !z || !target || !loss || !d_sigma_rgb || !workspace || n_rays <= 0 || n_sample <= 0 ||
-      n_sample > 32 * kCompMaxChunks)
-    return NERF_ERR_ARG;
+  if (!sigma_rgb || !z || !target || !loss || !d_sigma_rgb || !workspace || n_rays <= 0 || n_sample <= 0) return NERF_ERR_ARG;
   if (!nerf_aligned(sigma_rgb, 16) || !nerf_aligned(d_sigma_rgb, 16) || !nerf_aligned(workspace, 4)) return NERF_ERR_ALIGN;
   const unsigned blocks = blocks_for(n_rays, kCompWarpsPerBlock);
   float* partial = static_cast<float*>(workspace);
@@ -513,7 +534,10 @@ int nerf_composite_train(const float* sigma_rgb, const float* z, const float* ta
   else if (n_sample <= 128) composite_train_kernel<4><<<blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(sigma_rgb), z, target, n_rays, n_sample, grad_scale, loss, partial, ticket,
       reinterpret_cast<float4*>(d_sigma_rgb));
-  else composite_train_kernel<8><<<blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+  else if (n_sample <= 32 * kCompMaxChunks) composite_train_kernel<8><<<blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(sigma_rgb), z, target, n_rays, n_sample, grad_scale, loss, partial, ticket,
+      reinterpret_cast<float4*>(d_sigma_rgb));
+  else composite_backward_long_kernel<true><<<blocks, kCompWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(           /* two-pass form: any ray length */
       reinterpret_cast<const float4*>(sigma_rgb), z, target, n_rays, n_sample, grad_scale, loss, partial, ticket,
       reinterpret_cast<float4*>(d_sigma_rgb));
   NERF_LAUNCH_CHECK();
@@ -622,12 +646,6 @@ int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, in
   return NERF_OK;
 }
 
-// ------------------------------------------------------------------------------------ diagnostics
-int nerf_debug_trace(void* device_buffer) {
-  g_trace = static_cast<long long*>(device_buffer);
-  return NERF_OK;
-}
-
 // ------------------------------------------------------------------------------------ self test
 int nerf_selftest_umma(int variant, float* result_host) {
   DeviceInfo* dev;
@@ -644,6 +662,13 @@ int nerf_selftest_umma(int variant, float* result_host) {
   cudaFree(d);
   if (e != cudaSuccess) return (int)e;
   return (result_host[0] == 0.0f && result_host[1] > 0.0f) ? NERF_OK : NERF_ERR_SELFTEST;
+}
+
+#ifdef NERF_DIAGNOSTICS
+// ------------------------------------------------------------------------------------ diagnostics
+int nerf_debug_trace(void* device_buffer) {
+  g_trace.store(static_cast<long long*>(device_buffer));
+  return NERF_OK;
 }
 
 // diagnostics: UMMA issue-rate microbenchmark (selftest.cuh); cycles_host[0] = cycles, [1] = MMAs
@@ -666,5 +691,7 @@ int nerf_debug_umma_rate(int variant, int n_mma, long long* cycles_host) {
   cudaFree(d);
   return e == cudaSuccess ? NERF_OK : (int)e;
 }
+
+#endif  // NERF_DIAGNOSTICS
 
 }  // extern "C"

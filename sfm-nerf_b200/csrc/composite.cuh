@@ -280,6 +280,96 @@ composite_train_kernel(const float4* __restrict__ sigma_rgb, const float* __rest
   }
 }
 
+// Any ray length (S > 32 * kCompMaxChunks, e.g. --n_sample 512): two passes over the ray instead of per-lane state for every
+// chunk.  Pass 1 is the forward pass (rgb of the ray).  The backward needs suffix_i = sum_{j>i} w_j (g . c_j); since
+// sum_j w_j (g . c_j) = g . rgb, it is total - inclusive prefix, so pass 2 re-reads the ray front to back, recomputes
+// T / alpha / w per chunk and carries the prefix.  TRAIN: g = dL/d rgb of the MSE (train.py:460) and the loss partial sums, as in
+// composite_train_kernel; otherwise g comes from g_rgb.
+__device__ __forceinline__ float comp_chunk_forward(const CompChunk& ck, int s, int S, int lane, float& carry, float& alpha, float& om, float& delta) {
+  om = 1.0f; alpha = 0.0f; delta = 0.0f;
+  if (s < S) {
+    sample_alpha(ck.z, ck.zn, s, S, ck.v.x, delta, alpha);
+    om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+  }
+  const float incl = warp_incl_prod(om, lane);
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 1.0f;
+  const float T = carry * excl;
+  carry *= __shfl_sync(0xffffffffu, incl, 31);
+  return T;
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kCompWarpsPerBlock * 32)
+composite_backward_long_kernel(const float4* __restrict__ sigma_rgb, const float* __restrict__ z, const float* __restrict__ g_or_target,
+                               int64_t n_rays, int S, float grad_scale, float* __restrict__ loss, float* __restrict__ partial,
+                               unsigned int* __restrict__ ticket, float4* __restrict__ d_sigma_rgb) {
+  __shared__ float red[kCompWarpsPerBlock];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t ray = (int64_t)blockIdx.x * kCompWarpsPerBlock + wib;
+  float sq = 0.0f;
+  if (ray < n_rays) {
+    const float4* sr = sigma_rgb + ray * S;
+    const float* zr = z + ray * S;
+    float4* out = d_sigma_rgb + ray * S;
+    float g0 = g_or_target[3 * ray + 0], g1 = g_or_target[3 * ray + 1], g2 = g_or_target[3 * ray + 2];
+    float carry = 1.0f, ar = 0.f, ag = 0.f, ab = 0.f;
+    for (int base = 0; base < S; base += 32) {                    // pass 1: forward
+      const int s = base + lane;
+      const CompChunk ck = load_chunk(sr, zr, s, S);
+      float alpha, om, delta;
+      const float T = comp_chunk_forward(ck, s, S, lane, carry, alpha, om, delta);
+      const float w = alpha * T;
+      ar += w * ck.v.y; ag += w * ck.v.z; ab += w * ck.v.w;
+    }
+    const float r = warp_sum4_scatter(ar, ag, ab, 0.0f, lane);
+    ar = __shfl_sync(0xffffffffu, r, 0); ag = __shfl_sync(0xffffffffu, r, 8); ab = __shfl_sync(0xffffffffu, r, 16);
+    if (TRAIN) {
+      const float d0 = ar - g0, d1 = ag - g1, d2 = ab - g2;       // g_or_target holds the target colour
+      sq = d0 * d0 + d1 * d1 + d2 * d2;
+      const float gs = grad_scale * 2.0f / (float)(3 * n_rays);
+      g0 = gs * d0; g1 = gs * d1; g2 = gs * d2;
+    }
+    const float total = g0 * ar + g1 * ag + g2 * ab;              // = sum_j w_j (g . c_j)
+    float prefix = 0.0f;
+    carry = 1.0f;
+    for (int base = 0; base < S; base += 32) {                    // pass 2: backward, front to back
+      const int s = base + lane;
+      const CompChunk ck = load_chunk(sr, zr, s, S);
+      float alpha, om, delta;
+      const float T = comp_chunk_forward(ck, s, S, lane, carry, alpha, om, delta);
+      const float w = alpha * T;
+      const float gc = g0 * ck.v.y + g1 * ck.v.z + g2 * ck.v.w;
+      const float incl = warp_incl_sum(w * gc, lane);
+      const float suffix = total - (prefix + incl);               // sum over j > i
+      if (s < S) {
+        const float dalpha = T * gc - suffix / om;
+        out[s] = make_float4(delta * (1.0f - alpha) * dalpha, w * g0, w * g1, w * g2);
+      }
+      prefix += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  if (!TRAIN) return;
+  if (lane == 0) red[wib] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.0f;
+    for (int w = 0; w < kCompWarpsPerBlock; ++w) b += red[w];
+    partial[blockIdx.x] = b;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && wib == 0) {
+    __threadfence();
+    float acc = 0.0f;
+    for (unsigned int i = lane; i < gridDim.x; i += 32) acc += __ldcg(partial + i);
+    acc = warp_sum(acc);
+    if (lane == 0) { loss[0] = acc / (float)(3 * n_rays); *ticket = 0u; }
+  }
+}
+
 // train.py:460 nn.MSELoss (mean over n*3) and its gradient; single block.
 __global__ void __launch_bounds__(1024)
 mse_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ target, int64_t n3,

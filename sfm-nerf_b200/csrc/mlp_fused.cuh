@@ -290,9 +290,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           const uint32_t d_tmem = tmem_base + 256 * slot;
           tc::mbar_wait_cluster(bar_act + 8 * slot, act_phase & 1u);       // this slot's A tile of the layer is ready
           tc::tc_fence_after();
+#ifdef NERF_DIAGNOSTICS
           long long* tr = (a.trace != nullptr && blockIdx.x == 0 && lane == 0)
                               ? a.trace + ((size_t)((quad / n_clusters) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
           if (tr) tr[0] = clock64();
+#endif
           int k_done = 0;
 #pragma unroll 1
           for (int seg = 0; seg < 3; ++seg) {
@@ -380,7 +382,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           }
           if (tc::elect_one()) tc::umma_commit_pair(bar_acc + 8 * slot, 3);
           __syncwarp();
+#ifdef NERF_DIAGNOSTICS
           if (tr) tr[1] = clock64();
+#endif
         }
       }
     }
@@ -473,9 +477,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         }
         tc::mbar_wait(my_acc, acc_phase & 1u); ++acc_phase;
         tc::tc_fence_after();
+#ifdef NERF_DIAGNOSTICS
         long long* tr = (a.trace != nullptr && blockIdx.x == 0 && row == 0)
                             ? a.trace + ((size_t)((quad / n_clusters) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
         if (tr) tr[2] = clock64();
+#endif
         const int n_units = st.n >> 6;                 // 64 accumulator columns per TMEM load (4 or 2 units, even)
         const bool is_rgb = (MODE == MODE_FWD) && (st.flags & EPI_RGB) != 0;
         const bool is_dens = (MODE == MODE_FWD) && (st.flags & EPI_DENSITY) != 0;
@@ -545,7 +551,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         if (!(st.flags & EPI_LAST)) {                  // the next layer's MMAs may start NOW
           if (rank == 0) tc::mbar_arrive(bar_act + 8 * slot); else tc::mbar_arrive_cluster(leader_act);
         }
+#ifdef NERF_DIAGNOSTICS
         if (tr) tr[3] = clock64();
+#endif
 
         // ---- everything below is off the MMA -> epilogue -> MMA critical path ----
         if (MODE == MODE_FWD) {

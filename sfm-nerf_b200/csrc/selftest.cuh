@@ -125,6 +125,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) selftest_umma_p
   if (warp == 0) tc::tmem_dealloc_pair(tmem, 64);
 }
 
+#ifdef NERF_DIAGNOSTICS
 // Microbenchmark (diagnostics): issue rate of 128x256x16 bf16 UMMAs on one SM.
 //   variant 0: one thread, one accumulator          1: one thread, two accumulators alternating
 //   variant 2: two threads (warps 0 and 1), one accumulator each
@@ -267,5 +268,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) umma_pair_rate_
   tc::cluster_sync();
   if (warp == 0) tc::tmem_dealloc_pair(tmem, 512);
 }
+
+#endif  // NERF_DIAGNOSTICS
 
 }  // namespace nerf

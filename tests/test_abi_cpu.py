@@ -22,12 +22,50 @@ def libmod():
 
 def test_header_symbols_are_exported(libmod):
     header = open(os.path.join(ROOT, "include", "nerf_b200.h")).read()
-    declared = set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", header))
-    assert len(declared) >= 20
+    product, diag = re.split(r"#ifdef NERF_DIAGNOSTICS", header, maxsplit=1)
+    diag = diag.split("#endif", 1)[0]
+    declared = set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", product))
+    declared_diag = set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", diag))
+    assert len(declared) >= 20 and declared_diag == set(libmod.DIAG_PROTOTYPES)
     lib = ctypes.CDLL(libmod.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in nerf_b200.h but not exported"
     assert declared == set(libmod.PROTOTYPES), declared ^ set(libmod.PROTOTYPES)
+    # the product library exports exactly the declared C ABI: no diagnostics, nothing undeclared
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", libmod.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("nerf_")}
+    assert exported == declared, exported ^ declared
+    # the diagnostics build (-DNERF_DIAGNOSTICS) adds the nerf_debug_* entry points
+    dlib = ctypes.CDLL(libmod.build(diagnostics=True))
+    for name in declared | declared_diag:
+        assert hasattr(dlib, name), name
+
+
+def test_two_threads_first_calls_do_not_race(libmod):
+    """Header promise: re-entrant and thread-safe.  Two host threads make their FIRST calls into a freshly loaded copy of the
+    library at the same time (layout tables are built on first use); every query returns the right value in both."""
+    import shutil, tempfile, threading
+    with tempfile.TemporaryDirectory() as d:
+        for trial in range(4):
+            path = os.path.join(d, f"libnerf_copy{trial}.so")          # a new path = a new image with uninitialised statics
+            shutil.copyfile(libmod.LIB_PATH, path)
+            lib = ctypes.CDLL(path)
+            lib.nerf_param_count.restype = ctypes.c_int64
+            lib.nerf_param_offset.restype = ctypes.c_int64
+            lib.nerf_mlp_stash_bytes.restype = ctypes.c_int64
+            lib.nerf_mlp_stash_bytes.argtypes = [ctypes.c_int, ctypes.c_int64]
+            go = threading.Barrier(2)
+            res = [None, None]
+
+            def worker(i):
+                go.wait()
+                res[i] = (lib.nerf_param_count(i), lib.nerf_param_count(1 - i), lib.nerf_param_offset(0, 25), lib.nerf_mlp_stash_bytes(i, 128))
+            ts = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+            for t in ts: t.start()
+            for t in ts: t.join()
+            assert res[0][0] == 661636 and res[0][1] == 627844 and res[1][0] == 627844 and res[1][1] == 661636
+            assert res[0][2] == res[1][2] == 661636 - 3 and res[0][3] == res[1][3] > 0
 
 
 def test_train_step_struct_matches_header(libmod, tmp_path):

@@ -150,7 +150,7 @@ def test_composite_forward_backward(pkg, orc):
     gen = torch.Generator().manual_seed(11)
     # every kernel instance: straight-line forward for 32 / 64 / 128 / 192 / 256 samples, the generic forward (ragged lengths,
     # more than one 128-sample group), backward unrolled for 2 / 4 / 8 chunks, S == 1
-    for n, S in ((37, 64), (5, 192), (3, 1), (9, 40), (2, 256), (4, 32), (3, 128), (6, 100), (2, 200), (2, 300)):
+    for n, S in ((37, 64), (5, 192), (3, 1), (9, 40), (2, 256), (4, 32), (3, 128), (6, 100), (2, 200), (2, 300), (11, 512), (3, 257)):
         sigma = torch.rand(n, S, generator=gen) * 30.0 * (torch.rand(n, S, generator=gen) > 0.5)
         rgb = torch.rand(n, S, 3, generator=gen)
         z = orc.sample_z(n, S, 2.0, 6.0, torch.rand(n, S, generator=gen)) if S > 1 else torch.full((n, 1), 2.0)
@@ -161,10 +161,7 @@ def test_composite_forward_backward(pkg, orc):
         np.testing.assert_allclose(depth.cpu().numpy(), ref["depth"].numpy(), rtol=0, atol=1e-5)
         np.testing.assert_allclose(acc.cpu().numpy(), ref["acc"].numpy(), rtol=0, atol=2e-6)
         g = torch.randn(n, 3, generator=gen)
-        if S > 256:       # the backward kernels keep a ray in registers: S <= 256 (the reference never goes beyond 256)
-            with pytest.raises(pkg._lib.NerfB200Error):
-                pkg.engine.composite_backward(sr, z.cuda(), g.cuda())
-            continue
+        # S > 256 (e.g. --n_sample 512, which trains in the reference): the two-pass backward kernel
         if S == 1:        # reference quirk: empty `dists` -> all-zero outputs and gradients
             assert float(pkg.engine.composite_backward(sr, z.cuda(), g.cuda()).abs().max()) == 0.0
             continue
@@ -177,7 +174,7 @@ def test_composite_forward_backward(pkg, orc):
 def test_composite_train_fused(pkg, orc):
     """nerf_composite_train (forward + MSE + backward in one launch) equals the three separate entry points."""
     gen = torch.Generator().manual_seed(4)
-    for n_rays, S in ((5, 64), (257, 192), (33, 17)):
+    for n_rays, S in ((5, 64), (257, 192), (33, 17), (19, 512), (7, 300)):      # the last two: two-pass kernel for rays longer than 256 samples
         sr = torch.rand(n_rays, S, 4, generator=gen).cuda(); sr[..., 0] *= 8.0
         z = (2.0 + 4.0 * torch.sort(torch.rand(n_rays, S, generator=gen), dim=1).values).cuda()
         tgt = torch.rand(n_rays, 3, generator=gen).cuda()
@@ -558,6 +555,40 @@ def test_errors_are_loud(pkg, model_pe):
         cpu_model(torch.zeros(4, 3), torch.zeros(4, 3))
     with pytest.raises(NotImplementedError):
         pkg.NeRFmodel(num_channels=128).cuda()(torch.zeros(4, 3).cuda(), torch.zeros(4, 3).cuda())
+
+
+def test_two_host_threads_train_concurrently(pkg, orc, sd_pe256):
+    """include/nerf_b200.h: re-entrant and thread-safe.  Two host threads, each on its own stream, run whole train steps (every
+    kernel of the path, including the fork / join of the head-gradient kernel onto the per-thread helper stream) at the same time;
+    both reproduce the losses of a single-threaded run."""
+    import threading
+    E = pkg.engine
+    cam = orc.make_camera_info(40, 30)
+    poses = E.poses_to_device(orc.sphere_poses(4, seed=3), "cuda")
+    images = torch.tensor(np.random.default_rng(1).random((4, 30, 40, 3)).astype(np.float32)).cuda()
+
+    def run(out, i, go=None):
+        torch.cuda.set_device(0)
+        with torch.cuda.stream(torch.cuda.Stream()):
+            m = pkg.NeRFmodel().cuda()
+            m.load_state_dict(sd_pe256)
+            tr = E.Trainer(m, images, poses, cam, 384, 32, perturb=True, seed=5, graph=False)
+            if go is not None:
+                go.wait()
+            out[i] = [float(tr.step().item()) for _ in range(4)]
+            tr.close()
+        torch.cuda.synchronize()
+
+    ref = [None]
+    run(ref, 0)
+    go = threading.Barrier(2)
+    res = [None, None]
+    ts = [threading.Thread(target=run, args=(res, i, go)) for i in range(2)]
+    for t in ts: t.start()
+    for t in ts: t.join()
+    for r in res:
+        assert r is not None and r[0] == ref[0][0]
+        np.testing.assert_allclose(r, ref[0], rtol=2e-4)
 
 
 def test_no_pe_variant_gradients_vs_oracle(pkg, orc):

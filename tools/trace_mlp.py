@@ -1,6 +1,8 @@
 """Per-layer timeline of CTA 0 of the fused MLP kernel (clock64 stamps via nerf_debug_trace)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import importlib
+os.environ.setdefault("NERF_B200_LIB", importlib.import_module("sfm-nerf_b200._lib").build(diagnostics=True))   # -DNERF_DIAGNOSTICS build
 import torch
 import sfmnerf_b200 as s
 E = s.engine

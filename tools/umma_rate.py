@@ -1,6 +1,8 @@
 """UMMA issue-rate microbenchmark (nerf_debug_umma_rate): cycles per 128x256x16 MMA for different issue patterns."""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import importlib
+os.environ.setdefault("NERF_B200_LIB", importlib.import_module("sfm-nerf_b200._lib").build(diagnostics=True))   # -DNERF_DIAGNOSTICS build
 import torch
 import sfmnerf_b200 as s
 lib = s._lib.load()
