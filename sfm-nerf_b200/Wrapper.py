@@ -4,8 +4,9 @@ Only the SURFACE is mirrored.  `Wrapper.render` upstream differs numerically fro
 always-jittered t = (i + U)/S, last delta 1.0) and contains a bug -- its transmittance cumprod runs over a size-1 axis and
 is therefore the identity (`Wrapper.py:176`) -- so its numerics are deliberately NOT reproduced: every function here
 delegates to the `train.py` mirror (the kernels of libnerf_b200), keeping `Wrapper.py`'s names, argument lists and
-defaults.  `test_single_image` (the "gif" mode, `Wrapper.py:381-507`) renders the views of a circular fly-around of the
-loaded poses' radius and writes PNGs with cv2 when it is available (imageio / matplotlib are not needed).
+defaults.  `test_single_image` (the "gif" mode, `Wrapper.py:381-507`) renders the reference's 10-view orbit
+`pose_spherical(th, -30 deg, 4.0)` (converted to `PixelToRay`'s camera convention by default, see `orbit_poses`) and writes
+PNGs with cv2 when it is available (imageio / matplotlib are not needed).
 """
 from __future__ import annotations
 
@@ -34,9 +35,41 @@ def render(model, rays_origin, rays_direction, args, near=1.0, far=10.0):
     return _t.render(model, rays_origin, rays_direction, args, near, far)
 
 
+def pose_spherical(theta, phi, radius):
+    """Camera-to-world matrix of the reference's orbit (`Wrapper.py:443-470`, restated): translate by `radius` along z, rotate by
+    `phi` about x and `theta` about y (degrees), then the fixed axis permutation -- float32 factors like the reference's."""
+    trans_t = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, radius], [0, 0, 0, 1]], dtype=np.float32)
+    ph, th = phi / 180.0 * np.pi, theta / 180.0 * np.pi
+    rot_phi = np.array([[1, 0, 0, 0], [0, np.cos(ph), -np.sin(ph), 0], [0, np.sin(ph), np.cos(ph), 0], [0, 0, 0, 1]], dtype=np.float32)
+    rot_theta = np.array([[np.cos(th), 0, -np.sin(th), 0], [0, 1, 0, 0], [np.sin(th), 0, np.cos(th), 0], [0, 0, 0, 1]], dtype=np.float32)
+    c2w = rot_theta @ (rot_phi @ trans_t)
+    return np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]) @ c2w
+
+
+def orbit_poses(n_views=10, phi=-30.0, radius=4.0, convention="pixel_to_ray"):
+    """The `n_views` poses of the gif orbit: `pose_spherical(th, -30, 4.0)` for th in linspace(0, 360, 10, endpoint=False)
+    (`Wrapper.py:472-475`).  `pose_spherical` builds Blender / OpenGL camera frames (the camera looks along its -z, +y up), while
+    `PixelToRay` shoots rays along +z with +y down (`train.py:87-94`): the reference feeds the one into the other unconverted, so
+    its orbit looks AWAY from the object (SURVEY A.5 -- the degenerate image/*.png it ships).  convention="pixel_to_ray"
+    (default) flips the camera's y and z axes so that the orbit looks at the origin in PixelToRay's convention;
+    convention="reference" returns the matrices exactly as the reference uses them."""
+    out = []
+    for th in np.linspace(0.0, 360.0, n_views, endpoint=False):
+        c2w = np.asarray(pose_spherical(th, phi, radius), dtype=np.float64)
+        if convention == "pixel_to_ray":
+            c2w = c2w @ np.diag([1.0, -1.0, -1.0, 1.0])
+        elif convention != "reference":
+            raise ValueError("convention must be 'pixel_to_ray' or 'reference'")
+        out.append(c2w)
+    return np.stack(out)
+
+
 def test_single_image(images, poses, camera_info, args):
-    """"gif" mode (`Wrapper.py:381-507`): render every view of `poses` with the newest checkpoint under
-    `args.checkpoint_path`; returns the list of [H,W,3] float32 frames (and writes image_<k>.png when cv2 is present)."""
+    """"gif" mode (`Wrapper.py:381-507`): the newest checkpoint under `args.checkpoint_path` renders the 10 novel views of the
+    orbit `pose_spherical(th, -30 deg, 4.0)` (see `orbit_poses`; `args.orbit_convention`, default "pixel_to_ray").  Every frame is
+    one pass of ray generation + depths + fused MLP + compositing on the GPU per batch of `args.n_rays_batch` rays.  Returns the
+    list of [H,W,3] frames scaled to 0..255 like the reference's and writes image_<k>.png (k from 1) when cv2 is present; the
+    reference's matplotlib ray plots are not reproduced."""
     final = os.path.join(args.checkpoint_path, "final_model.pth")
     found = [final] if os.path.exists(final) else sorted(glob.glob(os.path.join(args.checkpoint_path, "model_*.pth")))[-1:]
     if not found:
@@ -50,15 +83,18 @@ def test_single_image(images, poses, camera_info, args):
     else:
         model = NeRFmodel().to(device)
         model.load_state_dict(sd)
+    print(f"Checkpoint {found[0]} loaded")
     os.makedirs(args.images_path, exist_ok=True)
+    H, W = int(camera_info["height"]), int(camera_info["width"])
+    blank = np.zeros((H, W, 3), dtype=np.float32)             # test_image also reports an MSE; there is no ground truth for novel views
     frames = []
-    for k in range(len(poses)):
-        pred, _ = test_image(model, images[k % len(images)], poses[k], camera_info, args)
-        frame = pred.detach().cpu().numpy().astype(np.float32)
+    for count, c2w in enumerate(orbit_poses(convention=getattr(args, "orbit_convention", "pixel_to_ray")), start=1):
+        pred, _ = test_image(model, blank, c2w, camera_info, args)
+        frame = pred.detach().cpu().numpy().astype(np.float32) * 255.0
         frames.append(frame)
         try:
             import cv2
-            cv2.imwrite(os.path.join(args.images_path, f"image_{k}.png"), (np.clip(frame[..., ::-1], 0, 1) * 255).astype(np.uint8))
+            cv2.imwrite(os.path.join(args.images_path, f"image_{count}.png"), frame)      # Wrapper.py:505-507 (RGB order as the reference writes it)
         except ImportError:
             pass
     return frames

@@ -925,6 +925,16 @@ def test_train_and_test_drivers_end_to_end(pkg, tmp_path):
     res = pkg.test(ims, ps, ci, args3)
     assert len(res) == 5 and all(np.isfinite(r[1]) for r in res)
     assert (tmp_path / "img" / "test_0.png").exists()
+    # gif mode (Wrapper.py:381-507): the 10-view orbit pose_spherical(th, -30 deg, 4.0), novel views of the trained model
+    args4 = pkg.Wrapper.configParser().parse_args(["--data_path", str(data) + "/", "--images_path", str(tmp_path / "gif"), "--n_sample", "32",
+                                                   "--n_rays_batch", "512", "--mode", "gif"])
+    args4.checkpoint_path, args4.near, args4.far, args4.perturb = str(ckdir), 2.0, 6.0, False
+    frames = pkg.Wrapper.test_single_image(ims, ps, ci, args4)
+    assert len(frames) == 10 and frames[0].shape == (32, 32, 3)
+    assert all(np.isfinite(f).all() and f.min() >= 0.0 and f.max() <= 255.0 for f in frames)
+    assert max(float(f.max()) for f in frames) > 25.0              # the converted orbit looks at the object: the frames are not black
+    assert not np.allclose(frames[0], frames[5])                    # opposite sides of the orbit differ
+    assert (tmp_path / "gif" / "image_1.png").exists() and (tmp_path / "gif" / "image_10.png").exists()
 
 
 def test_psnr_after_2k_steps_matches_reference_band(pkg):
