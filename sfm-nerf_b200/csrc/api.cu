@@ -53,8 +53,9 @@ int device_info(DeviceInfo** out) {
   }
   if (g_dev.cc_major != 10) return NERF_ERR_ARCH;
   if (!g_dev.attrs_set) {
-    NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
-    NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
+    NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
+    NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
+    NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_BWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
     NERF_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     NERF_CUDA_TRY(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
     NERF_CUDA_TRY(cudaFuncSetAttribute(selftest_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
@@ -65,7 +66,7 @@ int device_info(DeviceInfo** out) {
     at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
     cfg.attrs = &at; cfg.numAttrs = 1;
     int n_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&n_clusters, mlp_fused_kernel<MODE_FWD>, &cfg) != cudaSuccess || n_clusters < 1) {
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, mlp_fused_kernel<MODE_FWD, true>, &cfg) != cudaSuccess || n_clusters < 1) {
       (void)cudaGetLastError();
       n_clusters = g_dev.sms / 2;
     }
@@ -128,7 +129,8 @@ int launch_forward(const void* packed, int layout, const float* pos, const float
   a.stash = static_cast<uint8_t*>(stash);
   a.prog = m->fwd;
   const int grid = mlp_grid(*dev, a.n_tiles);
-  mlp_fused_kernel<MODE_FWD><<<grid, kMlpThreads, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
+  if (stash) mlp_fused_kernel<MODE_FWD, true><<<grid, kMlpThreads, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
+  else mlp_fused_kernel<MODE_FWD, false><<<grid, kMlpThreads, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
@@ -358,7 +360,7 @@ int nerf_mlp_dgrad(const void* packed, int layout, const void* stash, const floa
   a.dstash = static_cast<uint8_t*>(dstash);
   a.prog = m->bwd;
   const int grid = mlp_grid(*dev, a.n_tiles);
-  mlp_fused_kernel<MODE_BWD><<<grid, kMlpThreads, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
+  mlp_fused_kernel<MODE_BWD, false><<<grid, kMlpThreads, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }

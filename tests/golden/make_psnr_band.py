@@ -27,9 +27,14 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
 # the configuration both sides run (the GPU test reads it from psnr_band.json)
-CFG = {"steps": 2000, "n_rays_batch": 256, "n_sample": 32, "width": 48, "n_train": 12, "n_test": 4, "near": 2.0, "far": 6.0,
+CFG = {"steps": 2000, "n_rays_batch": 512, "n_sample": 32, "width": 48, "n_train": 12, "n_test": 4, "near": 2.0, "far": 6.0,
        "lrate": 5e-4, "lrate_decay_steps": 1500, "lrate_decay": 0.1, "batch_seed_base": 1000,
-       "eval_train_views": [0, 3, 6, 9], "scene": "textured_field, uint8-quantised views"}
+       "eval_train_views": [0, 3, 6, 9], "scene": "dense_field, uint8-quantised views"}
+# Why this configuration (tests/psnr_chaos_probe.py on the GPU, profiles/r2_psnr_chaos_probe.json): NeRF training is chaotic, and
+# a gate on 0.2 dB needs trajectories whose PSNR after 2,000 steps scatters by much less than that.  The finely textured scene
+# sits on a loss plateau for 500-1500 steps whose exit time decides the result (across-seed std 1.3 dB at 256 rays); the smooth
+# frame-filling scene with 512 rays per step and the last 500 steps at a tenth of the step size scatters by 0.27 dB (training
+# views) / 0.2 dB (held-out views) across seeds and by 0.22 / 0.05 dB when a seed is repeated.
 
 
 def make_scene():
@@ -37,7 +42,7 @@ def make_scene():
     W = CFG["width"]
     cam = s.synthetic.make_camera_info(W, W)
     poses = s.synthetic.sphere_poses(CFG["n_train"] + CFG["n_test"], seed=0)
-    images = s.synthetic.render_lego_images(poses, cam, n_sample=128, device="cpu", field=s.synthetic.textured_field).numpy()
+    images = s.synthetic.render_lego_images(poses, cam, n_sample=128, device="cpu", field=s.synthetic.dense_field).numpy()
     u8 = np.clip(np.rint(images * 255.0), 0, 255).astype(np.uint8)
     np.savez_compressed(os.path.join(HERE, "psnr_scene.npz"), images_u8=u8, poses=poses, K=cam["camera_matrix"])
     print("scene written:", u8.shape, "mean", u8.mean())
