@@ -12,6 +12,7 @@
 #include "rays.cuh"
 #include "selftest.cuh"
 #include "wgrad.cuh"
+#include "wgrad_pair.cuh"
 
 using namespace nerf;
 
@@ -57,6 +58,7 @@ int device_info(DeviceInfo** out) {
     NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
     NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_BWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
     NERF_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+    NERF_CUDA_TRY(cudaFuncSetAttribute(wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW2SmemBytes));
     NERF_CUDA_TRY(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
     NERF_CUDA_TRY(cudaFuncSetAttribute(selftest_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
     // how many CTA pairs of the fused MLP kernel the device can hold at once (one CTA per SM, pairs share a TPC)
@@ -108,7 +110,7 @@ void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t
 #ifdef NERF_DIAGNOSTICS
   a.trace = g_trace.load(std::memory_order_relaxed);
 #endif
-  a.st_pe = m.st_pe; a.st_de = m.st_de; a.st_r1 = m.st_r1; a.st_mask = m.st_mask; a.ds_y10 = m.ds_y[10]; a.ds_sr = m.ds_sr;
+  a.st_pe = m.st_pe; a.st_de = m.st_de; a.st_r1 = m.st_r1; a.st_mask = m.st_mask; a.ds_y10 = m.ds_y[10]; a.ds_sr = m.ds_sr; a.ds_cot = m.ds_cot;
 }
 
 int launch_forward(const void* packed, int layout, const float* pos, const float* dir, const float* z,
@@ -379,6 +381,24 @@ int nerf_mlp_wgrad(int layout, const void* stash, const void* dstash, int64_t n_
   if (n_rows == 0) return NERF_OK;
   const int n_tiles = (int)((n_rows + 127) / 128);
 
+#if NERF_WGRAD_PAIR
+  {
+    // CTA pairs (wgrad_pair.cuh).  All (item, tile) work is laid on one line in item order, weighted by the item's bytes per
+    // tile, and cut into n_pairs equal pieces: a pair gets a tile range of one item, or the tail of one and the head of the next.
+    W2PairArgs w;
+    std::memset(&w, 0, sizeof(w));
+    w.stash = static_cast<const uint8_t*>(stash); w.dstash = static_cast<const uint8_t*>(dstash); w.grads = grads;
+    w.stash_tile_bytes = m->stash_tile_bytes; w.dstash_tile_bytes = m->dstash_tile_bytes;
+    w.n_items = m->n_w2;
+    for (int i = 0; i < m->n_w2; ++i) w.items[i] = m->w2[i];
+    const int n_pairs = w2_partition(*m, n_tiles, dev->sms / 2, w.n_units, w.unit);
+    if (n_pairs < 1) return NERF_ERR_ARG;
+    w.n_pairs = n_pairs;
+    wgrad_pair_kernel<<<2 * n_pairs, kW2Threads, kW2SmemBytes, s>>>(w);
+    NERF_LAUNCH_CHECK();
+    return NERF_OK;
+  }
+#endif
   // weight gradients: split the SMs over the work items in proportion to their cost
   WgradArgs w;
   std::memset(&w, 0, sizeof(w));

@@ -59,6 +59,9 @@ constexpr int kMlpThreads = 384;
 // SM gets of the HBM write bandwidth when all 148 store at once is 5,600-7,000 cycles, more than the 4,700 cycles of MMAs.
 // These two kernels are bound by HBM WRITES (1.5 / 1.4 GB per launch), not by the epilogue code; the defaults below are the
 // fastest forms measured (profiles/r2_stash_store_variants.md).
+#ifndef NERF_WGRAD_PAIR
+#define NERF_WGRAD_PAIR 1           // 1: wgrad_pair.cuh (CTA pairs, heads on the tensor core); 0: wgrad.cuh + head_grad_kernel
+#endif
 #ifndef NERF_FWD_STASH_MODE
 #define NERF_FWD_STASH_MODE 0
 #endif
@@ -98,7 +101,7 @@ struct MlpArgs {
   uint8_t* stash;            // fwd: written when non-null; bwd: read
   uint8_t* dstash;           // bwd: written
   int32_t stash_tile_bytes, dstash_tile_bytes;
-  int32_t st_pe, st_de, st_r1, st_mask, ds_y10, ds_sr;
+  int32_t st_pe, st_de, st_r1, st_mask, ds_y10, ds_sr, ds_cot;
   long long* trace;          // diagnostics: per-(pair,step,slot) clock64 stamps of CTA 0 (or null)
   Program prog;
 };
@@ -496,7 +499,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         dsp = a.density_relu ? (o.x > 0.0f ? d.x : 0.0f)                 // relu'
                              : d.x * (1.0f - expf(-o.x));              // softplus'(x) = 1 - exp(-softplus(x))
         const float d0 = d.y * o.y * (1.0f - o.y), d1 = d.z * o.z * (1.0f - o.z), d2 = d.w * o.w * (1.0f - o.w);
-        if (tile_ok) reinterpret_cast<float4*>(dstash_tile + a.ds_sr)[row] = make_float4(dsp, d0, d1, d2);
+        if (tile_ok) {
+          // head cotangents for the weight-gradient kernel: a bf16 hi + lo pair per value (k-core 0: hi, k-core 1: lo; channels
+          // 0-3 of 8), so the heads' gradients ride on the tensor core with ~16 mantissa bits
+          const float c4[4] = {dsp, d0, d1, d2};
+          uint32_t hi[2], lo[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float h0 = __bfloat162float(__float2bfloat16_rn(c4[2 * j])), h1 = __bfloat162float(__float2bfloat16_rn(c4[2 * j + 1]));
+            hi[j] = tc::pack_bf16x2(h0, h1);
+            lo[j] = tc::pack_bf16x2(c4[2 * j] - h0, c4[2 * j + 1] - h1);
+          }
+          uint4* cot = reinterpret_cast<uint4*>(dstash_tile + a.ds_cot);
+          cot[row] = make_uint4(hi[0], hi[1], 0u, 0u);
+          cot[128 + row] = make_uint4(lo[0], lo[1], 0u, 0u);
+#if NERF_WGRAD_PAIR == 0
+          reinterpret_cast<float4*>(dstash_tile + a.ds_sr)[row] = make_float4(dsp, d0, d1, d2);      // single-CTA wgrad + CUDA-core head kernel
+#endif
+        }
         const float* w2 = sm + a.sm_w2;
         const uint32_t r1w[4] = {r1m.x, r1m.y, r1m.z, r1m.w};
 #pragma unroll

@@ -82,6 +82,41 @@ struct WgradItem {
 };
 constexpr int kMaxWgradItems = 16;
 
+// ---- CTA-pair wgrad (wgrad_pair.cuh): one work item = everything one pair accumulates from the operand blocks it stages ----
+enum : int32_t { W2_OUT_WEIGHT = 0, W2_OUT_BIAS = 1, W2_OUT_HEAD = 2 };
+struct W2Seg {            // one bulk copy: bytes from (dstash | stash) tile + off[rank] -- each CTA of the pair loads ITS half
+  int32_t off[2];
+  int32_t bytes;
+  int8_t from_dstash[2];
+  int8_t pad_[2];
+};
+struct W2Load { int32_t n_segs; W2Seg seg[3]; };                  // the segments land back to back in one 40 KB ring slot
+struct W2Mma {            // D[256 x n] (+)= A[rows x 256]^T . B[rows x n], 8 k-steps of 16 rows per 128-row tile
+  int32_t a_load, a_kc;   // A: load index of the tile + k-core offset inside its slot (16 k-cores = this CTA's 128 M rows)
+  int32_t b_load, b_kc;   // B: likewise (n/16 k-cores per CTA); b_load < 0: the constant-ones k-core (bias gradients)
+  int32_t n, d_col;
+};
+struct W2Out {            // what a block of TMEM columns is: rows = this CTA's 128 M rows
+  int32_t kind, d_col, n_valid, dst, ld, col0;   // WEIGHT: grads[dst + row*ld + col0 + j] += D[row][j], j < n_valid
+  int32_t row_base[2];                           // BIAS:   grads[dst + row] += D[row][0]
+  int32_t rank_mask;                             // HEAD:   grads[dst + (c-col0)*ld + row] += D[row][c] + D[row][c+8], col0 <= c < col0+n_valid
+};
+struct W2Item {
+  int32_t n_loads, n_mmas, n_outs;
+  int32_t depth, stage_bytes, load_off[3];   // ring geometry: `depth` stages of stage_bytes, load l of a tile at load_off[l] inside its stage
+  int32_t cot_load, cot_kc;   // where the head cotangents are staged (-1: not in this item)
+  int32_t g_bd, g_b2;         // float offsets of the head biases whose gradients come from the staged cotangents (-1: none)
+  int32_t cost;               // bytes per tile and CTA (for the split of the pairs over the items)
+  W2Load load[3];
+  W2Mma mma[5];
+  W2Out out[6];
+};
+constexpr int kMaxW2Items = 10;
+constexpr int kW2RingBytes = 221184;          // 216 KB of operand stages per CTA (wgrad_pair.cuh)
+constexpr int kW2MaxPairs = 96;
+constexpr int kW2MaxUnits = 2;
+struct W2Unit { int32_t item, t0, t1; };      // one pair works on tiles [t0, t1) of `item`, then flushes its accumulators
+
 // layout ids: 0 = live, positional encoding (10, 4); 1 = live, pos_encoding=False; 2 / 3 = the same parameter layouts with a
 // ReLU density head instead of softplus -- what the reference's shipped (legacy) checkpoints evaluate once their weights
 // are remapped onto the live layer table (sfm-nerf_b200/legacy.py; SURVEY A.4, commented class NeRFModel.py:7-99).
@@ -105,9 +140,11 @@ struct ModelLayout {
   // ([row][8 x u32] = 4 KB each; bit c of a row = output channel c of that layer was > 0)
   int32_t st_pe, st_de, st_h[10], st_r1, st_mask, stash_tile_bytes;
   // per-tile dstash: dY0..dY9 (64 KB each), dY10 (32 KB), dsr fp32 [128][4]
-  int32_t ds_y[11], ds_sr, dstash_tile_bytes;
+  int32_t ds_y[11], ds_sr, ds_cot, dstash_tile_bytes;     // ds_cot: bf16 head cotangents [hi | lo][128 rows][8] (wgrad_pair.cuh)
   int32_t n_wgrad;
   WgradItem wg[kMaxWgradItems];
+  int32_t n_w2;
+  W2Item w2[kMaxW2Items];
 };
 
 enum { L_FC1 = 0, L_FC0 = 1, L_SKIP = 5, L_FC2_0 = 6, L_DENS = 9, L_FEAT = 10, L_RGB1 = 11, L_RGB2 = 12 };
@@ -146,6 +183,7 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
   for (int i = 0; i < 10; ++i) { m.ds_y[i] = dso; dso += kActBytes; }
   m.ds_y[10] = dso; dso += 16 * kKcoreBytes;
   m.ds_sr = dso; dso += 128 * 16;
+  m.ds_cot = dso; dso += 2 * kKcoreBytes;
   m.dstash_tile_bytes = dso;
 
   auto add = [](Program& p, Step st) {
@@ -233,7 +271,148 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
   wadd(L_FEAT, m.ds_y[9], 32, m.st_h[8], 256, 256, 0, true);
   wadd(L_RGB1, m.ds_y[10], 16, m.st_h[9], 256, 256, 0, true);
   wadd(L_RGB1, m.ds_y[10], 16, m.st_de, dir_n, m.dir_in, 256, false);
+
+  // ---- CTA-pair wgrad items ---------------------------------------------------------------
+  const int H = 16 * kKcoreBytes;                     // half of a 256-channel block: this CTA's 16 k-cores
+  auto seg = [](int off0, int off1, int bytes, bool ds0, bool ds1) {
+    W2Seg sg{}; sg.off[0] = off0; sg.off[1] = off1; sg.bytes = bytes; sg.from_dstash[0] = ds0; sg.from_dstash[1] = ds1; return sg;
+  };
+  auto half_seg = [&](int off, int bytes_total, bool ds) { return seg(off, off + bytes_total / 2, bytes_total / 2, ds, ds); };
+  auto mma = [](int a_load, int a_kc, int b_load, int b_kc, int n, int d_col) { W2Mma q{a_load, a_kc, b_load, b_kc, n, d_col}; return q; };
+  auto out = [](int kind, int d_col, int n_valid, int dst, int ld, int col0, int rb0, int rb1, int mask) {
+    W2Out o{}; o.kind = kind; o.d_col = d_col; o.n_valid = n_valid; o.dst = dst; o.ld = ld; o.col0 = col0;
+    o.row_base[0] = rb0; o.row_base[1] = rb1; o.rank_mask = mask; return o;
+  };
+  auto finish = [&](W2Item& it) {
+    it.cost = 0;
+    for (int l = 0; l < it.n_loads; ++l) {
+      it.load_off[l] = it.cost;
+      for (int g = 0; g < it.load[l].n_segs; ++g) it.cost += it.load[l].seg[g].bytes;
+    }
+    it.stage_bytes = it.cost;
+    it.depth = kW2RingBytes / it.stage_bytes;
+    if (it.depth > 3) it.depth = 3;
+    m.w2[m.n_w2++] = it;
+  };
+  auto plain = [&](int lin, int dy_off, int x_off) {               // dY_l x h_(l-1), 256 x 256
+    W2Item it{}; it.cot_load = -1; it.cot_kc = 0; it.g_bd = -1; it.g_b2 = -1;
+    it.n_loads = 2;
+    it.load[0].n_segs = 1; it.load[0].seg[0] = half_seg(dy_off, 2 * H, true);
+    it.load[1].n_segs = 1; it.load[1].seg[0] = half_seg(x_off, 2 * H, false);
+    it.n_mmas = 2; it.mma[0] = mma(0, 0, 1, 0, 256, 0); it.mma[1] = mma(0, 0, -1, 0, 16, 256);
+    it.n_outs = 2;
+    it.out[0] = out(W2_OUT_WEIGHT, 0, 256, m.w_off[lin], m.in_f[lin], 0, 0, 128, 3);
+    it.out[1] = out(W2_OUT_BIAS, 256, 1, m.b_off[lin], 0, 0, 0, 128, 3);
+    finish(it);
+  };
+  {   // skip_layer: dY5 x [h4 | PE], and fc1: dY0 x PE from the same staged PE half
+    W2Item it{}; it.cot_load = -1; it.g_bd = -1; it.g_b2 = -1;
+    const int pe_bytes = (pos_n / 8) * kKcoreBytes;                // PE channels used by the MMAs (64 or 16), split over the pair
+    it.n_loads = 3;
+    it.load[0].n_segs = 1; it.load[0].seg[0] = half_seg(m.ds_y[5], 2 * H, true);
+    it.load[1].n_segs = 1; it.load[1].seg[0] = half_seg(m.ds_y[0], 2 * H, true);
+    it.load[2].n_segs = 2; it.load[2].seg[0] = half_seg(m.st_h[4], 2 * H, false); it.load[2].seg[1] = half_seg(m.st_pe, pe_bytes, false);
+    it.n_mmas = 5;
+    it.mma[0] = mma(0, 0, 2, 0, 256, 0);            // dY5 x h4
+    it.mma[1] = mma(0, 0, 2, 16, pos_n, 256);       // dY5 x PE
+    it.mma[2] = mma(1, 0, 2, 16, pos_n, 320);       // dY0 x PE
+    it.mma[3] = mma(0, 0, -1, 0, 16, 384);          // bias of skip_layer
+    it.mma[4] = mma(1, 0, -1, 0, 16, 400);          // bias of fc1
+    it.n_outs = 5;
+    it.out[0] = out(W2_OUT_WEIGHT, 0, 256, m.w_off[L_SKIP], m.in_f[L_SKIP], 0, 0, 128, 3);
+    it.out[1] = out(W2_OUT_WEIGHT, 256, m.pos_in, m.w_off[L_SKIP], m.in_f[L_SKIP], 256, 0, 128, 3);
+    it.out[2] = out(W2_OUT_WEIGHT, 320, m.pos_in, m.w_off[L_FC1], m.in_f[L_FC1], 0, 0, 128, 3);
+    it.out[3] = out(W2_OUT_BIAS, 384, 1, m.b_off[L_SKIP], 0, 0, 0, 128, 3);
+    it.out[4] = out(W2_OUT_BIAS, 400, 1, m.b_off[L_FC1], 0, 0, 0, 128, 3);
+    finish(it);
+  }
+  for (int i = 0; i < 4; ++i) plain(L_FC0 + i, m.ds_y[1 + i], m.st_h[i]);
+  for (int i = 0; i < 3; ++i) plain(L_FC2_0 + i, m.ds_y[6 + i], m.st_h[5 + i]);
+  {   // feature_layer: dY9 x h8, and density_layer's head: h8 (as the M side) x cotangents
+    W2Item it{}; it.g_b2 = -1;
+    it.n_loads = 2;
+    it.load[0].n_segs = 1; it.load[0].seg[0] = half_seg(m.ds_y[9], 2 * H, true);
+    it.load[1].n_segs = 2; it.load[1].seg[0] = half_seg(m.st_h[8], 2 * H, false); it.load[1].seg[1] = half_seg(m.ds_cot, 2 * kKcoreBytes, true);
+    it.cot_load = 1; it.cot_kc = 16; it.g_bd = m.b_off[L_DENS];
+    it.n_mmas = 3;
+    it.mma[0] = mma(0, 0, 1, 0, 256, 0);
+    it.mma[1] = mma(1, 0, 1, 16, 16, 256);          // h8 x cot
+    it.mma[2] = mma(0, 0, -1, 0, 16, 272);
+    it.n_outs = 3;
+    it.out[0] = out(W2_OUT_WEIGHT, 0, 256, m.w_off[L_FEAT], m.in_f[L_FEAT], 0, 0, 128, 3);
+    it.out[1] = out(W2_OUT_HEAD, 256, 1, m.w_off[L_DENS], 0, 0, 0, 128, 3);
+    it.out[2] = out(W2_OUT_BIAS, 272, 1, m.b_off[L_FEAT], 0, 0, 0, 128, 3);
+    finish(it);
+  }
+  {   // rgb_layer1: leader rows = dY10 (128 ch) x [h9 | DE]; peer rows = r1 (128 ch) x cotangents = rgb_layer2's head
+    W2Item it{}; it.g_bd = -1;
+    const int de_bytes = (dir_n / 8) * kKcoreBytes;
+    it.n_loads = 2;
+    it.load[0].n_segs = 1; it.load[0].seg[0] = seg(m.ds_y[10], m.st_r1, H, true, false);
+    it.load[1].n_segs = 3; it.load[1].seg[0] = half_seg(m.st_h[9], 2 * H, false); it.load[1].seg[1] = half_seg(m.st_de, de_bytes, false);
+    it.load[1].seg[2] = half_seg(m.ds_cot, 2 * kKcoreBytes, true);
+    const int de_kc = dir_n / 16;                                  // DE k-cores per CTA
+    it.cot_load = 1; it.cot_kc = 16 + de_kc; it.g_b2 = m.b_off[L_RGB2];
+    it.n_mmas = 4;
+    it.mma[0] = mma(0, 0, 1, 0, 256, 0);
+    it.mma[1] = mma(0, 0, 1, 16, dir_n, 256);
+    it.mma[2] = mma(0, 0, 1, 16 + de_kc, 16, 288);
+    it.mma[3] = mma(0, 0, -1, 0, 16, 304);
+    it.n_outs = 4;
+    it.out[0] = out(W2_OUT_WEIGHT, 0, 256, m.w_off[L_RGB1], m.in_f[L_RGB1], 0, 0, 0, 1);
+    it.out[1] = out(W2_OUT_WEIGHT, 256, m.dir_in, m.w_off[L_RGB1], m.in_f[L_RGB1], 256, 0, 0, 1);
+    it.out[2] = out(W2_OUT_HEAD, 288, 3, m.w_off[L_RGB2], 128, 1, 0, 0, 2);
+    it.out[3] = out(W2_OUT_BIAS, 304, 1, m.b_off[L_RGB1], 0, 0, 0, 0, 1);
+    finish(it);
+  }
   return true;
+}
+
+// Split of the pair-wgrad work over `n_pairs` CTA pairs.  All (item, tile) work is laid on one line in item order, weighted by
+// the item's bytes per tile, and cut into n_pairs equal pieces; piece boundaries are rounded to whole tiles.  A pair gets a tile
+// range of one item, or the tail of one item and the head of the next (<= kW2MaxUnits units).  Returns the number of pairs used
+// (tiny inputs: one pair per item), or -1 if a piece would need more units than that.
+inline int w2_partition(const ModelLayout& m, int n_tiles, int n_pairs, int32_t* n_units, W2Unit (*unit)[kW2MaxUnits]) {
+  if (n_pairs > kW2MaxPairs) n_pairs = kW2MaxPairs;
+  if (n_tiles < 16 || n_pairs < m.n_w2) {
+    for (int i = 0; i < m.n_w2; ++i) { n_units[i] = 1; unit[i][0] = W2Unit{i, 0, n_tiles}; }
+    return m.n_w2;
+  }
+  double total = 0.0;
+  for (int i = 0; i < m.n_w2; ++i) total += (double)m.w2[i].cost * n_tiles;
+  int prev_item = 0, prev_tile = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    // position of the END of piece p on the line -> (item, tile)
+    int item = m.n_w2, tile = 0;
+    if (p + 1 < n_pairs) {
+      const double end = total * (p + 1) / n_pairs;
+      double start = 0.0;
+      for (item = 0; item < m.n_w2; ++item) {
+        const double span = (double)m.w2[item].cost * n_tiles;
+        if (end < start + span) break;
+        start += span;
+      }
+      if (item < m.n_w2) {
+        tile = (int)((end - start) / (double)m.w2[item].cost + 0.5);
+        if (tile >= n_tiles) { ++item; tile = 0; }
+      }
+    }
+    if (item < prev_item || (item == prev_item && tile < prev_tile)) { item = prev_item; tile = prev_tile; }   // monotone
+    int nu = 0;
+    int it = prev_item, t = prev_tile;
+    while (it < item || (it == item && t < tile)) {
+      const int t_end = (it == item) ? tile : n_tiles;
+      if (t_end > t) {
+        if (nu == kW2MaxUnits) return -1;
+        unit[p][nu++] = W2Unit{it, t, t_end};
+      }
+      if (it == item) break;
+      ++it; t = 0;
+    }
+    n_units[p] = nu;
+    prev_item = item; prev_tile = tile;
+  }
+  return n_pairs;
 }
 
 }  // namespace nerf

@@ -61,3 +61,13 @@ def test_c_host_train_loop_matches_python_trainer(tmp_path):
     tr.close()
     assert np.float32(c_losses[0]) == np.float32(py_losses[0])   # same device RNG stream, deterministic forward (%.9g round-trips fp32)
     np.testing.assert_allclose(c_losses, py_losses, rtol=2e-4)
+
+
+def test_pair_wgrad_work_split(tmp_path):
+    """The split of the weight-gradient work over CTA pairs (csrc/mlp_layout.cuh: w2_partition, plain C++): every (item, tile) exactly
+    once, at most two units per pair, heaviest pair within 1 % of the mean at the benchmark shape, ring / TMEM budgets of every item."""
+    exe = str(tmp_path / "w2_check")
+    subprocess.run(["g++", "-std=c++17", "-x", "c++", "-I", os.path.join(ROOT, "sfm-nerf_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "c_host", "w2_partition_check.cpp"), "-o", exe], check=True, capture_output=True, text=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
