@@ -71,6 +71,9 @@ constexpr int kMlpThreads = 384;
 #ifndef NERF_STASH_YIELD
 #define NERF_STASH_YIELD 0
 #endif
+#ifndef NERF_READBACK_BATCH
+#define NERF_READBACK_BATCH 8       // k-cores (16 B per row each) a read-back loop loads before it stores the first
+#endif
 #define NERF_BWD_STASH_BULK (NERF_BWD_STASH_MODE == 1)
 // A bulk store waits in the SAME in-order queue of the SM's copy engine as the weight-slab loads, and drains only as fast as
 // HBM takes the writes (all SMs store at once: ~23 B/clk per SM): one 64 KB store per tile stretched a layer of MMAs from 2,350
@@ -747,20 +750,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           // the tile would be one instruction, but its shared-memory reads halve the UMMA issue rate (measured).
           uint4* gdst = reinterpret_cast<uint4*>(stash_tile + st.stash_off) + row;
           uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          // NERF_READBACK_BATCH k-cores are loaded before the first is stored: ncu showed this loop waiting on one LDS at a time
+          // (short-scoreboard stalls on the first use of every load; ~100 cycles each under the UMMA's operand traffic).
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            if (ch * 32 < st.n) {
+          for (int g = 0; g < 32 / NERF_READBACK_BATCH; ++g) {
+            if (g * NERF_READBACK_BATCH * 8 < st.n) {
               if (kYield) { while (ro_flag[slot ^ 1] != 0u) __nanosleep(40); }       // let the other slot's read-out through
+              uint4 pk[NERF_READBACK_BATCH];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 pk;
+              for (int q = 0; q < NERF_READBACK_BATCH; ++q)
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "r"(s_act + (ch * 4 + q) * kKcoreBytes + row * 16));
-                __stcs(gdst + (ch * 4 + q) * 128, pk);               // streaming (evict-first) store: the hot weight images stay in L2
-                mw[ch] |= ((pk.x + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 0));
-                mw[ch] |= ((pk.y + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 1));
-                mw[ch] |= ((pk.z + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 2));
-                mw[ch] |= ((pk.w + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * q + 3));
+                             : "=r"(pk[q].x), "=r"(pk[q].y), "=r"(pk[q].z), "=r"(pk[q].w)
+                             : "r"(s_act + (g * NERF_READBACK_BATCH + q) * kKcoreBytes + row * 16));
+#pragma unroll
+              for (int q = 0; q < NERF_READBACK_BATCH; ++q) {
+                const int kc = g * NERF_READBACK_BATCH + q;        // k-core: 8 channels; 4 k-cores per 32-column mask chunk
+                __stcs(gdst + kc * 128, pk[q]);                    // streaming (evict-first) store: the hot weight images stay in L2
+                mw[kc >> 2] |= ((pk[q].x + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * (kc & 3) + 0));
+                mw[kc >> 2] |= ((pk[q].y + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * (kc & 3) + 1));
+                mw[kc >> 2] |= ((pk[q].z + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * (kc & 3) + 2));
+                mw[kc >> 2] |= ((pk[q].w + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * (kc & 3) + 3));
               }
             }
           }
@@ -772,15 +781,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           // dstash: this thread reads back the 16-byte pieces of ITS OWN row of the bf16 tile it has just written and streams them
           // to HBM, after the release -- the read-out loop above then touches shared memory only (1,030 cycles instead of 3,100)
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
+          for (int g = 0; g < 32 / NERF_READBACK_BATCH; ++g) {
             if (kYield) { while (ro_flag[slot ^ 1] != 0u) __nanosleep(40); }
+            uint4 pk[NERF_READBACK_BATCH];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 pk;
+            for (int q = 0; q < NERF_READBACK_BATCH; ++q)
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "r"(s_act + (ch * 4 + q) * kKcoreBytes + row * 16));
-              __stcs(g_out + (ch * 4 + q) * 128, pk);
-            }
+                           : "=r"(pk[q].x), "=r"(pk[q].y), "=r"(pk[q].z), "=r"(pk[q].w)
+                           : "r"(s_act + (g * NERF_READBACK_BATCH + q) * kKcoreBytes + row * 16));
+#pragma unroll
+            for (int q = 0; q < NERF_READBACK_BATCH; ++q) __stcs(g_out + (g * NERF_READBACK_BATCH + q) * 128, pk[q]);
           }
         }
       }
