@@ -275,6 +275,10 @@ int nerf_debug_trace(void* device_buffer);
  * 4 two threads / same accumulator).  cycles_host[0] = SM cycles for n_mma MMAs, cycles_host[1] = n_mma.
  * Synchronises the device and allocates; not part of the hot path. */
 int nerf_debug_umma_rate(int variant, int n_mma, long long* cycles_host);
+/* Diagnostics: how fast can `warps` warps of ONE CTA per SM stream 512-byte warp stores (16 B per lane, the stash store pattern)
+ * to HBM?  mode 0 st.global.cs from shared memory, 1 st.global, 2 st.global.cs from registers.  out_host[0] = max cycles over
+ * CTAs, [1] = bytes per CTA, [2] = elapsed ns.  device_buffer must hold sms * iters * warps * 512 bytes. */
+int nerf_debug_store_rate(int warps, int iters, int mode, void* device_buffer, long long buffer_bytes, long long* out_host);
 
 #endif
 

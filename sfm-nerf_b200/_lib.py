@@ -112,6 +112,7 @@ PROTOTYPES = {
 DIAG_PROTOTYPES = {
     "nerf_debug_umma_rate": (_I, [_I, _I, _P]),
     "nerf_debug_trace": (_I, [_P]),
+    "nerf_debug_store_rate": (_I, [_I, _I, _I, _P, C.c_longlong, _P]),
 }
 
 _lib = None

@@ -714,6 +714,33 @@ int nerf_debug_umma_rate(int variant, int n_mma, long long* cycles_host) {
   return e == cudaSuccess ? NERF_OK : (int)e;
 }
 
+// diagnostics: store-rate microbenchmark (selftest.cuh); out_host[0] = max cycles over CTAs, [1] = bytes per CTA, [2] = elapsed ns
+int nerf_debug_store_rate(int warps, int iters, int mode, void* device_buffer, long long buffer_bytes, long long* out_host) {
+  DeviceInfo* dev;
+  int rc = device_info(&dev);
+  if (rc != NERF_OK) return rc;
+  if (warps < 1 || warps > 32 || iters < 1 || !device_buffer || !out_host) return NERF_ERR_ARG;
+  if ((long long)dev->sms * iters * warps * 512 > buffer_bytes) return NERF_ERR_ARG;
+  long long* d = nullptr;
+  NERF_CUDA_TRY(cudaMalloc(&d, 2 * sizeof(long long)));
+  cudaMemset(d, 0, 2 * sizeof(long long));
+  cudaFuncSetAttribute(store_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  store_rate_kernel<<<dev->sms, warps * 32, 200 * 1024>>>(static_cast<uint4*>(device_buffer), iters, mode, d);   // warm-up
+  cudaMemset(d, 0, 2 * sizeof(long long));
+  cudaEventRecord(e0);
+  store_rate_kernel<<<dev->sms, warps * 32, 200 * 1024>>>(static_cast<uint4*>(device_buffer), iters, mode, d);
+  cudaEventRecord(e1);
+  cudaError_t e = cudaDeviceSynchronize();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (e == cudaSuccess) e = cudaMemcpy(out_host, d, 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+  out_host[2] = (long long)(ms * 1e6);
+  cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return e == cudaSuccess ? NERF_OK : (int)e;
+}
+
 #endif  // NERF_DIAGNOSTICS
 
 }  // extern "C"

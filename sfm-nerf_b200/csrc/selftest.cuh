@@ -269,6 +269,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) umma_pair_rate_
   if (warp == 0) tc::tmem_dealloc_pair(tmem, 512);
 }
 
+// Store-rate microbenchmark: one CTA per SM, `warps` warps; every warp instruction stores 512 contiguous bytes (16 B per lane,
+// like the stash / dstash stores of the MLP kernels) of a [row][16 B] piece read from shared memory.  mode 0: st.global.cs,
+// 1: st.global (default policy), 2: st.global.cs of a register value (no shared-memory read).  Each CTA streams through its own
+// region of `buf`.  result[0] = max cycles over CTAs, result[1] = bytes per CTA.
+__global__ void store_rate_kernel(uint4* __restrict__ buf, int iters, int mode, long long* __restrict__ result) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint4* sm = reinterpret_cast<uint4*>(smem);
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = make_uint4(i, i + 1, i + 2, i + 3);
+  __syncthreads();
+  uint4* base = buf + (size_t)blockIdx.x * (size_t)iters * warps * 32;
+  const long long t0 = clock64();
+  uint4 v = sm[threadIdx.x & 4095];
+  for (int it = 0; it < iters; ++it) {
+    if (mode != 2) v = sm[(it * 128 + warp * 32 + lane) & 4095];
+    uint4* dst = base + ((size_t)it * warps + warp) * 32 + lane;
+    if (mode == 1) *dst = v; else __stcs(dst, v);
+  }
+  __syncthreads();
+  const long long dt = clock64() - t0;
+  if (threadIdx.x == 0) {
+    atomicMax(reinterpret_cast<unsigned long long*>(result), (unsigned long long)dt);
+    result[1] = (long long)iters * warps * 512;
+  }
+}
 #endif  // NERF_DIAGNOSTICS
 
 }  // namespace nerf

@@ -17,15 +17,15 @@ if [ "$a" = "ref" ]; then
 fi
 if [ "$a" = "ncu" ]; then
   # only this library's kernels: the synthetic-scene generation in front of the bench is thousands of torch launches
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
-      --kernel-name 'regex:mlp_fused|wgrad_kernel|head_grad|pack_|adam_|composite_|train_batch|sample_z|raygen_|draw_pixels|mse_loss' \
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv \
+      --kernel-name 'regex:mlp_fused|wgrad|head_grad|pack_|adam_|composite_|train_batch|sample_z|raygen_|draw_pixels|mse_loss' \
       python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
   tail -c 300 gpurun_out/ncu_bench.log
 fi
 if [ "$a" = "full" ]; then
   # one full-section capture of each hot kernel (inference fwd, training fwd, dgrad, wgrad, head-grad) at the C2 shape
   python tools/profile_kernels.py > gpurun_out/profile_plain.log 2>&1 && \
-  ncu --set full --import-source on --clock-control none --kernel-name 'regex:mlp_fused|wgrad_kernel|head_grad' \
+  ncu --set full --import-source on --clock-control none --kernel-name 'regex:mlp_fused|wgrad' \
       --launch-skip 10 -c 5 -f -o gpurun_out/prof_r2 python tools/profile_kernels.py > gpurun_out/ncu_full.log 2>&1
   tail -2 gpurun_out/ncu_full.log
 fi

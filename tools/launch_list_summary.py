@@ -3,7 +3,7 @@ share of the listed time.  usage: python tools/launch_list_summary.py gpurun_out
 import collections, csv, re, sys
 
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 14 and r[12] == "gpu__time_duration.sum"]
-ours = re.compile(r"^(nerf::)?(mlp_fused_kernel|wgrad_kernel|head_grad_kernel|pack_|adam_|composite_|mse_loss|sample_z|raygen_|draw_pixels|train_batch|encode_kernel)")
+ours = re.compile(r"^(nerf::)?(mlp_fused_kernel|wgrad_pair_kernel|wgrad_kernel|head_grad_kernel|pack_|adam_|composite_|mse_loss|sample_z|raygen_|draw_pixels|train_batch|encode_kernel)")
 agg = collections.OrderedDict()
 prev = ""
 for r in rows:
@@ -11,8 +11,8 @@ for r in rows:
     name = re.sub(r"^void ", "", name).replace("nerf::", "")
     if len(sys.argv) > 2 and not ours.match(name):
         continue
-    if name == "mlp_fused_kernel<0>":       # the forward kernel serves the train step (after train_batch_kernel) and the renders
-        name += " [train step]" if prev == "train_batch_kernel" else " [render frames / inference]"
+    name = {"mlp_fused_kernel<0, 1>": "mlp_fused_kernel<FWD, train> [train step]", "mlp_fused_kernel<0, 0>": "mlp_fused_kernel<FWD, inference> [render frames]",
+            "mlp_fused_kernel<1, 0>": "mlp_fused_kernel<BWD> [dgrad]"}.get(name, name)
     prev = re.sub(r" \[.*", "", name)
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1
