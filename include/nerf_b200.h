@@ -49,6 +49,12 @@ enum {
   NERF_LAYOUT_LIVE_NOPE_RELU = 3
 };
 
+/* Layout id of NeRFmodel(embed_pos_L, embed_direction_L, 256, pos_encoding) (NeRFModel.py:102-140; the CLI's --n_pos_freq /
+ * --n_dirc_freq, train.py:796-797): the four ids above for the defaults, a generalised id for any other frequency counts
+ * 0..10 (3 * (2L + 1) <= 63 channels fit the 64-channel encoding tile).  density_relu != 0: ReLU density head.  NERF_ERR_LAYOUT
+ * for counts out of range.  Every entry point that takes `layout` accepts these ids. */
+int nerf_layout_id(int embed_pos_L, int embed_direction_L, int pos_encoding, int density_relu);
+
 int nerf_abi_version(void);
 const char* nerf_error_string(int code);
 /* 0 when the current CUDA device can run the kernels (sm_100), else NERF_ERR_ARCH / cudaError_t. */

@@ -67,16 +67,15 @@ class NeRFmodel(nn.Module):
     def layout_id(self) -> int:
         """Which fixed-function layout of libnerf_b200 this instance maps to (raises otherwise)."""
         if self.num_channels != 256:
-            raise NotImplementedError("libnerf_b200 kernels are built for num_channels=256 (the reference default)")
-        if self.pos_encoding:
-            if (self.embed_pos_L, self.embed_direction_L) != (10, 4):
-                raise NotImplementedError("libnerf_b200 kernels are built for embed_pos_L=10, embed_direction_L=4")
-            base = _lib.LAYOUT_LIVE_PE
-        else:
-            base = _lib.LAYOUT_LIVE_NOPE
+            raise NotImplementedError("libnerf_b200 kernels are built for num_channels=256 (the reference default, --hidden_size 256)")
         if self.density_activation not in ("softplus", "relu"):
             raise NotImplementedError("density_activation must be 'softplus' or 'relu'")
-        return base + (2 if self.density_activation == "relu" else 0)
+        lid = int(_lib.load().nerf_layout_id(int(self.embed_pos_L), int(self.embed_direction_L), 1 if self.pos_encoding else 0,
+                                             1 if self.density_activation == "relu" else 0))
+        if lid < 0:
+            raise NotImplementedError("libnerf_b200 supports embed_pos_L / embed_direction_L (--n_pos_freq / --n_dirc_freq) from 0 to 10: "
+                                      "the encoding must fit the 64-channel operand tile")
+        return lid
 
     def ordered_parameters(self):
         """The 26 parameter tensors in state_dict order (weight, bias per layer)."""

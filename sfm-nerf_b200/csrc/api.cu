@@ -1,6 +1,8 @@
 // api.cu -- the C ABI of libnerf_b200.so (include/nerf_b200.h).  Argument checking, launch
 // geometry and nothing else: every entry point enqueues sm_100a kernels on the caller's stream.
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -94,8 +96,18 @@ struct LayoutCache {
 };
 const ModelLayout* get_layout(int layout) {
   static const LayoutCache cache;
-  if (layout < 0 || layout >= kNumLayouts) return nullptr;
-  return &cache.m[layout];
+  if (layout >= 0 && layout < kNumLayouts) return &cache.m[layout];
+  if (layout < 0 || !(layout & kLayoutCustomBit)) return nullptr;
+  // other encoding frequencies (nerf_layout_id): built on first use, kept for the life of the process
+  static std::mutex mu;
+  static std::map<int, ModelLayout*> custom;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = custom.find(layout);
+  if (it != custom.end()) return it->second;
+  ModelLayout* m = new ModelLayout;
+  if (!build_model_layout(layout, *m)) { delete m; return nullptr; }
+  custom[layout] = m;
+  return m;
 }
 
 void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t n_rows) {
@@ -164,6 +176,11 @@ const char* nerf_error_string(int code) {
 int nerf_device_check(void) {
   DeviceInfo* dev;
   return device_info(&dev);
+}
+
+int nerf_layout_id(int embed_pos_L, int embed_direction_L, int pos_encoding, int density_relu) {
+  const int id = make_layout_id(embed_pos_L, embed_direction_L, pos_encoding, density_relu);
+  return id < 0 ? NERF_ERR_LAYOUT : id;
 }
 
 int64_t nerf_param_count(int layout) {

@@ -151,24 +151,27 @@ __device__ __forceinline__ void pe_sincos(const TurnsF& t, int level, float& s, 
 // Encodes v[3] with L levels into bf16 channels [v, sin0(v), cos0(v), ...] padded with zeros to
 // 8*NKC channels, stored at enc + kcore*2048 + row*16.  ONE: the last channel is the constant 1.0
 // (the K column the packed weight images pair with the bias).
-template <int L, int NKC, bool ONE>
-__device__ __forceinline__ void write_encoding(uint32_t enc_smem, int row, const float v[3], uint8_t* gdst) {
+// MAXL: the levels this instance is unrolled for; `L` (<= MAXL, warp-uniform) levels are evaluated, the rest stay zero.
+template <int MAXL, int NKC, bool ONE>
+__device__ __forceinline__ void write_encoding(uint32_t enc_smem, int row, const float v[3], uint8_t* gdst, int L) {
   float e[NKC * 8];
 #pragma unroll
   for (int i = 0; i < NKC * 8; ++i) e[i] = 0.0f;
   e[0] = v[0]; e[1] = v[1]; e[2] = v[2];
-  if (L > 0) {
+  if (MAXL > 0) {
     TurnsF t[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) t[k] = pe_turns_f(v[k]);
 #pragma unroll
-    for (int i = 0; i < L; ++i) {
+    for (int i = 0; i < MAXL; ++i) {
+      if (i < L) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        float s, c;
-        pe_sincos(t[k], i, s, c);
-        e[3 + 6 * i + k] = s;
-        e[6 + 6 * i + k] = c;
+        for (int k = 0; k < 3; ++k) {
+          float s, c;
+          pe_sincos(t[k], i, s, c);
+          e[3 + 6 * i + k] = s;
+          e[6 + 6 * i + k] = c;
+        }
       }
     }
   }
@@ -488,8 +491,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           }
         }
         uint8_t* g_pe = store_out ? stash_tile + a.st_pe : nullptr;
-        if (a.pos_L == 10) write_encoding<10, 8, true>(s_enc, row, p, g_pe);
-        else write_encoding<0, 8, true>(s_enc, row, p, g_pe);
+        if (a.pos_L > 0) write_encoding<10, 8, true>(s_enc, row, p, g_pe, a.pos_L);
+        else write_encoding<0, 8, true>(s_enc, row, p, g_pe, 0);
       } else {
         // backward prologue: d(rgb2 pre-act), d(density pre-act), dR1 = d_rgb_pre . W2 masked by r1 > 0
         float4 d = make_float4(0.f, 0.f, 0.f, 0.f), o = make_float4(0.f, 0.5f, 0.5f, 0.5f);
@@ -692,8 +695,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         if (MODE == MODE_FWD) {
           if (st.flags & EPI_WRITE_DIR) {              // ENC k-cores 0-3 <- direction encoding (used by rgb_layer1)
             uint8_t* g_de = store_out ? stash_tile + a.st_de : nullptr;
-            if (a.dir_L == 4) write_encoding<4, 4, false>(s_enc, row, dirv, g_de);
-            else write_encoding<0, 4, false>(s_enc, row, dirv, g_de);
+            // 27 channels (4 levels, the reference default) or fewer: k-cores 0-3, the constant-1 channel 63 of the position tile
+            // stays; more levels: the whole 64-channel tile with its own constant 1
+            if (a.dir_L > 4) write_encoding<10, 8, true>(s_enc, row, dirv, g_de, a.dir_L);
+            else if (a.dir_L > 0) write_encoding<4, 4, false>(s_enc, row, dirv, g_de, a.dir_L);
+            else write_encoding<0, 4, false>(s_enc, row, dirv, g_de, 0);
             tc::fence_proxy_async_smem();
           }
           // The two CUDA-core heads read this thread's row of the bf16 tile it has just written, AFTER the layer loop:

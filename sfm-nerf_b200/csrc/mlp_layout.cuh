@@ -121,6 +121,16 @@ struct W2Unit { int32_t item, t0, t1; };      // one pair works on tiles [t0, t1
 // ReLU density head instead of softplus -- what the reference's shipped (legacy) checkpoints evaluate once their weights
 // are remapped onto the live layer table (sfm-nerf_b200/legacy.py; SURVEY A.4, commented class NeRFModel.py:7-99).
 constexpr int kNumLayouts = 4;
+// Generalised ids (nerf_layout_id): bit 24 set, bits [8,16) = embed_pos_L, [16,24) = embed_direction_L (each 0..10: the encoding
+// must fit the 64-channel tile next to the constant-1 channel), bit 0 = pos_encoding off, bit 1 = ReLU density.
+constexpr int kLayoutCustomBit = 1 << 24;
+constexpr int kMaxEncodingL = 10;
+inline int make_layout_id(int pos_L, int dir_L, int pos_encoding, int density_relu) {
+  if (pos_L < 0 || dir_L < 0 || pos_L > kMaxEncodingL || dir_L > kMaxEncodingL) return -1;
+  if (!pos_encoding) return 1 + (density_relu ? 2 : 0);
+  if (pos_L == 10 && dir_L == 4) return density_relu ? 2 : 0;
+  return kLayoutCustomBit | (pos_L << 8) | (dir_L << 16) | (density_relu ? 2 : 0);
+}
 
 struct ModelLayout {
   int32_t layout;
@@ -150,13 +160,19 @@ struct ModelLayout {
 enum { L_FC1 = 0, L_FC0 = 1, L_SKIP = 5, L_FC2_0 = 6, L_DENS = 9, L_FEAT = 10, L_RGB1 = 11, L_RGB2 = 12 };
 
 inline bool build_model_layout(int layout, ModelLayout& m) {
-  if (layout < 0 || layout >= kNumLayouts) return false;
+  int pos_L = 10, dir_L = 4;
+  if (layout >= 0 && (layout & kLayoutCustomBit)) {
+    pos_L = (layout >> 8) & 0xff; dir_L = (layout >> 16) & 0xff;
+    if ((layout & ~(kLayoutCustomBit | 0xffff00 | 2)) != 0 || pos_L > kMaxEncodingL || dir_L > kMaxEncodingL) return false;
+  } else if (layout < 0 || layout >= kNumLayouts) {
+    return false;
+  }
   m = ModelLayout{};
   m.layout = layout;
-  m.density_relu = layout >= 2 ? 1 : 0;
+  m.density_relu = (layout & 2) ? 1 : 0;
   const bool pe = (layout & 1) == 0;
-  m.pos_L = pe ? 10 : 0; m.dir_L = pe ? 4 : 0;
-  m.pos_in = pe ? 63 : 3; m.dir_in = pe ? 27 : 3;
+  m.pos_L = pe ? pos_L : 0; m.dir_L = pe ? dir_L : 0;
+  m.pos_in = 3 * (2 * m.pos_L + 1); m.dir_in = 3 * (2 * m.dir_L + 1);       // NeRFModel.py:112-114 (3 when the encoding is off)
   const int C = 256;
   const int outs[kNumLinear] = {C, C, C, C, C, C, C, C, C, 1, C, 128, 3};
   const int ins[kNumLinear] = {m.pos_in, C, C, C, C, C + m.pos_in, C, C, C, C, C, C + m.dir_in, 128};
@@ -174,7 +190,7 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
   // stash
   int so = 0;
   m.st_pe = so; so += 8 * kKcoreBytes;
-  m.st_de = so; so += 4 * kKcoreBytes;
+  m.st_de = so; so += (dir_ks > 2 ? 8 : 4) * kKcoreBytes;                  // direction-encoding tile: 32 channels (L <= 4) or 64
   for (int i = 0; i < 10; ++i) { m.st_h[i] = so; so += kActBytes; }
   m.st_r1 = so; so += 16 * kKcoreBytes;
   m.st_mask = so; so += 11 * 4096;
@@ -356,13 +372,14 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
     it.n_mmas = 4;
     it.mma[0] = mma(0, 0, 1, 0, 256, 0);
     it.mma[1] = mma(0, 0, 1, 16, dir_n, 256);
-    it.mma[2] = mma(0, 0, 1, 16 + de_kc, 16, 288);
-    it.mma[3] = mma(0, 0, -1, 0, 16, 304);
+    const int d_cot = 256 + dir_n, d_bias = d_cot + 16;            // TMEM columns behind the direction block
+    it.mma[2] = mma(0, 0, 1, 16 + de_kc, 16, d_cot);
+    it.mma[3] = mma(0, 0, -1, 0, 16, d_bias);
     it.n_outs = 4;
     it.out[0] = out(W2_OUT_WEIGHT, 0, 256, m.w_off[L_RGB1], m.in_f[L_RGB1], 0, 0, 0, 1);
     it.out[1] = out(W2_OUT_WEIGHT, 256, m.dir_in, m.w_off[L_RGB1], m.in_f[L_RGB1], 256, 0, 0, 1);
-    it.out[2] = out(W2_OUT_HEAD, 288, 3, m.w_off[L_RGB2], 128, 1, 0, 0, 2);
-    it.out[3] = out(W2_OUT_BIAS, 304, 1, m.b_off[L_RGB1], 0, 0, 0, 0, 1);
+    it.out[2] = out(W2_OUT_HEAD, d_cot, 3, m.w_off[L_RGB2], 128, 1, 0, 0, 2);
+    it.out[3] = out(W2_OUT_BIAS, d_bias, 1, m.b_off[L_RGB1], 0, 0, 0, 0, 1);
     finish(it);
   }
   return true;

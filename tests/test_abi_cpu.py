@@ -99,8 +99,16 @@ def test_abi_queries_without_gpu(libmod):
 def test_param_offsets_follow_state_dict_order(libmod):
     import sfmnerf_b200 as s
     lib = libmod.load()
-    for layout, kw in ((0, {}), (1, {"pos_encoding": False})):
+    cases = [(0, {}), (1, {"pos_encoding": False})]
+    for pl, dl in ((6, 2), (10, 10), (0, 3), (4, 4)):                  # --n_pos_freq / --n_dirc_freq: generalised layout ids
+        lid = lib.nerf_layout_id(pl, dl, 1, 0)
+        assert lid > 3
+        cases.append((lid, {"embed_pos_L": pl, "embed_direction_L": dl}))
+    assert lib.nerf_layout_id(10, 4, 1, 0) == 0 and lib.nerf_layout_id(10, 4, 1, 1) == 2 and lib.nerf_layout_id(7, 7, 0, 0) == 1
+    assert lib.nerf_layout_id(11, 4, 1, 0) == -4 and lib.nerf_layout_id(10, -1, 1, 0) == -4
+    for layout, kw in cases:
         m = s.NeRFmodel(**kw)
+        assert m.layout_id == layout
         off = 0
         for i, p in enumerate(m.ordered_parameters()):
             assert lib.nerf_param_offset(layout, i) == off
