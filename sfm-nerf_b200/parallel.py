@@ -93,6 +93,18 @@ class GradExchange:
                 if want in ("p2p", "nvls"):
                     raise
                 self.mode, self.why, self.handle = "nccl", f"{type(e).__name__}: {e}", None
+        # The mode must be the SAME on every rank (a rank alone in dist.all_reduce while the others wait in the symmetric-memory
+        # barrier would hang, or read gradients that were never exchanged): agree on the weakest mode any rank reached.
+        if self.world > 1 and self.device.type == "cuda" and want != "nccl" and dist.is_available() and dist.is_initialized():
+            code = {"nccl": 0, "p2p": 1, "nvls": 2}[self.mode]
+            t = torch.tensor([code], dtype=torch.int32, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            agreed = ("nccl", "p2p", "nvls")[int(t.item())]
+            if agreed != self.mode:
+                self.why = (self.why + "; " if self.why else "") + f"another rank only reached '{agreed}' (this rank: '{self.mode}')"
+                self.mode = agreed
+                if agreed == "nccl":
+                    self.handle = None
         if self.handle is None:
             self.buf = torch.zeros(2 * self.n_pad, dtype=torch.float32, device=self.device)
 

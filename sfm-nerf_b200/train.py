@@ -228,11 +228,14 @@ def train(images, poses, camera_info, args):
     val_every = int(getattr(args, "val_every", 1000))
     running, last = 0.0, float("nan")
     loss_acc = torch.zeros(1, device=dev)
+    n_acc = 0                                       # steps accumulated since the last read (the first window is not log_every long)
     for iteration in range(start_iter, int(args.max_iters)):
         loss_acc += trainer.step()                  # no host sync inside the loop body
+        n_acc += 1
         if iteration % log_every == 0 and iteration > start_iter:
-            running = loss_acc.item() / log_every   # one D2H read per log_every steps
+            running = loss_acc.item() / n_acc       # one D2H read per log_every steps
             loss_acc.zero_()
+            n_acc = 0
             last = running
             if writer:
                 writer.add_scalar("Loss/train_avg", running, iteration)
@@ -247,9 +250,12 @@ def train(images, poses, camera_info, args):
             trainer.st.frozen = True
             if iteration % int(args.save_ckpt_iter) == 0:
                 os.makedirs(args.checkpoint_path, exist_ok=True)
-                save_checkpoint(os.path.join(args.checkpoint_path, f"model_{iteration:06d}.pth"), model, trainer, iteration, last)
+                # 'loss' of a checkpoint: the last step's loss like the reference's loss.item() (train.py:516); saving is a sync point anyway
+                save_checkpoint(os.path.join(args.checkpoint_path, f"model_{iteration:06d}.pth"), model, trainer, iteration,
+                                float(trainer.loss.item()))
     os.makedirs(args.checkpoint_path, exist_ok=True)
-    save_checkpoint(os.path.join(args.checkpoint_path, "final_model.pth"), model, trainer, int(args.max_iters) - 1, last)
+    save_checkpoint(os.path.join(args.checkpoint_path, "final_model.pth"), model, trainer, int(args.max_iters) - 1,
+                    float(trainer.loss.item()))
     trainer.close()
     if writer:
         writer.close()
