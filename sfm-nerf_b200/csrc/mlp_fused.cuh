@@ -71,6 +71,9 @@ constexpr int kMlpThreads = 384;
 #ifndef NERF_STASH_YIELD
 #define NERF_STASH_YIELD 0
 #endif
+#ifndef NERF_SLOT_OFFSET
+#define NERF_SLOT_OFFSET 0          // layers by which tile slot 1 trails tile slot 0 (see the sequence comment in the kernel)
+#endif
 #ifndef NERF_READBACK_BATCH
 #define NERF_READBACK_BATCH 8       // k-cores (16 B per row each) a read-back loop loads before it stores the first
 #endif
@@ -237,6 +240,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   const Program& P = a.prog;
   const int n_quads = (a.n_tiles + 3) >> 2;            // 4 tiles per cluster iteration: tile = 4*quad + 2*slot + rank
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  // The MMA issuer, the loaders and the relays walk ONE sequence of (tile slot, layer) passes: tick t = 0, 1, ... with slot 0 on
+  // its pass t and slot 1 on its pass t - NERF_SLOT_OFFSET (pass p = layer p % n_steps of this cluster's quad p / n_steps).  With
+  // offset 0 both slots work on the same layer of the same quad; with an offset of half a quad one slot's store-free phases
+  // (encoding prologue, the K = 64 first layer, the N = 128 last layer and its heads) fall into the other slot's store-bound layers.
+  const int n_local = cluster_id < n_quads ? (n_quads - cluster_id + n_clusters - 1) / n_clusters : 0;   // quads of this cluster
+  const int n_pass = n_local * P.n_steps;
+  const int n_ticks = n_pass > 0 ? n_pass + NERF_SLOT_OFFSET : 0;
 
   if (warp == 8 || warp == 10) {
     // ===================== weight loaders (both CTAs: this CTA's N/2 rows of every slab, every layer twice) ==========
@@ -247,28 +257,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
     // complete while that arrival is pending, so the order is free) to get it on its way ~130 cycles earlier.
     const int which = (warp - 8) >> 1;
     const uint64_t keep_in_l2 = tc::l2_policy_evict_last();    // the 2.6 MB of weight images are re-read by every CTA, all the time
-    uint32_t it0 = 0, chunk = 0;                         // slabs issued before the current (layer, pass); trip counter
-    for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
-      for (int si = 0; si < P.n_steps; ++si) {
-        const Step& st = P.s[si];
+    uint32_t it0 = 0, chunk = 0;                         // slabs issued before the current pass; trip counter
+    for (int t = 0; t < n_ticks; ++t) {
+      for (int slot = 0; slot < 2; ++slot) {             // slot 0's pass of this tick, then slot 1's
+        const int ps = t - slot * NERF_SLOT_OFFSET;
+        if (ps < 0 || ps >= n_pass) continue;
+        const Step& st = P.s[ps % P.n_steps];
         const uint32_t bytes = (uint32_t)st.n * 16u;
         const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
         const uint8_t* src = a.packed + st.w_off + rank * bytes;
-        for (int pass = 0; pass < 2; ++pass) {           // slot 0's pass over the layer, then slot 1's
-          for (int k0 = 0; k0 < total; k0 += kLoadBatch, ++chunk) {
-            if ((int)(chunk & 1u) != which) continue;
-            const int k = k0 + lane;
-            if (lane < kLoadBatch && k < total) {
-              const uint32_t it = it0 + (uint32_t)k;
-              const uint32_t rs = it % kRingSlots, ph = (it / kRingSlots) & 1u;
-              tc::mbar_wait(bar_empty + 8 * (rs | (uint32_t)(kCommitGroup - 1)), ph ^ 1u);   // slots are released in groups
-              tc::bulk_g2s_hint(s_ring + rs * kRingSlotBytes, src + (size_t)k * (2u * bytes), bytes, bar_full + 8 * rs, keep_in_l2);
-              tc::mbar_arrive_expect_tx(bar_full + 8 * rs, bytes);
-            }
-            __syncwarp();
+        for (int k0 = 0; k0 < total; k0 += kLoadBatch, ++chunk) {
+          if ((int)(chunk & 1u) != which) continue;
+          const int k = k0 + lane;
+          if (lane < kLoadBatch && k < total) {
+            const uint32_t it = it0 + (uint32_t)k;
+            const uint32_t rs = it % kRingSlots, ph = (it / kRingSlots) & 1u;
+            tc::mbar_wait(bar_empty + 8 * (rs | (uint32_t)(kCommitGroup - 1)), ph ^ 1u);   // slots are released in groups
+            tc::bulk_g2s_hint(s_ring + rs * kRingSlotBytes, src + (size_t)k * (2u * bytes), bytes, bar_full + 8 * rs, keep_in_l2);
+            tc::mbar_arrive_expect_tx(bar_full + 8 * rs, bytes);
           }
-          it0 += (uint32_t)total;
+          __syncwarp();
         }
+        it0 += (uint32_t)total;
       }
     }
     if (warp == 8 && lane == 0) {
@@ -292,23 +302,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
     const int which = (warp - 9) >> 1;
     const uint32_t leader_full = tc::mapa(bar_full, 0);
     uint32_t it0 = 0, chunk = 0;
-    for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
-      for (int si = 0; si < P.n_steps; ++si) {
-        const int total = P.s[si].act_ksteps + P.s[si].enc_ksteps + P.s[si].bias_kstep;
-        for (int pass = 0; pass < 2; ++pass) {
-          for (int k0 = 0; k0 < total; k0 += kLoadBatch, ++chunk) {
-            if ((int)(chunk & 1u) != which) continue;
-            const int k = k0 + lane;
-            if (lane < kLoadBatch && k < total) {
-              const uint32_t it = it0 + (uint32_t)k;
-              const uint32_t rs = it % kRingSlots;
-              tc::mbar_wait(bar_full + 8 * rs, (it / kRingSlots) & 1u);
-              tc::mbar_arrive_cluster(leader_full + 8 * rs);
-            }
-            __syncwarp();
+    for (int t = 0; t < n_ticks; ++t) {
+      for (int slot = 0; slot < 2; ++slot) {
+        const int ps = t - slot * NERF_SLOT_OFFSET;
+        if (ps < 0 || ps >= n_pass) continue;
+        const Step& st = P.s[ps % P.n_steps];
+        const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
+        for (int k0 = 0; k0 < total; k0 += kLoadBatch, ++chunk) {
+          if ((int)(chunk & 1u) != which) continue;
+          const int k = k0 + lane;
+          if (lane < kLoadBatch && k < total) {
+            const uint32_t it = it0 + (uint32_t)k;
+            const uint32_t rs = it % kRingSlots;
+            tc::mbar_wait(bar_full + 8 * rs, (it / kRingSlots) & 1u);
+            tc::mbar_arrive_cluster(leader_full + 8 * rs);
           }
-          it0 += (uint32_t)total;
+          __syncwarp();
         }
+        it0 += (uint32_t)total;
       }
     }
   } else if (warp == 9) {
@@ -328,15 +339,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
     const uint32_t ring_lo = (s_ring & 0x3FFFFu) >> 4;
     constexpr uint32_t kStepLo = (2 * kKcoreBytes) >> 4;                                    // A descriptor advance per k-step
     constexpr uint32_t kSlabLo = kRingSlotBytes >> 4;
-    uint32_t rs = 0, par = 0, act_phase = 0;                       // ring slot / parity of the next slab
+    uint32_t rs = 0, par = 0;                                      // ring slot / parity of the next slab
 
-    for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
-      for (int si = 0; si < P.n_steps; ++si, ++act_phase) {
-        const int n = P.s[si].n, act_ks = P.s[si].act_ksteps, enc_ks = P.s[si].enc_ksteps, bias_ks = P.s[si].bias_kstep;
-        const uint32_t idesc = tc::umma_idesc_bf16(256, n, 0, 0);
-        const uint32_t b_lo = ((((uint32_t)n * 8u) >> 4) << 16) | ring_lo;      // LBO = (N/2 rows) * 16 B
+    for (int t = 0; t < n_ticks; ++t) {
+      {
 #pragma unroll 1
         for (int slot = 0; slot < 2; ++slot) {
+          const int ps = t - slot * NERF_SLOT_OFFSET;                // this slot's pass: its act_ready barrier is in phase ps
+          if (ps < 0 || ps >= n_pass) continue;
+          const int si = ps % P.n_steps;
+          const uint32_t act_phase = (uint32_t)ps;
+          const int n = P.s[si].n, act_ks = P.s[si].act_ksteps, enc_ks = P.s[si].enc_ksteps, bias_ks = P.s[si].bias_kstep;
+          const uint32_t idesc = tc::umma_idesc_bf16(256, n, 0, 0);
+          const uint32_t b_lo = ((((uint32_t)n * 8u) >> 4) << 16) | ring_lo;      // LBO = (N/2 rows) * 16 B
           const uint32_t act_lo = a_lbo | (((s_base + MlpSmem::kAct + slot * kActBytes) & 0x3FFFFu) >> 4);
           const uint32_t enc_lo = a_lbo | (((s_base + MlpSmem::kEnc + slot * kEncBytes) & 0x3FFFFu) >> 4);
           const uint32_t d_tmem = tmem_base + 256 * slot;
@@ -344,7 +359,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           tc::tc_fence_after();
 #ifdef NERF_DIAGNOSTICS
           long long* tr = (a.trace != nullptr && blockIdx.x == 0 && lane == 0)
-                              ? a.trace + ((size_t)((quad / n_clusters) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
+                              ? a.trace + ((size_t)((ps / P.n_steps) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
           if (tr) tr[0] = clock64();
 #endif
           int k_done = 0;

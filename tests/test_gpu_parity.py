@@ -605,6 +605,37 @@ def test_other_encoding_frequencies(pkg, orc, pos_L, dir_L):
     assert abs(l0 - loss_ref.item()) < 2e-3 and bool(torch.isfinite(m.fc1.weight).all())
 
 
+def test_training_with_long_rays(pkg, orc, model_pe, sd_pe256):
+    """--n_sample above 256 (the reference trains with any sample count; round 1 refused the compositing backward): render +
+    backward through autograd and one fused train step with 320 samples per ray against the oracle."""
+    gen = torch.Generator().manual_seed(31)
+    cam = orc.make_camera_info(32, 32)
+    pose = orc.look_at_pose(20.0, -35.0)
+    px = torch.randint(0, 32, (20, 2), generator=gen).numpy()
+    rays = orc.rays_from_indices(np.zeros((1, 32, 32, 3)), pose[None], cam, np.zeros(20, int), px[:, 0], px[:, 1])
+    o, d = torch.tensor(rays[:, 0:3]), torch.tensor(rays[:, 3:6])
+    target = torch.rand(20, 3, generator=gen)
+    S = 320
+    loss_ref, g_ref = orc.loss_and_grads(sd_pe256, o, d, target, S)
+    _, g_bf = orc.loss_and_grads(sd_pe256, o, d, target, S, operand_dtype=torch.bfloat16)
+    model_pe.zero_grad()
+    loss = pkg.loss(pkg.render(model_pe, o.cuda(), d.cuda(), _ns(n_sample=S, perturb=False)), target.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-3
+    for name, p in model_pe.named_parameters():
+        rel_bf = float((p.grad.cpu() - g_bf[name]).norm() / (g_bf[name].norm() + 1e-30))
+        rel_norm = abs(float(p.grad.cpu().norm() - g_ref[name].norm())) / float(g_ref[name].norm() + 1e-30)
+        assert rel_bf < GRAD_REL_TOL and rel_norm < 5e-2, (name, rel_bf, rel_norm)
+    model_pe.zero_grad()
+    m = pkg.NeRFmodel().cuda()
+    m.load_state_dict(sd_pe256)
+    tr = pkg.engine.Trainer(m, None, None, cam, 20, S, perturb=False)
+    l0 = float(tr.step(rays=(o.cuda(), d.cuda(), target.cuda())).item())
+    l1 = float(tr.step(rays=torch.cat([o, d, target], 1).contiguous().cuda()).item())               # [N,9] array: the one-call path too
+    tr.close()
+    assert abs(l0 - loss_ref.item()) < 1e-3 and np.isfinite(l1) and l1 < l0 + 1e-3
+
+
 def test_two_host_threads_train_concurrently(pkg, orc, sd_pe256):
     """include/nerf_b200.h: re-entrant and thread-safe.  Two host threads, each on its own stream, run whole train steps (every
     kernel of the path, including the fork / join of the head-gradient kernel onto the per-thread helper stream) at the same time;
