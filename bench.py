@@ -552,6 +552,10 @@ def run_ours(args):
         if name in traffic_alg:
             kern[name]["gbs"] = round(traffic_alg[name] / ms / 1e6, 1)
             kern[name]["hbm_frac"] = round(traffic_alg[name] / ms / 1e6 / peaks["hbm"], 4)
+        if name == "adam_reduce":      # every rank pulls the (world - 1) remote copies of the 2.6 MB gradient through NVLink while it updates
+            n_par = trainer.st.n_params
+            kern[name]["nvlink_bytes_in_per_rank"] = 4 * n_par * (world - 1)
+            kern[name]["nvlink_gbs_in_per_rank"] = round(4 * n_par * (world - 1) / ms / 1e6, 1)
     dom = max(work, key=lambda k: kern[k]["ms"])
     measured = {}
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")

@@ -560,16 +560,19 @@ class Trainer:
                 ex.barrier()
             peers, mc = ex.peer_pointers(self.iteration)
             self.iteration += 1
-            call("nerf_adam_step_reduce", ptr(st.flat), peers, self.world, mc, ptr(self.exp_avg), ptr(self.exp_avg_sq), st.n_params,
-                 lr, self.betas[0], self.betas[1], self.eps, self.iteration, parallel.mean_scale(self.world), stream_ptr())
+            with _timed(timers, "adam_reduce"):        # Adam reading the gradient sum over ranks through NVLink (multimem / peer loads)
+                call("nerf_adam_step_reduce", ptr(st.flat), peers, self.world, mc, ptr(self.exp_avg), ptr(self.exp_avg_sq), st.n_params,
+                     lr, self.betas[0], self.betas[1], self.eps, self.iteration, parallel.mean_scale(self.world), stream_ptr())
         else:
             if self.world > 1:
                 with _timed(timers, "allreduce"):
                     parallel.allreduce_sum_(self.grads, self.pg)
             self.iteration += 1
-            call("nerf_adam_step", ptr(st.flat), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), st.n_params,
-                 lr, self.betas[0], self.betas[1], self.eps, self.iteration, parallel.mean_scale(self.world), stream_ptr())
-        st.pack()
+            with _timed(timers, "adam"):
+                call("nerf_adam_step", ptr(st.flat), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), st.n_params,
+                     lr, self.betas[0], self.betas[1], self.eps, self.iteration, parallel.mean_scale(self.world), stream_ptr())
+        with _timed(timers, "pack"):
+            st.pack()
         launches += 2                               # adam, pack
         self.launches_per_step = launches
         return float(self.loss.item()) if loss_to_host else self.loss
