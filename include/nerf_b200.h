@@ -49,11 +49,12 @@ enum {
   NERF_LAYOUT_LIVE_NOPE_RELU = 3
 };
 
-/* Layout id of NeRFmodel(embed_pos_L, embed_direction_L, 256, pos_encoding) (NeRFModel.py:102-140; the CLI's --n_pos_freq /
- * --n_dirc_freq, train.py:796-797): the four ids above for the defaults, a generalised id for any other frequency counts
- * 0..10 (3 * (2L + 1) <= 63 channels fit the 64-channel encoding tile).  density_relu != 0: ReLU density head.  NERF_ERR_LAYOUT
- * for counts out of range.  Every entry point that takes `layout` accepts these ids. */
-int nerf_layout_id(int embed_pos_L, int embed_direction_L, int pos_encoding, int density_relu);
+/* Layout id of NeRFmodel(embed_pos_L, embed_direction_L, num_channels, pos_encoding) (NeRFModel.py:102-140; the CLI's
+ * --n_pos_freq / --n_dirc_freq / --hidden_size, train.py:796-797, 813): the four ids above for the defaults, a generalised id for
+ * any other frequency counts 0..10 (3 * (2L + 1) <= 63 channels fit the 64-channel encoding tile) and for num_channels 128
+ * (256 and 128 are built).  density_relu != 0: ReLU density head.  NERF_ERR_LAYOUT for anything else.  Every entry point that
+ * takes `layout` accepts these ids. */
+int nerf_layout_id(int embed_pos_L, int embed_direction_L, int pos_encoding, int density_relu, int num_channels);
 
 int nerf_abi_version(void);
 const char* nerf_error_string(int code);

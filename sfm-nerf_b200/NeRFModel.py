@@ -66,12 +66,12 @@ class NeRFmodel(nn.Module):
     @property
     def layout_id(self) -> int:
         """Which fixed-function layout of libnerf_b200 this instance maps to (raises otherwise)."""
-        if self.num_channels != 256:
-            raise NotImplementedError("libnerf_b200 kernels are built for num_channels=256 (the reference default, --hidden_size 256)")
+        if self.num_channels not in (256, 128):
+            raise NotImplementedError("libnerf_b200 kernels are built for num_channels 256 (the reference default) and 128 (--hidden_size)")
         if self.density_activation not in ("softplus", "relu"):
             raise NotImplementedError("density_activation must be 'softplus' or 'relu'")
         lid = int(_lib.load().nerf_layout_id(int(self.embed_pos_L), int(self.embed_direction_L), 1 if self.pos_encoding else 0,
-                                             1 if self.density_activation == "relu" else 0))
+                                             1 if self.density_activation == "relu" else 0, int(self.num_channels)))
         if lid < 0:
             raise NotImplementedError("libnerf_b200 supports embed_pos_L / embed_direction_L (--n_pos_freq / --n_dirc_freq) from 0 to 10: "
                                       "the encoding must fit the 64-channel operand tile")

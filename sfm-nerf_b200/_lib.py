@@ -78,7 +78,7 @@ PROTOTYPES = {
     "nerf_abi_version": (_I, []),
     "nerf_error_string": (C.c_char_p, [_I]),
     "nerf_device_check": (_I, []),
-    "nerf_layout_id": (_I, [_I, _I, _I, _I]),
+    "nerf_layout_id": (_I, [_I, _I, _I, _I, _I]),
     "nerf_param_count": (_L, [_I]),
     "nerf_param_offset": (_L, [_I, _I]),
     "nerf_raygen_image": (_I, [_P, _I, _D, _D, _D, _D, _I, _I, _L, _L, _P, _P, _P]),

@@ -114,7 +114,7 @@ void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t
   std::memset(&a, 0, sizeof(a));
   a.packed = static_cast<const uint8_t*>(packed);
   a.small = reinterpret_cast<const float*>(a.packed + m.small_off);
-  a.pos_L = m.pos_L; a.dir_L = m.dir_L; a.density_relu = m.density_relu;
+  a.pos_L = m.pos_L; a.dir_L = m.dir_L; a.density_relu = m.density_relu; a.c_kcores = m.hidden / 8;
   a.sm_wd = m.sm_wd; a.sm_bd = m.sm_bd; a.sm_w2 = m.sm_w2; a.sm_b2 = m.sm_b2;
   a.n_rows = n_rows;
   a.n_tiles = (int)((n_rows + 127) / 128);
@@ -178,8 +178,8 @@ int nerf_device_check(void) {
   return device_info(&dev);
 }
 
-int nerf_layout_id(int embed_pos_L, int embed_direction_L, int pos_encoding, int density_relu) {
-  const int id = make_layout_id(embed_pos_L, embed_direction_L, pos_encoding, density_relu);
+int nerf_layout_id(int embed_pos_L, int embed_direction_L, int pos_encoding, int density_relu, int num_channels) {
+  const int id = make_layout_id(embed_pos_L, embed_direction_L, pos_encoding, density_relu, num_channels);
   return id < 0 ? NERF_ERR_LAYOUT : id;
 }
 
@@ -320,6 +320,7 @@ static int launch_pack(const float* params, int layout, void* packed, unsigned l
   if (!nerf_aligned(packed, 16)) return NERF_ERR_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
   PackSmallArgs p{};
+  p.hidden = m->hidden;
   p.wd_src = m->w_off[L_DENS]; p.bd_src = m->b_off[L_DENS]; p.w2_src = m->w_off[L_RGB2]; p.b2_src = m->b_off[L_RGB2];
   p.sm_wd = m->sm_wd; p.sm_bd = m->sm_bd; p.sm_w2 = m->sm_w2; p.sm_b2 = m->sm_b2;
   // one launch: grid.y = forward steps, dgrad steps, then one row of blocks for the fp32 head table

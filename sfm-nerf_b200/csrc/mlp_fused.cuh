@@ -99,6 +99,7 @@ struct MlpArgs {
   int32_t n_sample;
   int32_t pos_L, dir_L;
   int32_t density_relu;      // density head activation: 1 = ReLU (legacy checkpoints), 0 = softplus
+  int32_t c_kcores;          // hidden width / 8: k-cores of an activation tile that hold data (32 or 16)
   int32_t sm_wd, sm_bd, sm_w2, sm_b2;
   int64_t n_rows;
   int32_t n_tiles;
@@ -724,7 +725,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             const float4* wd = reinterpret_cast<const float4*>(sm + a.sm_wd);
             float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll 8
-            for (int kc = 0; kc < 32; ++kc) {
+            for (int kc = 0; kc < a.c_kcores; ++kc) {       // the hidden channels only: k-cores beyond them hold stale shared memory
               uint32_t x0, x1, x2, x3;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(s_act + kc * kKcoreBytes + row * 16));
               const float4 wa = wd[2 * kc], wb = wd[2 * kc + 1];
@@ -859,12 +860,13 @@ __device__ __forceinline__ void pack_image_step(const float* __restrict__ params
 }
 
 struct PackSmallArgs {
+  int32_t hidden;
   int32_t wd_src, bd_src, w2_src, b2_src;
   int32_t sm_wd, sm_bd, sm_w2, sm_b2;
 };
 __device__ __forceinline__ void pack_small(const float* __restrict__ params, const PackSmallArgs& p, float* __restrict__ small) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 256) small[p.sm_wd + i] = params[p.wd_src + i];
+  if (i < 256) small[p.sm_wd + i] = i < p.hidden ? params[p.wd_src + i] : 0.0f;
   if (i < 384) small[p.sm_w2 + i] = params[p.w2_src + i];
   if (i < 3) small[p.sm_b2 + i] = params[p.b2_src + i];
   if (i == 0) { small[p.sm_bd] = params[p.bd_src]; small[p.sm_bd + 1] = 0.f; small[p.sm_bd + 2] = 0.f; small[p.sm_bd + 3] = 0.f; small[p.sm_b2 + 3] = 0.f; }

@@ -122,19 +122,23 @@ struct W2Unit { int32_t item, t0, t1; };      // one pair works on tiles [t0, t1
 // are remapped onto the live layer table (sfm-nerf_b200/legacy.py; SURVEY A.4, commented class NeRFModel.py:7-99).
 constexpr int kNumLayouts = 4;
 // Generalised ids (nerf_layout_id): bit 24 set, bits [8,16) = embed_pos_L, [16,24) = embed_direction_L (each 0..10: the encoding
-// must fit the 64-channel tile next to the constant-1 channel), bit 0 = pos_encoding off, bit 1 = ReLU density.
+// must fit the 64-channel tile next to the constant-1 channel), bit 0 = pos_encoding off, bit 1 = ReLU density, bit 2 = hidden
+// width 128 instead of 256.
 constexpr int kLayoutCustomBit = 1 << 24;
+constexpr int kLayoutHidden128Bit = 4;
 constexpr int kMaxEncodingL = 10;
-inline int make_layout_id(int pos_L, int dir_L, int pos_encoding, int density_relu) {
-  if (pos_L < 0 || dir_L < 0 || pos_L > kMaxEncodingL || dir_L > kMaxEncodingL) return -1;
-  if (!pos_encoding) return 1 + (density_relu ? 2 : 0);
-  if (pos_L == 10 && dir_L == 4) return density_relu ? 2 : 0;
-  return kLayoutCustomBit | (pos_L << 8) | (dir_L << 16) | (density_relu ? 2 : 0);
+inline int make_layout_id(int pos_L, int dir_L, int pos_encoding, int density_relu, int hidden) {
+  if (pos_L < 0 || dir_L < 0 || pos_L > kMaxEncodingL || dir_L > kMaxEncodingL || (hidden != 256 && hidden != 128)) return -1;
+  const int flags = (density_relu ? 2 : 0) | (hidden == 128 ? kLayoutHidden128Bit : 0);
+  if (!pos_encoding) return hidden == 256 ? 1 + flags : (kLayoutCustomBit | 1 | flags);
+  if (pos_L == 10 && dir_L == 4 && hidden == 256) return flags;
+  return kLayoutCustomBit | (pos_L << 8) | (dir_L << 16) | flags;
 }
 
 struct ModelLayout {
   int32_t layout;
   int32_t density_relu;              // 1: density = relu(.) (legacy checkpoints), 0: softplus (NeRFModel.py:192)
+  int32_t hidden;                    // num_channels: 256 or 128
   int32_t pos_in, dir_in;            // 63/27 or 3/3
   int32_t pos_L, dir_L;              // 10/4 or 0/0
   int32_t n_params;
@@ -163,7 +167,7 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
   int pos_L = 10, dir_L = 4;
   if (layout >= 0 && (layout & kLayoutCustomBit)) {
     pos_L = (layout >> 8) & 0xff; dir_L = (layout >> 16) & 0xff;
-    if ((layout & ~(kLayoutCustomBit | 0xffff00 | 2)) != 0 || pos_L > kMaxEncodingL || dir_L > kMaxEncodingL) return false;
+    if ((layout & ~(kLayoutCustomBit | 0xffff00 | 7)) != 0 || pos_L > kMaxEncodingL || dir_L > kMaxEncodingL) return false;
   } else if (layout < 0 || layout >= kNumLayouts) {
     return false;
   }
@@ -173,7 +177,10 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
   const bool pe = (layout & 1) == 0;
   m.pos_L = pe ? pos_L : 0; m.dir_L = pe ? dir_L : 0;
   m.pos_in = 3 * (2 * m.pos_L + 1); m.dir_in = 3 * (2 * m.dir_L + 1);       // NeRFModel.py:112-114 (3 when the encoding is off)
-  const int C = 256;
+  const int C = (layout >= 0 && (layout & kLayoutCustomBit) && (layout & kLayoutHidden128Bit)) ? 128 : 256;   // num_channels
+  m.hidden = C;
+  const int block_bytes = (C / 8) * kKcoreBytes;                            // one C-channel activation / gradient block of a tile
+  const int c_ks = C / 16;                                                  // K = 16 steps over a C-channel activation tile
   const int outs[kNumLinear] = {C, C, C, C, C, C, C, C, C, 1, C, 128, 3};
   const int ins[kNumLinear] = {m.pos_in, C, C, C, C, C + m.pos_in, C, C, C, C, C, C + m.dir_in, 128};
   int off = 0;
@@ -191,12 +198,12 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
   int so = 0;
   m.st_pe = so; so += 8 * kKcoreBytes;
   m.st_de = so; so += (dir_ks > 2 ? 8 : 4) * kKcoreBytes;                  // direction-encoding tile: 32 channels (L <= 4) or 64
-  for (int i = 0; i < 10; ++i) { m.st_h[i] = so; so += kActBytes; }
+  for (int i = 0; i < 10; ++i) { m.st_h[i] = so; so += block_bytes; }
   m.st_r1 = so; so += 16 * kKcoreBytes;
   m.st_mask = so; so += 11 * 4096;
   m.stash_tile_bytes = so;
   int dso = 0;
-  for (int i = 0; i < 10; ++i) { m.ds_y[i] = dso; dso += kActBytes; }
+  for (int i = 0; i < 10; ++i) { m.ds_y[i] = dso; dso += block_bytes; }
   m.ds_y[10] = dso; dso += 16 * kKcoreBytes;
   m.ds_sr = dso; dso += 128 * 16;
   m.ds_cot = dso; dso += 2 * kKcoreBytes;
@@ -217,7 +224,7 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
     st.bias_off = 256 * bias_slot++;
     st.flags = flags; st.stash_off = stash_off; st.mask_off = -1;
     st.p_w = m.w_off[lin]; st.p_in = m.in_f[lin]; st.p_transpose = 0;
-    st.act_cols = act_ks ? 256 : 0; st.enc_col0 = enc_col0; st.enc_cols = enc_cols;
+    st.act_cols = act_ks ? C : 0; st.enc_col0 = enc_col0; st.enc_cols = enc_cols;
     st.p_rows = m.out_f[lin];
     st.p_bias = m.b_off[lin];
     st.bias_in_enc = (enc_ks == 4 && enc_col0 + 63 >= st.p_in) ? 1 : 0;   // PE tile (64 ch): channel 63 is free
@@ -225,23 +232,23 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
     return st;
   };
   Program& f = m.fwd;
-  add(f, fstep(L_FC1, 256, 0, pos_ks, 0, m.pos_in, 0, m.st_h[0]));
-  for (int i = 0; i < 4; ++i) add(f, fstep(L_FC0 + i, 256, 16, 0, 0, 0, 0, m.st_h[1 + i]));
-  add(f, fstep(L_SKIP, 256, 16, pos_ks, 256, m.pos_in, EPI_WRITE_DIR, m.st_h[5]));
+  add(f, fstep(L_FC1, C, 0, pos_ks, 0, m.pos_in, 0, m.st_h[0]));
+  for (int i = 0; i < 4; ++i) add(f, fstep(L_FC0 + i, C, c_ks, 0, 0, 0, 0, m.st_h[1 + i]));
+  add(f, fstep(L_SKIP, C, c_ks, pos_ks, C, m.pos_in, EPI_WRITE_DIR, m.st_h[5]));
   for (int i = 0; i < 3; ++i)
-    add(f, fstep(L_FC2_0 + i, 256, 16, 0, 0, 0, (i == 2 ? EPI_DENSITY : 0), m.st_h[6 + i]));
-  add(f, fstep(L_FEAT, 256, 16, 0, 0, 0, 0, m.st_h[9]));
-  add(f, fstep(L_RGB1, 128, 16, dir_ks, 256, m.dir_in, EPI_RGB | EPI_LAST, m.st_r1));
+    add(f, fstep(L_FC2_0 + i, C, c_ks, 0, 0, 0, (i == 2 ? EPI_DENSITY : 0), m.st_h[6 + i]));
+  add(f, fstep(L_FEAT, C, c_ks, 0, 0, 0, 0, m.st_h[9]));
+  add(f, fstep(L_RGB1, 128, c_ks, dir_ks, C, m.dir_in, EPI_RGB | EPI_LAST, m.st_r1));
   for (int i = 0; i < f.n_steps; ++i) f.s[i].mask_off = m.st_mask + i * 4096;
 
   // ---- backward (dgrad) program: dX = dY . W, masked by relu'(x) ---------------------------
   auto bstep = [&](int lin, int act_ks, int flags, int dstash_off, int mask_off) {
     Step st{};
-    st.n = 256; st.act_ksteps = act_ks; st.enc_ksteps = 0;
+    st.n = C; st.act_ksteps = act_ks; st.enc_ksteps = 0;
     st.bias_off = -1; st.flags = flags; st.stash_off = dstash_off; st.mask_off = mask_off;
     st.p_w = m.w_off[lin]; st.p_in = m.in_f[lin]; st.p_transpose = 1;
     st.act_cols = m.out_f[lin]; st.enc_col0 = 0; st.enc_cols = 0;
-    st.p_rows = 256;                    // only the first 256 input columns carry gradient
+    st.p_rows = C;                      // only the first C input columns (the activations, not the encodings) carry gradient
     st.p_bias = -1; st.bias_kstep = 0; st.bias_in_enc = 0;
     return st;
   };
@@ -249,15 +256,15 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
   // dY10 (rgb1 pre-activation grad, 128 ch) is produced by the prologue.  Step j outputs the
   // masked gradient w.r.t. the pre-activation of forward step (9-j): dY9 (feature) ... dY0 (fc1).
   add(b, bstep(L_RGB1, 8, 0, m.ds_y[9], m.st_mask + 9 * 4096));
-  add(b, bstep(L_FEAT, 16, EPI_BWD_SIGMA, m.ds_y[8], m.st_mask + 8 * 4096));
-  add(b, bstep(L_FC2_0 + 2, 16, 0, m.ds_y[7], m.st_mask + 7 * 4096));
-  add(b, bstep(L_FC2_0 + 1, 16, 0, m.ds_y[6], m.st_mask + 6 * 4096));
-  add(b, bstep(L_FC2_0 + 0, 16, 0, m.ds_y[5], m.st_mask + 5 * 4096));
-  add(b, bstep(L_SKIP, 16, 0, m.ds_y[4], m.st_mask + 4 * 4096));
-  add(b, bstep(L_FC0 + 3, 16, 0, m.ds_y[3], m.st_mask + 3 * 4096));
-  add(b, bstep(L_FC0 + 2, 16, 0, m.ds_y[2], m.st_mask + 2 * 4096));
-  add(b, bstep(L_FC0 + 1, 16, 0, m.ds_y[1], m.st_mask + 1 * 4096));
-  add(b, bstep(L_FC0 + 0, 16, EPI_LAST, m.ds_y[0], m.st_mask + 0 * 4096));
+  add(b, bstep(L_FEAT, c_ks, EPI_BWD_SIGMA, m.ds_y[8], m.st_mask + 8 * 4096));
+  add(b, bstep(L_FC2_0 + 2, c_ks, 0, m.ds_y[7], m.st_mask + 7 * 4096));
+  add(b, bstep(L_FC2_0 + 1, c_ks, 0, m.ds_y[6], m.st_mask + 6 * 4096));
+  add(b, bstep(L_FC2_0 + 0, c_ks, 0, m.ds_y[5], m.st_mask + 5 * 4096));
+  add(b, bstep(L_SKIP, c_ks, 0, m.ds_y[4], m.st_mask + 4 * 4096));
+  add(b, bstep(L_FC0 + 3, c_ks, 0, m.ds_y[3], m.st_mask + 3 * 4096));
+  add(b, bstep(L_FC0 + 2, c_ks, 0, m.ds_y[2], m.st_mask + 2 * 4096));
+  add(b, bstep(L_FC0 + 1, c_ks, 0, m.ds_y[1], m.st_mask + 1 * 4096));
+  add(b, bstep(L_FC0 + 0, c_ks, EPI_LAST, m.ds_y[0], m.st_mask + 0 * 4096));
 
   // packed buffer
   const int fwd_bytes = f.image_bytes, bwd_bytes = b.image_bytes;
@@ -279,6 +286,7 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
     m.wg[m.n_wgrad++] = w;
   };
   const int pos_n = pos_ks * 16, dir_n = dir_ks * 16;
+  if (C == 256) {                                      // the round-1 single-CTA kernel (wgrad.cuh) is built for 256 channels only
   wadd(L_FC1, m.ds_y[0], 32, m.st_pe, pos_n, m.pos_in, 0, true);
   for (int i = 0; i < 4; ++i) wadd(L_FC0 + i, m.ds_y[1 + i], 32, m.st_h[i], 256, 256, 0, true);
   wadd(L_SKIP, m.ds_y[5], 32, m.st_h[4], 256, 256, 0, true);
@@ -287,6 +295,7 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
   wadd(L_FEAT, m.ds_y[9], 32, m.st_h[8], 256, 256, 0, true);
   wadd(L_RGB1, m.ds_y[10], 16, m.st_h[9], 256, 256, 0, true);
   wadd(L_RGB1, m.ds_y[10], 16, m.st_de, dir_n, m.dir_in, 256, false);
+  }
 
   // ---- CTA-pair wgrad items ---------------------------------------------------------------
   const int H = 16 * kKcoreBytes;                     // half of a 256-channel block: this CTA's 16 k-cores
@@ -310,6 +319,7 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
     if (it.depth > 3) it.depth = 3;
     m.w2[m.n_w2++] = it;
   };
+  if (C == 256) {
   auto plain = [&](int lin, int dy_off, int x_off) {               // dY_l x h_(l-1), 256 x 256
     W2Item it{}; it.cot_load = -1; it.cot_kc = 0; it.g_bd = -1; it.g_b2 = -1;
     it.n_loads = 2;
@@ -381,6 +391,76 @@ inline bool build_model_layout(int layout, ModelLayout& m) {
     it.out[2] = out(W2_OUT_HEAD, d_cot, 3, m.w_off[L_RGB2], 128, 1, 0, 0, 2);
     it.out[3] = out(W2_OUT_BIAS, d_bias, 1, m.b_off[L_RGB1], 0, 0, 0, 0, 1);
     finish(it);
+  }
+  } else {
+    // ---- hidden width 128: a layer's dY has 128 channels = ONE CTA's rows of the M = 256 pair, so every item carries TWO layers:
+    // the leader's rows are dY of layer a, the peer's rows dY of layer b, and B = [X_a | X_b] (each CTA loads the block of its own
+    // layer).  Of the four blocks of D the two diagonal ones are the gradients; the off-diagonal ones are never read out.
+    const int Bk = 16 * kKcoreBytes;                   // a 128-channel block of a tile (16 k-cores)
+    auto two = [&](int lin_a, int dy_a, int x_a, int lin_b, int dy_b, int x_b, bool dens_head_on_b) {
+      W2Item it{}; it.cot_load = -1; it.cot_kc = 0; it.g_bd = -1; it.g_b2 = -1;
+      it.n_loads = 2;
+      it.load[0].n_segs = 1; it.load[0].seg[0] = seg(dy_a, dy_b, Bk, true, true);
+      it.load[1].n_segs = 1; it.load[1].seg[0] = seg(x_a, x_b, Bk, false, false);
+      it.n_mmas = 2; it.mma[0] = mma(0, 0, 1, 0, 256, 0); it.mma[1] = mma(0, 0, -1, 0, 16, 256);
+      const int d_head = 272;
+      if (dens_head_on_b) {                            // X_b = h8 on the peer: h8 (as the M side) x cotangents = density_layer's gradient
+        it.load[1].n_segs = 2; it.load[1].seg[1] = half_seg(m.ds_cot, 2 * kKcoreBytes, true);
+        it.cot_load = 1; it.cot_kc = 16; it.g_bd = m.b_off[L_DENS];
+        it.mma[2] = mma(1, 0, 1, 16, 16, d_head); it.n_mmas = 3;
+      }
+      it.n_outs = 0;
+      it.out[it.n_outs++] = out(W2_OUT_WEIGHT, 0, 128, m.w_off[lin_a], m.in_f[lin_a], 0, 0, 0, 1);
+      it.out[it.n_outs++] = out(W2_OUT_WEIGHT, 128, 128, m.w_off[lin_b], m.in_f[lin_b], 0, 0, 0, 2);
+      it.out[it.n_outs++] = out(W2_OUT_BIAS, 256, 1, m.b_off[lin_a], 0, 0, 0, 0, 1);
+      it.out[it.n_outs++] = out(W2_OUT_BIAS, 256, 1, m.b_off[lin_b], 0, 0, 0, 0, 2);
+      if (dens_head_on_b) it.out[it.n_outs++] = out(W2_OUT_HEAD, d_head, 1, m.w_off[L_DENS], 0, 0, 0, 0, 2);
+      finish(it);
+    };
+    {   // leader: skip_layer (dY5), peer: fc1 (dY0); B = [h4 | PE], each CTA half of both parts
+      W2Item it{}; it.cot_load = -1; it.g_bd = -1; it.g_b2 = -1;
+      const int pe_bytes = (pos_n / 8) * kKcoreBytes;
+      it.n_loads = 2;
+      it.load[0].n_segs = 1; it.load[0].seg[0] = seg(m.ds_y[5], m.ds_y[0], Bk, true, true);
+      it.load[1].n_segs = 2; it.load[1].seg[0] = half_seg(m.st_h[4], Bk, false); it.load[1].seg[1] = half_seg(m.st_pe, pe_bytes, false);
+      it.n_mmas = 3;
+      it.mma[0] = mma(0, 0, 1, 0, 128, 0);            // [dY5 ; dY0] x h4   (the peer's block is not read out)
+      it.mma[1] = mma(0, 0, 1, 8, pos_n, 128);        // [dY5 ; dY0] x PE
+      it.mma[2] = mma(0, 0, -1, 0, 16, 192);
+      it.n_outs = 5;
+      it.out[0] = out(W2_OUT_WEIGHT, 0, 128, m.w_off[L_SKIP], m.in_f[L_SKIP], 0, 0, 0, 1);
+      it.out[1] = out(W2_OUT_WEIGHT, 128, m.pos_in, m.w_off[L_SKIP], m.in_f[L_SKIP], 128, 0, 0, 1);
+      it.out[2] = out(W2_OUT_WEIGHT, 128, m.pos_in, m.w_off[L_FC1], m.in_f[L_FC1], 0, 0, 0, 2);
+      it.out[3] = out(W2_OUT_BIAS, 192, 1, m.b_off[L_SKIP], 0, 0, 0, 0, 1);
+      it.out[4] = out(W2_OUT_BIAS, 192, 1, m.b_off[L_FC1], 0, 0, 0, 0, 2);
+      finish(it);
+    }
+    two(L_FC0 + 0, m.ds_y[1], m.st_h[0], L_FC0 + 1, m.ds_y[2], m.st_h[1], false);
+    two(L_FC0 + 2, m.ds_y[3], m.st_h[2], L_FC0 + 3, m.ds_y[4], m.st_h[3], false);
+    two(L_FC2_0 + 0, m.ds_y[6], m.st_h[5], L_FC2_0 + 1, m.ds_y[7], m.st_h[6], false);
+    two(L_FC2_0 + 2, m.ds_y[8], m.st_h[7], L_FEAT, m.ds_y[9], m.st_h[8], true);
+    {   // leader: rgb_layer1 (dY10), peer: r1 rows for rgb_layer2's head; B = [h9 | DE | cot], each CTA half of every part
+      W2Item it{}; it.g_bd = -1;
+      const int de_bytes = (dir_n / 8) * kKcoreBytes;
+      it.n_loads = 2;
+      it.load[0].n_segs = 1; it.load[0].seg[0] = seg(m.ds_y[10], m.st_r1, Bk, true, false);
+      it.load[1].n_segs = 3; it.load[1].seg[0] = half_seg(m.st_h[9], Bk, false); it.load[1].seg[1] = half_seg(m.st_de, de_bytes, false);
+      it.load[1].seg[2] = half_seg(m.ds_cot, 2 * kKcoreBytes, true);
+      const int de_kc = dir_n / 16;
+      it.cot_load = 1; it.cot_kc = 8 + de_kc; it.g_b2 = m.b_off[L_RGB2];
+      const int d_de = 128, d_cot = 128 + dir_n, d_bias = d_cot + 16;
+      it.n_mmas = 4;
+      it.mma[0] = mma(0, 0, 1, 0, 128, 0);
+      it.mma[1] = mma(0, 0, 1, 8, dir_n, d_de);
+      it.mma[2] = mma(0, 0, 1, 8 + de_kc, 16, d_cot);
+      it.mma[3] = mma(0, 0, -1, 0, 16, d_bias);
+      it.n_outs = 4;
+      it.out[0] = out(W2_OUT_WEIGHT, 0, 128, m.w_off[L_RGB1], m.in_f[L_RGB1], 0, 0, 0, 1);
+      it.out[1] = out(W2_OUT_WEIGHT, d_de, m.dir_in, m.w_off[L_RGB1], m.in_f[L_RGB1], 128, 0, 0, 1);
+      it.out[2] = out(W2_OUT_HEAD, d_cot, 3, m.w_off[L_RGB2], 128, 1, 0, 0, 2);
+      it.out[3] = out(W2_OUT_BIAS, d_bias, 1, m.b_off[L_RGB1], 0, 0, 0, 0, 1);
+      finish(it);
+    }
   }
   return true;
 }

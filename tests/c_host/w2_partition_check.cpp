@@ -8,7 +8,9 @@
 using namespace nerf;
 int main() {
   int bad = 0;
-  for (int layout = 0; layout < 4; ++layout) {
+  const int layouts[] = {0, 1, 2, 3, make_layout_id(6, 2, 1, 0, 256), make_layout_id(10, 10, 1, 0, 256), make_layout_id(10, 4, 1, 0, 128),
+                         make_layout_id(3, 8, 1, 1, 128), make_layout_id(0, 0, 0, 0, 128)};
+  for (int layout : layouts) {
     ModelLayout m;
     if (!build_model_layout(layout, m)) return 2;
     for (int n_pairs : {74, 66, 9, 96, 120}) {

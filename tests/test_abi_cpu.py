@@ -100,12 +100,13 @@ def test_param_offsets_follow_state_dict_order(libmod):
     import sfmnerf_b200 as s
     lib = libmod.load()
     cases = [(0, {}), (1, {"pos_encoding": False})]
-    for pl, dl in ((6, 2), (10, 10), (0, 3), (4, 4)):                  # --n_pos_freq / --n_dirc_freq: generalised layout ids
-        lid = lib.nerf_layout_id(pl, dl, 1, 0)
+    for pl, dl, ch in ((6, 2, 256), (10, 10, 256), (0, 3, 256), (4, 4, 256), (10, 4, 128), (2, 9, 128)):   # --n_pos_freq / --n_dirc_freq / --hidden_size
+        lid = lib.nerf_layout_id(pl, dl, 1, 0, ch)
         assert lid > 3
-        cases.append((lid, {"embed_pos_L": pl, "embed_direction_L": dl}))
-    assert lib.nerf_layout_id(10, 4, 1, 0) == 0 and lib.nerf_layout_id(10, 4, 1, 1) == 2 and lib.nerf_layout_id(7, 7, 0, 0) == 1
-    assert lib.nerf_layout_id(11, 4, 1, 0) == -4 and lib.nerf_layout_id(10, -1, 1, 0) == -4
+        cases.append((lid, {"embed_pos_L": pl, "embed_direction_L": dl, "num_channels": ch}))
+    cases.append((lib.nerf_layout_id(10, 4, 0, 0, 128), {"pos_encoding": False, "num_channels": 128}))
+    assert lib.nerf_layout_id(10, 4, 1, 0, 256) == 0 and lib.nerf_layout_id(10, 4, 1, 1, 256) == 2 and lib.nerf_layout_id(7, 7, 0, 0, 256) == 1
+    assert lib.nerf_layout_id(11, 4, 1, 0, 256) == -4 and lib.nerf_layout_id(10, -1, 1, 0, 256) == -4 and lib.nerf_layout_id(10, 4, 1, 0, 64) == -4
     for layout, kw in cases:
         m = s.NeRFmodel(**kw)
         assert m.layout_id == layout

@@ -554,20 +554,20 @@ def test_errors_are_loud(pkg, model_pe):
     with pytest.raises(pkg._lib.NerfB200Error):
         cpu_model(torch.zeros(4, 3), torch.zeros(4, 3))
     with pytest.raises(NotImplementedError):
-        pkg.NeRFmodel(num_channels=128).cuda()(torch.zeros(4, 3).cuda(), torch.zeros(4, 3).cuda())
+        pkg.NeRFmodel(num_channels=64).cuda()(torch.zeros(4, 3).cuda(), torch.zeros(4, 3).cuda())        # 256 and 128 are built
     with pytest.raises(NotImplementedError):
         pkg.NeRFmodel(embed_pos_L=11).cuda()(torch.zeros(4, 3).cuda(), torch.zeros(4, 3).cuda())     # 69 channels do not fit the tile
 
 
-@pytest.mark.parametrize("pos_L,dir_L", [(6, 2), (10, 8), (3, 7), (0, 0)])
-def test_other_encoding_frequencies(pkg, orc, pos_L, dir_L):
-    """--n_pos_freq / --n_dirc_freq other than 10 / 4 (train.py:796-797; NeRFmodel(embed_pos_L, embed_direction_L), NeRFModel.py:102-114):
-    same kernels, generalised layout ids.  Same init draws as the reference class, forward against the fp32 oracle, render + backward
-    against the bf16-operand restatement (every tensor), norms against fp32."""
+@pytest.mark.parametrize("pos_L,dir_L,hidden", [(6, 2, 256), (10, 8, 256), (3, 7, 256), (0, 0, 256), (10, 4, 128), (5, 6, 128)])
+def test_other_model_shapes(pkg, orc, pos_L, dir_L, hidden):
+    """--n_pos_freq / --n_dirc_freq other than 10 / 4 and --hidden_size 128 (train.py:796-797, 813; NeRFmodel(embed_pos_L,
+    embed_direction_L, num_channels), NeRFModel.py:102-140): same kernels, generalised layout ids.  Same init draws as the reference
+    class, forward against the fp32 oracle, render + backward against the bf16-operand restatement (every tensor), norms against fp32."""
     torch.manual_seed(4)
-    m = pkg.NeRFmodel(embed_pos_L=pos_L, embed_direction_L=dir_L)
+    m = pkg.NeRFmodel(embed_pos_L=pos_L, embed_direction_L=dir_L, num_channels=hidden)
     kw = dict(embed_pos_L=pos_L, embed_direction_L=dir_L)
-    sd0 = orc.init_state_dict(4, **kw)
+    sd0 = orc.init_state_dict(4, num_channels=hidden, **kw)
     for k, v in m.state_dict().items():
         assert torch.equal(v, sd0[k]), k
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
