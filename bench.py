@@ -372,6 +372,12 @@ def run_ours(args):
     launches = trainer.launches_per_step * K * WINDOWS            # this repo's kernels only (the gradient memset is the driver's)
     graph_replay = len(trainer._graphs) > 0
     graph_error = trainer.graph_error
+    if graph_error or not graph_replay:                           # the headline path is the graph-replayed step: never time a silent fallback
+        if rank == 0:
+            print(json.dumps({"error": "CUDA-graph capture of nerf_train_step failed; the step ran as direct launches", "graph_error": graph_error}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        sys.exit(4)
     # per-kernel durations: the same K steps again with the same kernels launched one by one, each bracketed by CUDA events on
     # the launch stream (events cannot be read from inside a graph replay); 3 untimed steps first (the first launches of the
     # per-kernel sequence pay one-off costs: lazy module load of the un-graphed barrier kernel, allocator growth)
@@ -640,7 +646,7 @@ def run_ours(args):
         "e2e": {"value": n_rays * world * K / e2e_ms * 1e3, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 9 * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K, "timing": e2e_info},
         "gpu_launches": launches,
-        "step_launch": {"mode": ("cuda graph replay of nerf_train_step (8 kernels + 1 memset per step" + (", cross-rank barrier inside the graph)" if world > 1 else ")")) if graph_replay else
+        "step_launch": {"mode": ("cuda graph replay of nerf_train_step (7 kernels + 1 memset per step" + (", cross-rank barrier inside the graph)" if world > 1 else ")")) if graph_replay else
                                 "per-kernel sequence from the host",
                         "graph_error": graph_error, "ms_per_step_instrumented": ms_instrumented / K,
                         "note": "`kernels` / `roofline` durations: the same steps launched kernel by kernel with CUDA events, timed right after the headline region"},

@@ -13,8 +13,10 @@
 #include "mlp_layout.cuh"
 #include "rays.cuh"
 #include "selftest.cuh"
-#include "wgrad.cuh"
 #include "wgrad_pair.cuh"
+#if !NERF_WGRAD_PAIR
+#include "wgrad.cuh"            // the round-1 single-CTA kernel + CUDA-core head kernel: A/B builds only (-DNERF_WGRAD_PAIR=0)
+#endif
 
 using namespace nerf;
 
@@ -59,7 +61,9 @@ int device_info(DeviceInfo** out) {
     NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
     NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
     NERF_CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel<MODE_BWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal));
+#if !NERF_WGRAD_PAIR
     NERF_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+#endif
     NERF_CUDA_TRY(cudaFuncSetAttribute(wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW2SmemBytes));
     NERF_CUDA_TRY(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
     NERF_CUDA_TRY(cudaFuncSetAttribute(selftest_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
@@ -416,7 +420,8 @@ int nerf_mlp_wgrad(int layout, const void* stash, const void* dstash, int64_t n_
     NERF_LAUNCH_CHECK();
     return NERF_OK;
   }
-#endif
+#else
+  if (m->n_wgrad == 0) return NERF_ERR_LAYOUT;      /* the single-CTA kernel is built for 256 channels */
   // weight gradients: split the SMs over the work items in proportion to their cost
   WgradArgs w;
   std::memset(&w, 0, sizeof(w));
@@ -468,6 +473,7 @@ int nerf_mlp_wgrad(int layout, const void* stash, const void* dstash, int64_t n_
   NERF_LAUNCH_CHECK();
   NERF_CUDA_TRY(cudaStreamWaitEvent(s, dev->ev_join, 0));
   return NERF_OK;
+#endif
 }
 
 int nerf_mlp_backward(const void* packed, int layout, const void* stash, const float* sigma_rgb,

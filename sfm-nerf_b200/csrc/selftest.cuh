@@ -282,9 +282,18 @@ __global__ void store_rate_kernel(uint4* __restrict__ buf, int iters, int mode, 
   uint4* base = buf + (size_t)blockIdx.x * (size_t)iters * warps * 32;
   const long long t0 = clock64();
   uint4 v = sm[threadIdx.x & 4095];
+  // modes 0-2: every CTA streams through its own contiguous region.  mode 3: 64 KB blocks interleaved over the CTAs (block j of
+  // CTA b at (j * gridDim + b) * 64 KB: what a [layer][tile] stash layout would give); mode 4: 2 KB pieces interleaved over the CTAs.
+  const int per_block = (65536 / 512) / warps;          // iterations per 64 KB block
   for (int it = 0; it < iters; ++it) {
     if (mode != 2) v = sm[(it * 128 + warp * 32 + lane) & 4095];
     uint4* dst = base + ((size_t)it * warps + warp) * 32 + lane;
+    if (mode == 3 && per_block > 0) {
+      const size_t blk = (size_t)(it / per_block) * gridDim.x + blockIdx.x;
+      dst = buf + blk * 4096 + ((size_t)(it % per_block) * warps + warp) * 32 + lane;
+    } else if (mode == 4) {
+      dst = buf + ((size_t)it * gridDim.x + blockIdx.x) * (size_t)warps * 32 + warp * 32 + lane;
+    }
     if (mode == 1) *dst = v; else __stcs(dst, v);
   }
   __syncthreads();

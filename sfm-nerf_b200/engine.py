@@ -481,7 +481,7 @@ class Trainer:
             self._run_segment((key, parity, "step"), lambda: rest(1))
         self.iteration += 1
         self._dev_iteration += 1
-        self.launches_per_step = 8                  # batch, mlp fwd, composite_train, dgrad, wgrad, heads, adam, pack (+1 memset)
+        self.launches_per_step = 7                  # batch, mlp fwd, composite_train, dgrad, wgrad (pairs), adam, pack (+1 memset)
         if loss_to_host:
             self._loss_event.synchronize()
             return float(self._loss_host[0])
@@ -552,7 +552,7 @@ class Trainer:
             self.grads = ex.local(self.iteration)
         with _timed(timers, "mlp_wgrad"):
             call("nerf_mlp_wgrad", st.layout, ptr(self.stash), ptr(self.dstash), rows, ptr(self.grads), 0, stream_ptr())
-        launches += 5                               # mlp fwd, composite_train, dgrad, wgrad, heads (+1 memset)
+        launches += 4                               # mlp fwd, composite_train, dgrad, wgrad (pairs) (+1 memset)
         lr = self.lr()
         if ex is not None and ex.mode != "nccl":
             # the gradient exchange is fused into the optimiser: barrier, then Adam reads the sum over ranks through NVLink

@@ -8,8 +8,9 @@ import sfmnerf_b200 as s
 lib = s._lib.load()
 buf = torch.empty(6 << 30, dtype=torch.uint8, device="cuda")
 sms = torch.cuda.get_device_properties(0).multi_processor_count
-for mode, name in ((0, "st.global.cs from smem"), (1, "st.global from smem"), (2, "st.global.cs from registers")):
-    for warps in (1, 2, 4, 8, 12, 16, 32):
+for mode, name in ((0, "st.global.cs from smem"), (1, "st.global from smem"), (2, "st.global.cs from registers"),
+                   (3, "64 KB blocks interleaved over CTAs"), (4, "2 KB pieces interleaved over CTAs")):
+    for warps in ((1, 2, 4, 8, 12, 16, 32) if mode < 3 else (4, 8, 16)):
         iters = (32 << 20) // (warps * 512)            # 32 MB per CTA
         out = (ctypes.c_longlong * 3)()
         rc = lib.nerf_debug_store_rate(warps, iters, mode, ctypes.c_void_p(buf.data_ptr()), buf.numel(), out)
