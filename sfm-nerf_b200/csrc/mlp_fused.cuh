@@ -40,53 +40,21 @@ constexpr int MODE_BWD = 1;
 // warp's index in the CTA tied to the SM sub-partition it runs on: with 320 threads the epilogue warps were seen in
 // rotated hardware slots (cuda-gdb) and tcgen05.ld raised "misaligned address", depending on what ran on the SM before.
 constexpr int kMlpThreads = 384;
-// How a layer's output tile reaches the training stash (forward) / the gradient stash (dgrad).  Per-layer clock stamps
-// (tools/trace_mlp.py, gpurun_out/trace_r2_*.txt) showed both training kernels EPILOGUE-bound: 3,400-3,700 cycles (forward:
-// every thread reads its row of the tile back from shared memory and stores it, 128 x 16 B) and 3,000-3,200 cycles (dgrad:
-// the same stores from registers inside the accumulator read-out loop) against 1,030 cycles in the inference kernel and a
-// 2,350-cycle layer of MMAs to hide them behind.
-//   NERF_FWD_STASH_MODE  0: read-back by the epilogue threads after the release   1: st.global from the read-out loop's registers
-//                        2: ONE bulk (TMA) store of the tile per layer, issued by one thread after the release
-//   NERF_BWD_STASH_MODE  0: st.global from the read-out loop's registers   1: bulk store   2: read-back after the release
-// Measured (tools/gpu_ab.sh, 4096 x 64): bulk stores lose in every form -- one 64 KB copy per tile 0.42 / 0.35 ms (forward /
-// dgrad), 2-8 KB pieces with 0-2 in flight 0.37-0.44 / 0.37-0.44 ms, against 0.36 / 0.33 ms for the thread stores: a bulk store
-// waits in the same in-order queue of the SM's copy engine as the weight-slab loads and drains only as fast as HBM takes the
-// writes, so the MMAs starve behind it.
-// NERF_STASH_YIELD 1: the read-back stores of one tile slot pause while the OTHER slot's warpgroup drains its accumulator (both
-// share the SM's load/store path, and the HBM-paced global stores stretch that read-out from 1,030 to 3,400 cycles).  Measured:
-// the read-out does drop to 1,200 cycles, but the kernels get SLOWER (forward 0.352 -> 0.368 ms, dgrad with read-back 0.36 -> 0.44
-// ms): the store phase of a tile takes ~5,000 cycles whoever issues it -- 2 x 64 KB per SM and layer pair at the ~18-23 B/clk an
-// SM gets of the HBM write bandwidth when all 148 store at once is 5,600-7,000 cycles, more than the 4,700 cycles of MMAs.
-// These two kernels are bound by HBM WRITES (1.5 / 1.4 GB per launch), not by the epilogue code; the defaults below are the
-// fastest forms measured (profiles/r2_stash_store_variants.md).
+// How a layer's output tile reaches the training stash (forward) / the gradient stash (dgrad): the forward's epilogue threads read
+// their rows of the tile back after the release and stream them with 16-byte stores; dgrad stores the packed words straight
+// from the accumulator read-out loop.  Round 2 built and A/B-timed every alternative -- stores from the read-out registers in
+// the forward, one bulk (TMA) store per tile, bulk stores in 2-8 KB pieces with 0-2 in flight, read-back for dgrad, read-back
+// stores that yield to the other slot's read-out -- and all were equal or slower: both kernels are bound by how fast an SM
+// streams these stores (22 B/clk = 6.3 TB/s chip-wide, tools/store_rate.py), not by who issues them.  The table is
+// profiles/r2_stash_store_variants.md; the code of the variants is in the history (commits 74f67cc .. a0e94fb).
 #ifndef NERF_WGRAD_PAIR
 #define NERF_WGRAD_PAIR 1           // 1: wgrad_pair.cuh (CTA pairs, heads on the tensor core); 0: wgrad.cuh + head_grad_kernel
-#endif
-#ifndef NERF_FWD_STASH_MODE
-#define NERF_FWD_STASH_MODE 0
-#endif
-#ifndef NERF_BWD_STASH_MODE
-#define NERF_BWD_STASH_MODE 0
-#endif
-#ifndef NERF_STASH_YIELD
-#define NERF_STASH_YIELD 0
 #endif
 #ifndef NERF_SLOT_OFFSET
 #define NERF_SLOT_OFFSET 0          // layers by which tile slot 1 trails tile slot 0 (see the sequence comment in the kernel)
 #endif
 #ifndef NERF_READBACK_BATCH
 #define NERF_READBACK_BATCH 8       // k-cores (16 B per row each) a read-back loop loads before it stores the first
-#endif
-#define NERF_BWD_STASH_BULK (NERF_BWD_STASH_MODE == 1)
-// A bulk store waits in the SAME in-order queue of the SM's copy engine as the weight-slab loads, and drains only as fast as
-// HBM takes the writes (all SMs store at once: ~23 B/clk per SM): one 64 KB store per tile stretched a layer of MMAs from 2,350
-// to 6,000+ cycles (trace_r2b_*.txt).  So the tile goes out in PIECES, and the issuing thread keeps at most NERF_STASH_INFLIGHT
-// pieces queued: a slab load never waits behind more than that.
-#ifndef NERF_STASH_PIECE_BYTES
-#define NERF_STASH_PIECE_BYTES 4096
-#endif
-#ifndef NERF_STASH_INFLIGHT
-#define NERF_STASH_INFLIGHT 1
 #endif
 
 struct MlpArgs {
@@ -118,9 +86,7 @@ struct MlpSmem {
   static constexpr int kEnc = kAct + 2 * kActBytes;                // 2 x 16 KB
   static constexpr int kRing = kEnc + 2 * kEncBytes;               // 16 x 4 KB (this CTA's half of every slab)
   static constexpr int kBars = kRing + kRingSlots * kRingSlotBytes;
-  // barriers (8 B each): full[16] @0, empty[16] @128, acc_full[2] @256, act_ready[2] @272, drain @288; read-out flags (2 x u32) @304;
-  // tmem ptr @320
-  static constexpr int kFlags = kBars + 304;
+  // barriers (8 B each): full[16] @0, empty[16] @128, acc_full[2] @256, act_ready[2] @272, drain @288; tmem ptr @320
   static constexpr int kTmemPtr = kBars + 320;
   static constexpr int kHead = kBars + 384;                        // fp32 head tables (w_d, b_d, W2, b2): 648 floats
   static constexpr int kHeadFloats = 648;
@@ -229,8 +195,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
     // act_ready lives in the leader: 128 epilogue threads of each CTA arrive on it
     for (int i = 0; i < 2; ++i) { tc::mbar_init(bar_acc + 8 * i, 1); tc::mbar_init(bar_act + 8 * i, 256); }
     tc::mbar_init(bar_drain, 1);                       // the MMA warp: "all my MMAs have completed" (multicast to both CTAs)
-    reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kFlags)[0] = 0u;
-    reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kFlags)[1] = 0u;
     tc::fence_mbar_init();
   }
   if (warp == 8) tc::tmem_alloc_pair(tc::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
@@ -468,13 +432,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256 * slot;
     const uint32_t my_acc = bar_acc + 8 * slot;
     const uint32_t leader_act = tc::mapa(bar_act + 8 * slot, 0);   // "A tile of this slot is ready" lives in the leader
-    const uint64_t stream_once = tc::l2_policy_evict_first();        // stash / dstash bulk stores: written once, read by a later kernel
-    (void)stream_once;
-    // "this slot's warpgroup is draining its accumulator" (advisory; see NERF_STASH_YIELD)
-    volatile uint32_t* ro_flag = reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kFlags);
-    constexpr bool kYield = (NERF_STASH_YIELD != 0) && (((MODE == MODE_FWD) && TRAIN && NERF_FWD_STASH_MODE == 0) ||
-                                                        ((MODE == MODE_BWD) && NERF_BWD_STASH_MODE == 2));
-    (void)ro_flag;
     constexpr bool train = TRAIN || (MODE == MODE_BWD);   // the stash exists: written by the training forward, read (masks) by dgrad
     uint32_t acc_phase = 0;
     for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
@@ -553,25 +510,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           const uint4 pk = make_uint4(tc::pack_bf16x2(g[0], g[1]), tc::pack_bf16x2(g[2], g[3]),
                                       tc::pack_bf16x2(g[4], g[5]), tc::pack_bf16x2(g[6], g[7]));
           tc::st_shared_v4(s_act + kc * kKcoreBytes + row * 16, pk.x, pk.y, pk.z, pk.w);
-          if (!NERF_BWD_STASH_BULK && store_out) __stcs(reinterpret_cast<uint4*>(dstash_tile + a.ds_y10 + kc * kKcoreBytes) + row, pk);
+          if (store_out) __stcs(reinterpret_cast<uint4*>(dstash_tile + a.ds_y10 + kc * kKcoreBytes) + row, pk);
         }
       }
       tc::fence_proxy_async_smem();
       if (rank == 0) tc::mbar_arrive(bar_act + 8 * slot); else tc::mbar_arrive_cluster(leader_act);
-      if (MODE == MODE_BWD && NERF_BWD_STASH_BULK) {                 // dY10 (16 k-cores) to the dstash by bulk copies, see the layer steps
-        tc::named_bar_sync(1 + slot, 128);
-        if (row == 0) {
-          if (store_out) {
-            for (uint32_t off = 0; off < 16u * kKcoreBytes; off += NERF_STASH_PIECE_BYTES) {
-              tc::bulk_s2g_hint(dstash_tile + a.ds_y10 + off, s_act + off, NERF_STASH_PIECE_BYTES, stream_once);
-              tc::bulk_commit();
-              tc::bulk_wait_read<NERF_STASH_INFLIGHT>();
-            }
-          }
-          tc::bulk_wait_read0();
-        }
-        tc::named_bar_sync(1 + slot, 128);
-      }
 
       // ---------------- layer steps ----------------
       for (int si = 0; si < P.n_steps; ++si) {
@@ -583,7 +526,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         }
         tc::mbar_wait(my_acc, acc_phase & 1u); ++acc_phase;
         tc::tc_fence_after();
-        if (kYield && row == 0) ro_flag[slot] = 1u;
 #ifdef NERF_DIAGNOSTICS
         long long* tr = (a.trace != nullptr && blockIdx.x == 0 && row == 0)
                             ? a.trace + ((size_t)((quad / n_clusters) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
@@ -596,15 +538,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
 
         uint4* g_out = (MODE == MODE_BWD && tile_ok) ? reinterpret_cast<uint4*>(dstash_tile + st.stash_off) + row : nullptr;
         (void)g_out;
-        constexpr bool kRegStash = (MODE == MODE_FWD) && TRAIN && (NERF_FWD_STASH_MODE != 0);      // masks from the packed registers
-        constexpr bool kFwdBulk = (MODE == MODE_FWD) && TRAIN && (NERF_FWD_STASH_MODE == 2);
-        constexpr bool kBwdBulk = (MODE == MODE_BWD) && NERF_BWD_STASH_BULK;
-        uint4* g_st = (kRegStash && !kFwdBulk && store_out) ? reinterpret_cast<uint4*>(stash_tile + st.stash_off) + row : nullptr;
-        uint2* g_mask = (kRegStash && store_out) ? reinterpret_cast<uint2*>(stash_tile + st.mask_off) + row * 4 : nullptr;
-        (void)g_st; (void)g_mask;
         // one 64-column unit: activation / mask, bf16 pack, store as the next A tile
         auto process = [&](uint32_t (&v)[64], int u) {
-          if (MODE == MODE_FWD && !kRegStash) {
+          if (MODE == MODE_FWD) {
             {                                          // ReLU + bf16 pack in one cvt; the bias came through the MMA
 #pragma unroll
               for (int q = 0; q < 8; ++q)
@@ -614,24 +550,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
                                  tc::pack_bf16x2_relu(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
                                  tc::pack_bf16x2_relu(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
             }
-          } else if (MODE == MODE_FWD) {
-            // training: the packed words go to the next A tile AND straight to the stash from registers (a warp writes 512
-            // contiguous bytes per instruction), and into the ReLU bit masks of this unit's two 32-column chunks
-            // (bit of column c of a chunk: (c >> 1) + 16 * (c & 1), i.e. word i of the chunk's 16 packed words -> bits i / i + 16)
-            uint32_t m_lo = 0u, m_hi = 0u;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              uint32_t p[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                p[t] = tc::pack_bf16x2_relu(__uint_as_float(v[8 * q + 2 * t]), __uint_as_float(v[8 * q + 2 * t + 1]));
-                const uint32_t bits = ((p[t] + 0x7fff7fffu) & 0x80008000u) >> (15 - (4 * (q & 3) + t));
-                if (q < 4) m_lo |= bits; else m_hi |= bits;
-              }
-              tc::st_shared_v4(s_act + (u * 8 + q) * kKcoreBytes + row * 16, p[0], p[1], p[2], p[3]);
-              if (g_st != nullptr) __stcs(g_st + (u * 8 + q) * 128, make_uint4(p[0], p[1], p[2], p[3]));
-            }
-            if (g_mask != nullptr) __stcs(g_mask + u, make_uint2(m_lo, m_hi));
           } else {
             const uint32_t w_lo = pick8(mk_a, mk_b, 2 * u), w_hi = pick8(mk_a, mk_b, 2 * u + 1);
             if (add_sigma) {                           // density head: d h8 += d_sigma_pre * w_d
@@ -659,7 +577,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
                 p[t] = tc::pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & (((w >> (i & 15)) & 0x00010001u) * 0xFFFFu);
               }
               tc::st_shared_v4(s_act + (u * 8 + q) * kKcoreBytes + row * 16, p[0], p[1], p[2], p[3]);
-              if (NERF_BWD_STASH_MODE == 0 && g_out != nullptr) __stcs(g_out + (u * 8 + q) * 128, make_uint4(p[0], p[1], p[2], p[3]));   // streaming: keep the weights in L2
+              if (g_out != nullptr) __stcs(g_out + (u * 8 + q) * 128, make_uint4(p[0], p[1], p[2], p[3]));   // streaming: keep the weights in L2
             }
           }
         };
@@ -682,32 +600,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         if (!(st.flags & EPI_LAST)) {                  // the next layer's MMAs may start NOW
           if (rank == 0) tc::mbar_arrive(bar_act + 8 * slot); else tc::mbar_arrive_cluster(leader_act);
         }
-        if (kYield && row == 0) ro_flag[slot] = 0u;
 #ifdef NERF_DIAGNOSTICS
         if (tr) tr[3] = clock64();
 #endif
 
         // ---- everything below is off the MMA -> epilogue -> MMA critical path ----
-        if (kFwdBulk || kBwdBulk) {
-          // The tile this warpgroup has just written ([k_core][row][8] = the stash block's own layout) goes to HBM as ONE bulk
-          // copy issued by one thread: the other 127 are done.  Barrier 1: every row of the tile is written (and fenced for
-          // the async proxy, above).  Barrier 2: the copy has finished READING shared memory -- the next layer's epilogue
-          // overwrites the tile in place.  Both sit in the slack before this slot's next accumulator is complete.
-          tc::named_bar_sync(1 + slot, 128);
-          if (row == 0) {
-            if (store_out) {
-              uint8_t* dst = (MODE == MODE_FWD ? stash_tile : dstash_tile) + st.stash_off;
-              const uint32_t bytes = (uint32_t)st.n * 256u;                                  // n channels x 128 rows x 2 B
-              for (uint32_t off = 0; off < bytes; off += NERF_STASH_PIECE_BYTES) {
-                tc::bulk_s2g_hint(dst + off, s_act + off, NERF_STASH_PIECE_BYTES, stream_once);
-                tc::bulk_commit();
-                tc::bulk_wait_read<NERF_STASH_INFLIGHT>();
-              }
-            }
-            tc::bulk_wait_read0();
-          }
-          tc::named_bar_sync(1 + slot, 128);
-        }
         if (MODE == MODE_FWD) {
           if (st.flags & EPI_WRITE_DIR) {              // ENC k-cores 0-3 <- direction encoding (used by rgb_layer1)
             uint8_t* g_de = store_out ? stash_tile + a.st_de : nullptr;
@@ -763,7 +660,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             }
           }
         }
-        if (MODE == MODE_FWD && TRAIN && store_out && !kRegStash) {
+        if (MODE == MODE_FWD && TRAIN && store_out) {
           // Training stash: this thread reads back the 16-byte pieces of ITS OWN row of the bf16 tile it
           // just wrote and streams them to HBM (a warp writes 512 contiguous bytes per instruction), and
           // folds them into the ReLU bit masks (bit of column c in a 32-column chunk: (c>>1) + 16*(c&1)).
@@ -777,7 +674,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
 #pragma unroll
           for (int g = 0; g < 32 / NERF_READBACK_BATCH; ++g) {
             if (g * NERF_READBACK_BATCH * 8 < st.n) {
-              if (kYield) { while (ro_flag[slot ^ 1] != 0u) __nanosleep(40); }       // let the other slot's read-out through
               uint4 pk[NERF_READBACK_BATCH];
 #pragma unroll
               for (int q = 0; q < NERF_READBACK_BATCH; ++q)
@@ -799,26 +695,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           __stcs(mp, make_uint4(mw[0], mw[1], mw[2], mw[3]));
           __stcs(mp + 1, make_uint4(mw[4], mw[5], mw[6], mw[7]));
         }
-        if (MODE == MODE_BWD && NERF_BWD_STASH_MODE == 2 && g_out != nullptr) {
-          // dstash: this thread reads back the 16-byte pieces of ITS OWN row of the bf16 tile it has just written and streams them
-          // to HBM, after the release -- the read-out loop above then touches shared memory only (1,030 cycles instead of 3,100)
-#pragma unroll
-          for (int g = 0; g < 32 / NERF_READBACK_BATCH; ++g) {
-            if (kYield) { while (ro_flag[slot ^ 1] != 0u) __nanosleep(40); }
-            uint4 pk[NERF_READBACK_BATCH];
-#pragma unroll
-            for (int q = 0; q < NERF_READBACK_BATCH; ++q)
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(pk[q].x), "=r"(pk[q].y), "=r"(pk[q].z), "=r"(pk[q].w)
-                           : "r"(s_act + (g * NERF_READBACK_BATCH + q) * kKcoreBytes + row * 16));
-#pragma unroll
-            for (int q = 0; q < NERF_READBACK_BATCH; ++q) __stcs(g_out + (g * NERF_READBACK_BATCH + q) * 128, pk[q]);
-          }
-        }
       }
     }
   }
-  if (warp < 8 && (threadIdx.x & 127) == 0) tc::bulk_wait0();   // this thread's bulk stores (stash / dstash tiles) are complete
   tc::tc_fence_before();
   tc::cluster_sync();                                  // no remote arrive / multicast commit may target a CTA that has exited
   if (warp == 8) tc::tmem_dealloc_pair(tmem_base, 512);
