@@ -197,10 +197,16 @@ int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
  * multicast_grads != NULL: through the NVLink multicast address of the buffers (multimem.ld_reduce, the switch adds);
  * else: from peer_grads_host[0..n_ranks) (HOST array of device pointers, rank order) over NVLink -- and applies Adam with
  * grad_scale (= 1/n_ranks for the mean).  n must be a multiple of 4 and all pointers 16-byte aligned.  Every rank gets
- * bit-identical parameters. */
+ * bit-identical parameters.
+ * The cross-rank barrier can be FUSED into the kernel: peer_flags_host[0..n_ranks) = every rank's array of 8 unsigned words
+ * (symmetric memory, zero before the first exchange, peer-mapped like the gradient buffers; HOST array of device pointers),
+ * rank = this rank, exchange_epoch = a device word holding the number of exchanges done so far (the kernel announces / waits for
+ * *exchange_epoch + 1; the caller advances it after the call, nerf_train_step does so itself).  exchange_epoch == NULL: no barrier
+ * inside, the caller's own barrier precedes the call. */
 int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, int n_ranks, const float* multicast_grads,
                           float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2, double eps,
-                          int64_t step, float grad_scale, void* stream);
+                          int64_t step, float grad_scale, unsigned int* const* peer_flags_host, int rank,
+                          const unsigned long long* exchange_epoch, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * One frame (or a contiguous slice of its rays) by ONE call -- the body of test_image (train.py:735-757): K1 rays of ray ids
@@ -251,13 +257,16 @@ typedef struct NerfTrainStep {
   unsigned long long* step_state;
   const float* peer_grads[8];      /* data parallel (world > 1), as nerf_adam_step_reduce: the ranks' gradient buffers ... */
   const float* multicast_grads;    /* ... or their NVLink multicast address; both NULL: plain Adam on `grads` */
+  unsigned int* peer_flags[8];     /* data parallel: the ranks' barrier words (see nerf_adam_step_reduce) and ... */
+  unsigned long long* exchange_epoch;  /* ... the device word counting the exchanges; NULL: the caller barriers before UPDATE */
 } NerfTrainStep;
 /* phases (bit mask): NERF_STEP_FORWARD = batch + render + loss (cfg->loss[0] is final when these launches complete);
  * NERF_STEP_GRADS = dgrad + wgrad (cfg->grads is final); NERF_STEP_UPDATE = Adam + re-pack + counter advance.
  * A host that wants the loss of every step (train.py:468) enqueues FORWARD, an async D2H copy of the loss + event, then
  * BACKWARD, and waits on the event only: the backward launches are still running while it prepares the next step.
- * A data-parallel host enqueues FORWARD | GRADS, its cross-rank barrier, then UPDATE with peer_grads / multicast_grads set
- * (the gradient sum over ranks is read through NVLink inside the Adam kernel; grad_scale = 1/world). */
+ * A data-parallel host sets peer_grads / multicast_grads (the gradient sum over ranks is read through NVLink inside the Adam
+ * kernel; grad_scale = 1/world) and either peer_flags + exchange_epoch -- then NERF_STEP_ALL is the whole step, the cross-rank
+ * barrier included -- or enqueues FORWARD | GRADS, its own cross-rank barrier, then UPDATE. */
 #define NERF_STEP_FORWARD 1
 #define NERF_STEP_GRADS 2
 #define NERF_STEP_UPDATE 4

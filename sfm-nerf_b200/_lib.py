@@ -70,7 +70,7 @@ class NerfTrainStep(C.Structure):
          ("lr0", _D), ("lr_decay", _D), ("lr_decay_steps", _L), ("beta1", _D), ("beta2", _D), ("eps", _D), ("grad_scale", _F), ("pad_", _F)] + \
         [(n, _P) for n in ("poses", "images", "batch9", "rays_o", "rays_d", "target", "z", "sigma_rgb", "d_sigma_rgb", "loss",
                            "composite_ws", "stash", "dstash", "packed", "params", "grads", "exp_avg", "exp_avg_sq", "step_state")] + \
-        [("peer_grads", _P * 8), ("multicast_grads", _P)]
+        [("peer_grads", _P * 8), ("multicast_grads", _P), ("peer_flags", _P * 8), ("exchange_epoch", _P)]
 
 
 # name -> (restype, argtypes); must list every symbol include/nerf_b200.h declares
@@ -99,7 +99,7 @@ PROTOTYPES = {
     "nerf_mlp_wgrad": (_I, [_I, _P, _P, _L, _P, _I, _P]),
     "nerf_composite_forward": (_I, [_P, _P, _L, _I, _P, _P, _P, _P]),
     "nerf_composite_backward": (_I, [_P, _P, _P, _L, _I, _P, _P]),
-    "nerf_adam_step_reduce": (_I, [_P, _P, _I, _P, _P, _P, _L, _D, _D, _D, _D, _L, _F, _P]),
+    "nerf_adam_step_reduce": (_I, [_P, _P, _I, _P, _P, _P, _L, _D, _D, _D, _D, _L, _F, _P, _I, _P, _P]),
     "nerf_composite_train_workspace_bytes": (_L, [_L]),
     "nerf_composite_train": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P, _P]),
     "nerf_mse_loss": (_I, [_P, _P, _L, _F, _P, _P, _P]),

@@ -314,7 +314,7 @@ int64_t nerf_mlp_packed_bytes(int layout) {
   return m ? m->packed_bytes : NERF_ERR_LAYOUT;
 }
 
-static int launch_pack(const float* params, int layout, void* packed, unsigned long long* bump, void* stream) {
+static int launch_pack(const float* params, int layout, void* packed, unsigned long long* bump, unsigned long long* bump2, void* stream) {
   DeviceInfo* dev;
   int rc = device_info(&dev);
   if (rc != NERF_OK) return rc;
@@ -330,13 +330,13 @@ static int launch_pack(const float* params, int layout, void* packed, unsigned l
   // one launch: grid.y = forward steps, dgrad steps, then one row of blocks for the fp32 head table
   pack_all_kernel<<<dim3(64, m->fwd.n_steps + m->bwd.n_steps + 1), 256, 0, s>>>(
       params, m->fwd, m->bwd, p, static_cast<uint8_t*>(packed), reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + m->small_off),
-      bump);
+      bump, bump2);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
 
 int nerf_mlp_pack_weights(const float* params, int layout, void* packed, void* stream) {
-  return launch_pack(params, layout, packed, nullptr, stream);
+  return launch_pack(params, layout, packed, nullptr, nullptr, stream);
 }
 
 int64_t nerf_mlp_stash_bytes(int layout, int64_t n_rows) {
@@ -659,18 +659,26 @@ int nerf_train_step(const NerfTrainStep* c, int phases, void* stream) {
       if (!c->peer_grads[r] || !nerf_aligned(c->peer_grads[r], 16)) return NERF_ERR_ALIGN;
       peers.ptr[r] = c->peer_grads[r];
     }
+    PeerFlags flags{};
+    const bool fused_barrier = c->exchange_epoch != nullptr;
+    for (int r = 0; r < c->world && fused_barrier; ++r) {
+      if (!c->peer_flags[r] || !nerf_aligned(c->peer_flags[r], 4)) return NERF_ERR_ALIGN;
+      flags.ptr[r] = c->peer_flags[r];
+    }
     adam_reduce_kernel<<<blocks_for(m->n_params / 4, 256), 256, 0, s>>>(c->params, peers, c->world, c->multicast_grads, c->exp_avg,
-                                                                        c->exp_avg_sq, m->n_params / 4, AdamCoef{}, c->grad_scale, sched);
+                                                                        c->exp_avg_sq, m->n_params / 4, AdamCoef{}, c->grad_scale, sched,
+                                                                        flags, c->rank, fused_barrier ? c->exchange_epoch : nullptr);
   } else {
     launch_adam(c->params, c->grads, c->exp_avg, c->exp_avg_sq, m->n_params, AdamCoef{}, c->grad_scale, sched, s);
   }
   NERF_LAUNCH_CHECK();
-  return launch_pack(c->params, c->layout, c->packed, c->step_state, stream);
+  return launch_pack(c->params, c->layout, c->packed, c->step_state, (c->world > 1) ? c->exchange_epoch : nullptr, stream);
 }
 
 int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, int n_ranks, const float* multicast_grads,
                           float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2, double eps, int64_t step,
-                          float grad_scale, void* stream) {
+                          float grad_scale, unsigned int* const* peer_flags_host, int rank, const unsigned long long* exchange_epoch,
+                          void* stream) {
   DeviceInfo* dev;
   int rc = device_info(&dev);
   if (rc != NERF_OK) return rc;
@@ -685,9 +693,17 @@ int nerf_adam_step_reduce(float* params, const float* const* peer_grads_host, in
       (multicast_grads && !nerf_aligned(multicast_grads, 16)))
     return NERF_ERR_ALIGN;
   if (n == 0) return NERF_OK;
+  PeerFlags flags{};
+  if (exchange_epoch != nullptr) {
+    if (!peer_flags_host || rank < 0 || rank >= n_ranks) return NERF_ERR_ARG;
+    for (int r = 0; r < n_ranks; ++r) {
+      if (!peer_flags_host[r] || !nerf_aligned(peer_flags_host[r], 4)) return NERF_ERR_ALIGN;
+      flags.ptr[r] = peer_flags_host[r];
+    }
+  }
   adam_reduce_kernel<<<blocks_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(params, peers, n_ranks, multicast_grads, exp_avg, exp_avg_sq,
                                                                              n / 4, adam_coef(lr, beta1, beta2, eps, (double)step),
-                                                                             grad_scale, AdamSchedule{});
+                                                                             grad_scale, AdamSchedule{}, flags, rank, exchange_epoch);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }

@@ -466,9 +466,35 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // -- so there is no allreduce kernel and no reduced copy in HBM.  Both forms give every rank the same bits (the same
 // operation on the same operands in the same order), so the replicated weights stay bit-identical.  4 elements per thread.
 struct PeerGrads { const float* ptr[8]; };
+// Cross-rank barrier fused into the kernel: flags.ptr[r] = rank r's array of 8 epoch words (symmetric memory, mapped here);
+// word i of rank r's array is written by rank i.  Every rank announces "my gradient of exchange number `epoch` is complete"
+// to all ranks, then every block waits until all ranks have announced it to this rank.  Epochs only grow, so nothing is reset.
+struct PeerFlags { unsigned int* ptr[8]; };
 __global__ void adam_reduce_kernel(float* __restrict__ p, PeerGrads peers, int n_ranks, const float* mc_grads, float* __restrict__ m,
-                                   float* __restrict__ v, int64_t n4, AdamCoef c, float grad_scale, AdamSchedule sched) {
+                                   float* __restrict__ v, int64_t n4, AdamCoef c, float grad_scale, AdamSchedule sched,
+                                   PeerFlags flags, int rank, const unsigned long long* __restrict__ epoch_ptr) {
   adam_device_schedule(sched, c);
+  if (epoch_ptr != nullptr) {                            // block-uniform
+    const unsigned int epoch = (unsigned int)(*epoch_ptr) + 1u;
+    if (blockIdx.x == 0 && (int)threadIdx.x < n_ranks) {
+      // this kernel runs after wgrad in stream order: the local gradient is complete; make it visible system-wide, then signal
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.ptr[threadIdx.x] + rank), "r"(epoch) : "memory");
+    }
+    if ((int)threadIdx.x < n_ranks) {
+      const unsigned int* mine = flags.ptr[rank] + threadIdx.x;
+      unsigned int seen;
+      const long long t0 = clock64();
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+        if ((int)(seen - epoch) < 0 && (clock64() - t0) > 20000000000LL) {      // ~10 s: a rank is missing -- fail loudly, do not hang the box
+          printf("nerf_b200: gradient-exchange barrier timeout, rank %d waits for rank %d (epoch %u, seen %u)\n", rank, (int)threadIdx.x, epoch, seen);
+          __trap();
+        }
+      } while ((int)(seen - epoch) < 0);
+    }
+    __syncthreads();
+  }
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 g;

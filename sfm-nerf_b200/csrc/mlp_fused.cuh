@@ -756,9 +756,10 @@ __device__ __forceinline__ void pack_small(const float* __restrict__ params, con
 // is the last launch of a step and does not read it, so one thread advances it here for the next step.
 __global__ void pack_all_kernel(const float* __restrict__ params, const __grid_constant__ Program fwd, const __grid_constant__ Program bwd,
                                 const PackSmallArgs small_args, uint8_t* __restrict__ packed, float* __restrict__ small,
-                                unsigned long long* __restrict__ bump) {
+                                unsigned long long* __restrict__ bump, unsigned long long* __restrict__ bump2) {
   const int y = blockIdx.y;
   if (bump != nullptr && blockIdx.x == 0 && y == 0 && threadIdx.x == 0) *bump += 1ull;
+  if (bump2 != nullptr && blockIdx.x == 0 && y == 0 && threadIdx.x == 0) *bump2 += 1ull;       // gradient-exchange epoch (data parallel)
   if (y < fwd.n_steps) pack_image_step(params, fwd.s[y], packed);
   else if (y < fwd.n_steps + bwd.n_steps) pack_image_step(params, bwd.s[y - fwd.n_steps], packed);
   else if (blockIdx.x < 2) pack_small(params, small_args, small);

@@ -361,6 +361,7 @@ class Trainer:
         import os
         self.use_graph = bool(graph) and os.environ.get("NERF_TRAIN_GRAPH", "1") != "0"
         self.step_state = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.exchange_epoch = torch.zeros(1, dtype=torch.int64, device=dev)    # exchanges done so far (data parallel; only ever grows)
         self._dev_iteration = 0
         self._fixed = None                          # (odt, z, sigma_rgb, dsr, batch9) once the first fast step allocates them
         self._cfg = {}                              # (from_batch9, step parity) -> NerfTrainStep
@@ -415,9 +416,12 @@ class Trainer:
             # kernel reads the sum over ranks through the peers' mappings / the multicast address
             c.grads = self.exchange.local(parity).data_ptr()
             peers, mc = self.exchange.peer_pointers(parity)
+            flags = self.exchange.flag_pointers()
             for r in range(self.world):
                 c.peer_grads[r] = peers[r]
+                c.peer_flags[r] = flags[r]
             c.multicast_grads = mc
+            c.exchange_epoch = self.exchange_epoch.data_ptr()          # the cross-rank barrier runs inside the reduce-Adam kernel
         return c
 
     def _run_segment(self, name, fn):
@@ -462,12 +466,7 @@ class Trainer:
             call("nerf_train_step", cfg, mask, stream_ptr())
 
         def rest(first):                                      # everything after (or including) the forward phase
-            if ex is None:
-                phases(first | 6)
-            else:
-                phases(first | 2)
-                ex.barrier()
-                phases(4)
+            phases(first | 6)                                 # data parallel: the cross-rank barrier is inside the reduce-Adam kernel
 
         if loss_to_host:
             if self._loss_host is None:
@@ -556,13 +555,15 @@ class Trainer:
         lr = self.lr()
         if ex is not None and ex.mode != "nccl":
             # the gradient exchange is fused into the optimiser: barrier, then Adam reads the sum over ranks through NVLink
-            with _timed(timers, "grad_barrier"):
-                ex.barrier()
             peers, mc = ex.peer_pointers(self.iteration)
             self.iteration += 1
-            with _timed(timers, "adam_reduce"):        # Adam reading the gradient sum over ranks through NVLink (multimem / peer loads)
+            # Adam reading the gradient sum over ranks through NVLink (multimem / peer loads), the cross-rank barrier fused in: the
+            # time of this launch = wait for the slowest rank + the reduction + the update
+            with _timed(timers, "adam_reduce"):
                 call("nerf_adam_step_reduce", ptr(st.flat), peers, self.world, mc, ptr(self.exp_avg), ptr(self.exp_avg_sq), st.n_params,
-                     lr, self.betas[0], self.betas[1], self.eps, self.iteration, parallel.mean_scale(self.world), stream_ptr())
+                     lr, self.betas[0], self.betas[1], self.eps, self.iteration, parallel.mean_scale(self.world), ex.flag_pointers(),
+                     self.rank, ptr(self.exchange_epoch), stream_ptr())
+            self.exchange_epoch += 1
         else:
             if self.world > 1:
                 with _timed(timers, "allreduce"):

@@ -73,13 +73,14 @@ class GradExchange:
         import os
         self.n, self.world, self.group, self.device = int(n_params), int(world), group, torch.device(device)
         self.n_pad = (self.n + 63) // 64 * 64                                  # 256-byte aligned second buffer
+        self.n_flags = 64                                                      # barrier words behind the two gradient buffers (8 used)
         self.mode, self.why, self.handle = "nccl", "", None
         want = os.environ.get("NERF_GRAD_EXCHANGE", "")
         if self.world > 1 and self.device.type == "cuda" and want != "nccl":
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 grp = group if group is not None else dist.group.WORLD
-                buf = symm_mem.empty(2 * self.n_pad, dtype=torch.float32, device=self.device)
+                buf = symm_mem.empty(2 * self.n_pad + self.n_flags, dtype=torch.float32, device=self.device)
                 buf.zero_()
                 self.handle = symm_mem.rendezvous(buf, grp)
                 self.buf = buf
@@ -106,7 +107,7 @@ class GradExchange:
                 if agreed == "nccl":
                     self.handle = None
         if self.handle is None:
-            self.buf = torch.zeros(2 * self.n_pad, dtype=torch.float32, device=self.device)
+            self.buf = torch.zeros(2 * self.n_pad + self.n_flags, dtype=torch.float32, device=self.device)
 
     def local(self, step: int) -> torch.Tensor:
         """This rank's gradient buffer of ``step`` (wgrad writes it)."""
@@ -114,9 +115,16 @@ class GradExchange:
         return self.buf[o:o + self.n]
 
     def barrier(self):
-        """Stream-ordered cross-rank barrier: every rank's gradient of this step is complete and visible."""
+        """Stream-ordered cross-rank barrier (torch's symmetric-memory barrier kernel).  The train step does not use it any more:
+        the barrier is fused into the reduce-Adam kernel through ``flag_pointers`` (one launch less, no 16 us barrier kernel)."""
         if self.handle is not None:
             self.handle.barrier(channel=0)
+
+    def flag_pointers(self):
+        """ctypes array of every rank's barrier-word array (8 unsigned words behind its gradient buffers), in rank order."""
+        import ctypes as C
+        off = 2 * self.n_pad * 4
+        return (C.c_void_p * self.world)(*[p + off for p in self.peer_ptrs])
 
     def peer_pointers(self, step: int):
         """(ctypes array of the ranks' buffer addresses in rank order, multicast address or None) for ``step``."""
