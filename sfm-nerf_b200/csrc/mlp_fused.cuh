@@ -14,7 +14,7 @@
 //     slot 0 layer L (all k-steps) | slot 1 layer L | slot 0 layer L+1 | slot 1 layer L+1 | ...
 // and the tensor pipe executes in issue order, so slot 0's epilogue of layer L runs exactly under slot 1's MMAs of
 // layer L and vice versa: the pipe only idles if an epilogue takes longer than a layer of MMAs.  The loader streams the
-// slabs in that same order through one 16-slot ring (each layer's slabs twice, once per slot: 32 B/clk/SM from L2).
+// slabs in that same order through one ring of 8 slab pairs (each layer's slabs twice, once per slot: 32 B/clk/SM from L2).
 // Sharing one pass of slabs between the slots was measured too: it ties the slots to within one ring of each other,
 // too close to hide an epilogue (also with the lane-parallel loaders); a private 8-slot ring per slot covers less
 // than the load latency.
@@ -50,9 +50,6 @@ constexpr int kMlpThreads = 384;
 #ifndef NERF_WGRAD_PAIR
 #define NERF_WGRAD_PAIR 1           // 1: wgrad_pair.cuh (CTA pairs, heads on the tensor core); 0: wgrad.cuh + head_grad_kernel
 #endif
-#ifndef NERF_SLOT_OFFSET
-#define NERF_SLOT_OFFSET 0          // layers by which tile slot 1 trails tile slot 0 (see the sequence comment in the kernel)
-#endif
 #ifndef NERF_READBACK_BATCH
 #define NERF_READBACK_BATCH 8       // k-cores (16 B per row each) a read-back loop loads before it stores the first
 #endif
@@ -84,9 +81,9 @@ struct MlpArgs {
 struct MlpSmem {
   static constexpr int kAct = 0;                                   // 2 x 64 KB
   static constexpr int kEnc = kAct + 2 * kActBytes;                // 2 x 16 KB
-  static constexpr int kRing = kEnc + 2 * kEncBytes;               // 16 x 4 KB (this CTA's half of every slab)
+  static constexpr int kRing = kEnc + 2 * kEncBytes;               // 8 x 8 KB (slab pairs: this CTA's half of two k-steps each)
   static constexpr int kBars = kRing + kRingSlots * kRingSlotBytes;
-  // barriers (8 B each): full[16] @0, empty[16] @128, acc_full[2] @256, act_ready[2] @272, drain @288; tmem ptr @320
+  // barriers (8 B each): full[8] @0, empty[8] @128, acc_full[2] @256, act_ready[2] @272, drain @288; tmem ptr @320
   static constexpr int kTmemPtr = kBars + 320;
   static constexpr int kHead = kBars + 384;                        // fp32 head tables (w_d, b_d, W2, b2): 648 floats
   static constexpr int kHeadFloats = 648;
@@ -205,86 +202,82 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   const Program& P = a.prog;
   const int n_quads = (a.n_tiles + 3) >> 2;            // 4 tiles per cluster iteration: tile = 4*quad + 2*slot + rank
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  // The MMA issuer, the loaders and the relays walk ONE sequence of (tile slot, layer) passes: tick t = 0, 1, ... with slot 0 on
-  // its pass t and slot 1 on its pass t - NERF_SLOT_OFFSET (pass p = layer p % n_steps of this cluster's quad p / n_steps).  With
-  // offset 0 both slots work on the same layer of the same quad; with an offset of half a quad one slot's store-free phases
-  // (encoding prologue, the K = 64 first layer, the N = 128 last layer and its heads) fall into the other slot's store-bound layers.
+  // The MMA issuer, the loaders and the relays walk ONE sequence of passes: pass p = layer p % n_steps of this cluster's quad
+  // p / n_steps, tile slot 0's pass p and then tile slot 1's pass p.  The ring is addressed in SLAB PAIRS (two consecutive
+  // k-steps of a pass, 2 x 4 KB per CTA, one full and one empty barrier per pair): every pass starts on a fresh pair, a pass with
+  // an odd number of k-steps (16 activation k-steps + the bias k-step) leaves the second half of its last pair unused.  Before
+  // that (one barrier per slab, released in pairs) slot 1's passes began on an odd slab: the loader lane of the even slab then
+  // waited for a release that came a whole MMA group later, and those passes issued at ~170 instead of ~135 cycles per MMA
+  // (tools/trace_mlp.py: 2,900 against 2,300 cycles per 17-k-step pass, except at the 20-k-step skip layer).
   const int n_local = cluster_id < n_quads ? (n_quads - cluster_id + n_clusters - 1) / n_clusters : 0;   // quads of this cluster
   const int n_pass = n_local * P.n_steps;
-  const int n_ticks = n_pass > 0 ? n_pass + NERF_SLOT_OFFSET : 0;
 
   if (warp == 8 || warp == 10) {
     // ===================== weight loaders (both CTAs: this CTA's N/2 rows of every slab, every layer twice) ==========
-    // One slab per LANE, kLoadBatch slabs per trip, the two loader warps taking alternate trips: a single thread doing
-    // wait(empty) -> bulk copy -> arrive.expect_tx slab after slab is a chain of ~130-cycle barrier operations (~350
-    // cycles per slab -- what limited every earlier variant of this kernel); across lanes the same operations issue
-    // together, and two warps overlap their trips.  The copy is issued before the expect_tx arrival (the phase cannot
-    // complete while that arrival is pending, so the order is free) to get it on its way ~130 cycles earlier.
+    // One slab pair per trip, the two loader warps taking alternate trips (a single thread doing wait(empty) -> bulk copies ->
+    // arrive.expect_tx pair after pair is a chain of ~130-cycle barrier operations; two warps overlap their trips).  The
+    // copies are issued before the expect_tx arrival (the phase cannot complete while that arrival is pending, so the order
+    // is free) to get them on their way ~130 cycles earlier.
     const int which = (warp - 8) >> 1;
     const uint64_t keep_in_l2 = tc::l2_policy_evict_last();    // the 2.6 MB of weight images are re-read by every CTA, all the time
-    uint32_t it0 = 0, chunk = 0;                         // slabs issued before the current pass; trip counter
-    for (int t = 0; t < n_ticks; ++t) {
-      for (int slot = 0; slot < 2; ++slot) {             // slot 0's pass of this tick, then slot 1's
-        const int ps = t - slot * NERF_SLOT_OFFSET;
-        if (ps < 0 || ps >= n_pass) continue;
-        const Step& st = P.s[ps % P.n_steps];
-        const uint32_t bytes = (uint32_t)st.n * 16u;
-        const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
-        const uint8_t* src = a.packed + st.w_off + rank * bytes;
-        for (int k0 = 0; k0 < total; k0 += kLoadBatch, ++chunk) {
-          if ((int)(chunk & 1u) != which) continue;
-          const int k = k0 + lane;
-          if (lane < kLoadBatch && k < total) {
-            const uint32_t it = it0 + (uint32_t)k;
+    uint32_t pj0 = 0, trip = 0;                          // slab pairs issued before the current pass; trip counter
+    int si = 0;
+    for (int ps = 0; ps < n_pass; ++ps) {
+      const Step& st = P.s[si];
+      si = (si + 1 == P.n_steps) ? 0 : si + 1;
+      const uint32_t bytes = (uint32_t)st.n * 16u;
+      const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
+      const int n_pairs = (total + 1) >> 1;
+      const uint8_t* src = a.packed + st.w_off + rank * bytes;
+      for (int slot = 0; slot < 2; ++slot) {             // slot 0's pass, then slot 1's
+        for (int j = 0; j < n_pairs; ++j, ++trip) {
+          if ((int)(trip & 1u) != which) continue;
+          if (lane == 0) {
+            const uint32_t it = pj0 + (uint32_t)j;
             const uint32_t rs = it % kRingSlots, ph = (it / kRingSlots) & 1u;
-            tc::mbar_wait(bar_empty + 8 * (rs | (uint32_t)(kCommitGroup - 1)), ph ^ 1u);   // slots are released in groups
-            tc::bulk_g2s_hint(s_ring + rs * kRingSlotBytes, src + (size_t)k * (2u * bytes), bytes, bar_full + 8 * rs, keep_in_l2);
-            tc::mbar_arrive_expect_tx(bar_full + 8 * rs, bytes);
+            const bool two = 2 * j + 1 < total;
+            tc::mbar_wait(bar_empty + 8 * rs, ph ^ 1u);
+            tc::bulk_g2s_hint(s_ring + rs * kRingSlotBytes, src + (size_t)(2 * j) * (2u * bytes), bytes, bar_full + 8 * rs, keep_in_l2);
+            if (two) tc::bulk_g2s_hint(s_ring + rs * kRingSlotBytes + kSlabBytes, src + (size_t)(2 * j + 1) * (2u * bytes), bytes, bar_full + 8 * rs, keep_in_l2);
+            tc::mbar_arrive_expect_tx(bar_full + 8 * rs, two ? 2u * bytes : bytes);
           }
           __syncwarp();
         }
-        it0 += (uint32_t)total;
+        pj0 += (uint32_t)n_pairs;
       }
     }
     if (warp == 8 && lane == 0) {
-      // tail: every multicast commit onto this CTA's barriers has landed before it may exit.  Complete groups are
-      // waited for like a further load would; a trailing partial group is covered by the drain barrier, which the MMA
-      // warp commits to last (a ring barrier must never complete a phase the loader has not waited for yet: a second
-      // completion would alias the parity wait).
-      const uint32_t n_slabs = it0;
-      uint32_t it = it0;
-      for (int t = 0; t < kRingSlots; ++t, ++it) {
-        const uint32_t group_last = (it - kRingSlots) | (uint32_t)(kCommitGroup - 1);      // of the slab this wait covers
-        if (it >= (uint32_t)kRingSlots && group_last < n_slabs)
-          tc::mbar_wait(bar_empty + 8 * (group_last % kRingSlots), ((it / kRingSlots) & 1u) ^ 1u);
-      }
+      // tail: every multicast commit onto this CTA's barriers has landed before it may exit -- the releases of the last
+      // ring-ful of pairs (each is the phase a further load into that slot would wait for), then the drain barrier
+      const uint32_t n_all = pj0;
+      for (uint32_t it = n_all > (uint32_t)kRingSlots ? n_all - kRingSlots : 0u; it < n_all; ++it)
+        tc::mbar_wait(bar_empty + 8 * (it % kRingSlots), (it / kRingSlots) & 1u);
       tc::mbar_wait(bar_drain, 0);
     }
     __syncwarp();
   } else if ((warp == 9 || warp == 11) && rank != 0) {
-    // ===================== peer: relay "my half of slab j has landed" to the leader's full barrier =====================
-    // (one slab per lane, alternate trips per warp, like the loaders)
+    // ===================== peer: relay "my half of slab pair j has landed" to the leader's full barrier ================
+    // (alternate trips per warp, like the loaders)
     const int which = (warp - 9) >> 1;
     const uint32_t leader_full = tc::mapa(bar_full, 0);
-    uint32_t it0 = 0, chunk = 0;
-    for (int t = 0; t < n_ticks; ++t) {
+    uint32_t pj0 = 0, trip = 0;
+    int si = 0;
+    for (int ps = 0; ps < n_pass; ++ps) {
+      const Step& st = P.s[si];
+      si = (si + 1 == P.n_steps) ? 0 : si + 1;
+      const int n_pairs = (st.act_ksteps + st.enc_ksteps + st.bias_kstep + 1) >> 1;
       for (int slot = 0; slot < 2; ++slot) {
-        const int ps = t - slot * NERF_SLOT_OFFSET;
-        if (ps < 0 || ps >= n_pass) continue;
-        const Step& st = P.s[ps % P.n_steps];
-        const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
-        for (int k0 = 0; k0 < total; k0 += kLoadBatch, ++chunk) {
-          if ((int)(chunk & 1u) != which) continue;
-          const int k = k0 + lane;
-          if (lane < kLoadBatch && k < total) {
-            const uint32_t it = it0 + (uint32_t)k;
+        for (int j = 0; j < n_pairs; ++j, ++trip) {
+          if ((int)(trip & 1u) != which) continue;
+          if (lane == 0) {
+            const uint32_t it = pj0 + (uint32_t)j;
             const uint32_t rs = it % kRingSlots;
             tc::mbar_wait(bar_full + 8 * rs, (it / kRingSlots) & 1u);
             tc::mbar_arrive_cluster(leader_full + 8 * rs);
           }
           __syncwarp();
         }
-        it0 += (uint32_t)total;
+        pj0 += (uint32_t)n_pairs;
       }
     }
   } else if (warp == 9) {
@@ -294,133 +287,107 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
     // (all measured, tools/umma_rate.py + tools/trace_mlp.py):
     //  * consecutive UTCHMMAs that reuse the same uniform registers for their descriptors serialise on the previous
     //    one's scoreboard (~225 cycles per MMA): k-steps are issued four at a time from ONE asm block whose eight
-    //    descriptors are live inputs (tc::umma_bf16_pair_x4), the A descriptors advancing linearly inside three runs
-    //    (activation k-steps, encoding k-steps, the bias k-step);
-    //  * any mbarrier operation costs the warp ~130 cycles: the four full barriers of a group are probed back to back
-    //    (independent try_waits overlap) and blocked on one by one only when a slab has not landed yet;
-    //  * ring slots are released (tcgen05.commit, multicast to both CTAs) per kCommitGroup = 2 k-steps.
+    //    descriptors are live inputs, with the two ring releases (tcgen05.commit, multicast to both CTAs) inside the block;
+    //  * any mbarrier operation costs the warp ~130 cycles: the full barriers of a trip (8 k-steps = 4 slab pairs) are probed
+    //    back to back (independent try_waits overlap) and blocked on one by one only when a pair has not landed yet;
+    //  * the next pass's "A tile ready" barrier is probed together with the last trip's full barriers, so the hand-over
+    //    from one tile slot to the other costs no serial barrier round trip (the pipe ran dry for 400-900 cycles there);
+    //  * k-steps are grouped from the start of the pass, across the activation / encoding / bias runs of the A operand.
     const uint64_t desc_hi = (uint64_t)(((128u >> 4) & 0x3FFFu) | (1u << 14)) << 32;      // SBO = 128 B, version 1
     const uint32_t a_lbo = ((uint32_t)kKcoreBytes >> 4) << 16;                              // LBO = 2048 B
     const uint32_t ring_lo = (s_ring & 0x3FFFFu) >> 4;
     constexpr uint32_t kStepLo = (2 * kKcoreBytes) >> 4;                                    // A descriptor advance per k-step
-    constexpr uint32_t kSlabLo = kRingSlotBytes >> 4;
-    uint32_t rs = 0, par = 0;                                      // ring slot / parity of the next slab
+    constexpr uint32_t kSlotLo = kRingSlotBytes >> 4, kSlabLo = kSlabBytes >> 4;
+    uint32_t pj = 0;                                               // slab pairs consumed so far: ring slot pj % 8, parity (pj / 8) & 1
+    bool act_ok = false;                                           // the coming pass's A tile was already seen ready
+    int si = 0;
+    for (int ps = 0; ps < n_pass; ++ps) {
+      const int n = P.s[si].n, act_ks = P.s[si].act_ksteps, enc_ks = P.s[si].enc_ksteps;
+      const int total = act_ks + enc_ks + P.s[si].bias_kstep;
+      const int si_now = si; (void)si_now;
+      si = (si + 1 == P.n_steps) ? 0 : si + 1;
+      const uint32_t idesc = tc::umma_idesc_bf16(256, n, 0, 0);
+      const uint32_t b_lo = ((((uint32_t)n * 8u) >> 4) << 16) | ring_lo;        // LBO = (N/2 rows) * 16 B
+#pragma unroll 1
+      for (int slot = 0; slot < 2; ++slot) {
+        const uint32_t act_lo = a_lbo | (((s_base + MlpSmem::kAct + slot * kActBytes) & 0x3FFFFu) >> 4);
+        const uint32_t enc_lo = a_lbo | (((s_base + MlpSmem::kEnc + slot * kEncBytes) & 0x3FFFFu) >> 4);
+        const uint32_t d_tmem = tmem_base + 256 * slot;
+        // the pass after this one: the other slot's pass ps (slot 0 -> 1) or slot 0's pass ps + 1
+        const bool has_next = slot == 0 || ps + 1 < n_pass;
+        const uint32_t next_bar = bar_act + 8 * (slot ^ 1), next_par = (uint32_t)(ps + slot) & 1u;
+        // A descriptor of k-step k of the pass: activation k-steps, then encoding k-steps, then the bias k-step (ENC k-step 3)
+        auto a_desc = [&](int k) -> uint64_t {
+          const int e = k - act_ks;
+          return desc_hi | ((e < 0) ? act_lo + (uint32_t)k * kStepLo : enc_lo + (uint32_t)(e < enc_ks ? e : 3) * kStepLo);
+        };
+        auto b_desc = [&](uint32_t pair, uint32_t half) -> uint64_t {
+          return desc_hi | (b_lo + (pair % kRingSlots) * kSlotLo + half * kSlabLo);
+        };
+        auto full_bar = [&](uint32_t pair) -> uint32_t { return bar_full + 8 * (pair % kRingSlots); };
+        auto empty_bar = [&](uint32_t pair) -> uint32_t { return bar_empty + 8 * (pair % kRingSlots); };
+        auto par_of = [&](uint32_t pair) -> uint32_t { return (pair / kRingSlots) & 1u; };
 
-    for (int t = 0; t < n_ticks; ++t) {
-      {
-#pragma unroll 1
-        for (int slot = 0; slot < 2; ++slot) {
-          const int ps = t - slot * NERF_SLOT_OFFSET;                // this slot's pass: its act_ready barrier is in phase ps
-          if (ps < 0 || ps >= n_pass) continue;
-          const int si = ps % P.n_steps;
-          const uint32_t act_phase = (uint32_t)ps;
-          const int n = P.s[si].n, act_ks = P.s[si].act_ksteps, enc_ks = P.s[si].enc_ksteps, bias_ks = P.s[si].bias_kstep;
-          const uint32_t idesc = tc::umma_idesc_bf16(256, n, 0, 0);
-          const uint32_t b_lo = ((((uint32_t)n * 8u) >> 4) << 16) | ring_lo;      // LBO = (N/2 rows) * 16 B
-          const uint32_t act_lo = a_lbo | (((s_base + MlpSmem::kAct + slot * kActBytes) & 0x3FFFFu) >> 4);
-          const uint32_t enc_lo = a_lbo | (((s_base + MlpSmem::kEnc + slot * kEncBytes) & 0x3FFFFu) >> 4);
-          const uint32_t d_tmem = tmem_base + 256 * slot;
-          tc::mbar_wait_cluster(bar_act + 8 * slot, act_phase & 1u);       // this slot's A tile of the layer is ready
-          tc::tc_fence_after();
+        if (!act_ok) tc::mbar_wait_cluster(bar_act + 8 * slot, (uint32_t)ps & 1u);   // this slot's A tile of the layer is ready
+        act_ok = false;
+        tc::tc_fence_after();
 #ifdef NERF_DIAGNOSTICS
-          long long* tr = (a.trace != nullptr && blockIdx.x == 0 && lane == 0)
-                              ? a.trace + ((size_t)((ps / P.n_steps) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
-          if (tr) tr[0] = clock64();
+        long long* tr = (a.trace != nullptr && blockIdx.x == 0 && lane == 0)
+                            ? a.trace + ((size_t)((ps / P.n_steps) * kMaxSteps + si_now) * 2 + slot) * 4 : nullptr;
+        if (tr) tr[0] = clock64();
 #endif
-          int k_done = 0;
+        int k = 0;
 #pragma unroll 1
-          for (int seg = 0; seg < 3; ++seg) {
-            int cnt = (seg == 0) ? act_ks : (seg == 1) ? enc_ks : bias_ks;
-            uint32_t a_cur = (seg == 0) ? act_lo : (seg == 1) ? enc_lo : enc_lo + 3u * kStepLo;     // bias: ENC k-step 3
+        while (total - k >= 8) {                         // a trip: 8 k-steps = 4 slab pairs, two 4-MMA blocks
+          const bool last = (total - k == 8);
+          const uint64_t a0 = a_desc(k), a1 = a_desc(k + 1), a2 = a_desc(k + 2), a3 = a_desc(k + 3),
+                         a4 = a_desc(k + 4), a5 = a_desc(k + 5), a6 = a_desc(k + 6), a7 = a_desc(k + 7);
+          const uint64_t b0 = b_desc(pj, 0), b1 = b_desc(pj, 1), b2 = b_desc(pj + 1, 0), b3 = b_desc(pj + 1, 1),
+                         b4 = b_desc(pj + 2, 0), b5 = b_desc(pj + 2, 1), b6 = b_desc(pj + 3, 0), b7 = b_desc(pj + 3, 1);
+          const uint32_t r01 = (uint32_t)tc::mbar_try_wait_cluster(full_bar(pj), par_of(pj)) & (uint32_t)tc::mbar_try_wait_cluster(full_bar(pj + 1), par_of(pj + 1));
+          const uint32_t r23 = (uint32_t)tc::mbar_test_wait(full_bar(pj + 2), par_of(pj + 2)) & (uint32_t)tc::mbar_test_wait(full_bar(pj + 3), par_of(pj + 3));
+          if (last && has_next) act_ok = tc::mbar_test_wait(next_bar, next_par);
+          if (!r01) { tc::mbar_wait_cluster(full_bar(pj), par_of(pj)); tc::mbar_wait_cluster(full_bar(pj + 1), par_of(pj + 1)); }
+          if (tc::elect_one())
+            tc::umma_bf16_pair_x4_release2(d_tmem, a0, a1, a2, a3, b0, b1, b2, b3, idesc, k > 0 ? 1u : 0u, empty_bar(pj), empty_bar(pj + 1));
+          __syncwarp();
+          if (!r23) { tc::mbar_wait_cluster(full_bar(pj + 2), par_of(pj + 2)); tc::mbar_wait_cluster(full_bar(pj + 3), par_of(pj + 3)); }
+          if (tc::elect_one())
+            tc::umma_bf16_pair_x4_release2(d_tmem, a4, a5, a6, a7, b4, b5, b6, b7, idesc, 1u, empty_bar(pj + 2), empty_bar(pj + 3));
+          __syncwarp();
+          pj += 4; k += 8;
+        }
 #pragma unroll 1
-            // Two groups per trip while eight k-steps remain, all sixteen descriptors and parities derived up front: the
-            // second group goes out right behind the first one's commits (measured: 6200 -> 5570 cycles per layer pair).
-            // ptxas still stages both groups' descriptors through the same uniform registers (also when the second
-            // set is kept live across the first block), and one 8-MMA block needs all eight slabs landed (much slower).
-            while (cnt >= 2 * kWaitGroup) {
-              const uint32_t s0 = rs & (kRingSlots - 1), s1 = (rs + 1) & (kRingSlots - 1), s2 = (rs + 2) & (kRingSlots - 1),
-                             s3 = (rs + 3) & (kRingSlots - 1), s4 = (rs + 4) & (kRingSlots - 1), s5 = (rs + 5) & (kRingSlots - 1),
-                             s6 = (rs + 6) & (kRingSlots - 1), s7 = (rs + 7) & (kRingSlots - 1);
-              const uint64_t a0 = desc_hi | a_cur, a1 = desc_hi | (a_cur + kStepLo), a2 = desc_hi | (a_cur + 2 * kStepLo),
-                             a3 = desc_hi | (a_cur + 3 * kStepLo), a4 = desc_hi | (a_cur + 4 * kStepLo), a5 = desc_hi | (a_cur + 5 * kStepLo),
-                             a6 = desc_hi | (a_cur + 6 * kStepLo), a7 = desc_hi | (a_cur + 7 * kStepLo);
-              const uint64_t b0 = desc_hi | (b_lo + s0 * kSlabLo), b1 = desc_hi | (b_lo + s1 * kSlabLo), b2 = desc_hi | (b_lo + s2 * kSlabLo),
-                             b3 = desc_hi | (b_lo + s3 * kSlabLo), b4 = desc_hi | (b_lo + s4 * kSlabLo), b5 = desc_hi | (b_lo + s5 * kSlabLo),
-                             b6 = desc_hi | (b_lo + s6 * kSlabLo), b7 = desc_hi | (b_lo + s7 * kSlabLo);
-              const uint32_t p0 = par ^ (rs >> 4), p1 = par ^ ((rs + 1) >> 4), p2 = par ^ ((rs + 2) >> 4), p3 = par ^ ((rs + 3) >> 4),
-                             p4 = par ^ ((rs + 4) >> 4), p5 = par ^ ((rs + 5) >> 4), p6 = par ^ ((rs + 6) >> 4), p7 = par ^ ((rs + 7) >> 4);
-              uint32_t ready = (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s0, p0) & (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s1, p1) &
-                               (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s2, p2) & (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s3, p3);
-              if (!ready) {
-                tc::mbar_wait_cluster(bar_full + 8 * s0, p0); tc::mbar_wait_cluster(bar_full + 8 * s1, p1);
-                tc::mbar_wait_cluster(bar_full + 8 * s2, p2); tc::mbar_wait_cluster(bar_full + 8 * s3, p3);
+        while (k < total) {                              // the remainder of the pass: up to four k-steps (two pairs) at a time
+          const int kn = (total - k) < 4 ? (total - k) : 4;
+          const bool last = (k + kn == total);
+          const uint32_t r0 = (uint32_t)tc::mbar_try_wait_cluster(full_bar(pj), par_of(pj));
+          const uint32_t r1 = kn > 2 ? (uint32_t)tc::mbar_test_wait(full_bar(pj + 1), par_of(pj + 1)) : 1u;
+          if (last && has_next) act_ok = tc::mbar_test_wait(next_bar, next_par);
+          if (!r0) tc::mbar_wait_cluster(full_bar(pj), par_of(pj));
+          if (!r1) tc::mbar_wait_cluster(full_bar(pj + 1), par_of(pj + 1));
+          if (tc::elect_one()) {
+            if (kn == 4) {
+              tc::umma_bf16_pair_x4_release2(d_tmem, a_desc(k), a_desc(k + 1), a_desc(k + 2), a_desc(k + 3), b_desc(pj, 0), b_desc(pj, 1),
+                                             b_desc(pj + 1, 0), b_desc(pj + 1, 1), idesc, k > 0 ? 1u : 0u, empty_bar(pj), empty_bar(pj + 1));
+            } else {
+              for (int q = 0; q < kn; ++q) {
+                tc::umma_bf16_pair(d_tmem, a_desc(k + q), b_desc(pj + (uint32_t)(q >> 1), (uint32_t)(q & 1)), idesc, (k + q) > 0 ? 1u : 0u);
+                if ((q & 1) || q == kn - 1) tc::umma_commit_pair(empty_bar(pj + (uint32_t)(q >> 1)), 3);
               }
-              if (tc::elect_one()) {
-                tc::umma_bf16_pair_x4(d_tmem, a0, a1, a2, a3, b0, b1, b2, b3, idesc, k_done > 0 ? 1u : 0u);
-                tc::umma_commit_pair(bar_empty + 8 * ((s0 & 1u) ? s0 : s1), 3);
-                tc::umma_commit_pair(bar_empty + 8 * ((s0 & 1u) ? s2 : s3), 3);
-              }
-              __syncwarp();
-              ready = (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s4, p4) & (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s5, p5) &
-                      (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s6, p6) & (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * s7, p7);
-              if (!ready) {
-                tc::mbar_wait_cluster(bar_full + 8 * s4, p4); tc::mbar_wait_cluster(bar_full + 8 * s5, p5);
-                tc::mbar_wait_cluster(bar_full + 8 * s6, p6); tc::mbar_wait_cluster(bar_full + 8 * s7, p7);
-              }
-              if (tc::elect_one()) {
-                tc::umma_bf16_pair_x4(d_tmem, a4, a5, a6, a7, b4, b5, b6, b7, idesc, 1u);
-                tc::umma_commit_pair(bar_empty + 8 * ((s0 & 1u) ? s4 : s5), 3);
-                tc::umma_commit_pair(bar_empty + 8 * ((s0 & 1u) ? s6 : s7), 3);
-              }
-              __syncwarp();
-              rs += 2 * kWaitGroup;
-              if (rs >= (uint32_t)kRingSlots) { rs -= kRingSlots; par ^= 1u; }
-              a_cur += 2 * kWaitGroup * kStepLo;
-              cnt -= 2 * kWaitGroup; k_done += 2 * kWaitGroup;
-            }
-            while (cnt > 0) {
-              const int kn = cnt < kWaitGroup ? cnt : kWaitGroup;
-              uint32_t ready = 1u;
-#pragma unroll
-              for (int q = 0; q < kWaitGroup; ++q) {
-                if (q < kn) ready &= (uint32_t)tc::mbar_try_wait_cluster(bar_full + 8 * ((rs + q) & (kRingSlots - 1)), par ^ ((rs + q) >> 4));
-              }
-              if (!ready) {
-                for (int q = 0; q < kn; ++q) tc::mbar_wait_cluster(bar_full + 8 * ((rs + q) & (kRingSlots - 1)), par ^ ((rs + q) >> 4));
-              }
-              if (tc::elect_one()) {
-                if (kn == kWaitGroup) {
-                  const uint32_t s0 = rs & (kRingSlots - 1), s1 = (rs + 1) & (kRingSlots - 1), s2 = (rs + 2) & (kRingSlots - 1),
-                                 s3 = (rs + 3) & (kRingSlots - 1);
-                  tc::umma_bf16_pair_x4(d_tmem, desc_hi | a_cur, desc_hi | (a_cur + kStepLo), desc_hi | (a_cur + 2 * kStepLo),
-                                        desc_hi | (a_cur + 3 * kStepLo), desc_hi | (b_lo + s0 * kSlabLo), desc_hi | (b_lo + s1 * kSlabLo),
-                                        desc_hi | (b_lo + s2 * kSlabLo), desc_hi | (b_lo + s3 * kSlabLo), idesc, k_done > 0 ? 1u : 0u);
-                  tc::umma_commit_pair(bar_empty + 8 * ((s0 & 1u) ? s0 : s1), 3);   // the odd slot's barrier stands for its pair
-                  tc::umma_commit_pair(bar_empty + 8 * ((s0 & 1u) ? s2 : s3), 3);
-                } else {
-                  for (int q = 0; q < kn; ++q) {
-                    const uint32_t sl = (rs + q) & (kRingSlots - 1);
-                    tc::umma_bf16_pair(d_tmem, desc_hi | (a_cur + (uint32_t)q * kStepLo), desc_hi | (b_lo + sl * kSlabLo), idesc, (k_done + q) > 0 ? 1u : 0u);
-                    if (sl & 1u) tc::umma_commit_pair(bar_empty + 8 * sl, 3);
-                  }
-                }
-              }
-              __syncwarp();
-              rs += (uint32_t)kn;
-              if (rs >= (uint32_t)kRingSlots) { rs -= kRingSlots; par ^= 1u; }
-              a_cur += (uint32_t)kn * kStepLo;
-              cnt -= kn; k_done += kn;
             }
           }
-          if (tc::elect_one()) tc::umma_commit_pair(bar_acc + 8 * slot, 3);
           __syncwarp();
-#ifdef NERF_DIAGNOSTICS
-          if (tr) tr[1] = clock64();
-#endif
+          pj += (uint32_t)((kn + 1) >> 1); k += kn;
         }
+        if (tc::elect_one()) tc::umma_commit_pair(bar_acc + 8 * slot, 3);
+        __syncwarp();
+#ifdef NERF_DIAGNOSTICS
+        if (tr) tr[1] = clock64();
+#endif
       }
     }
-    // a trailing odd slab has no commit of its own: the drain barrier covers it (and every earlier commit)
+    // every earlier commit is covered by the drain barrier (both CTAs' loaders wait for it before they exit)
     if (tc::elect_one()) tc::umma_commit_pair(bar_drain, 3);
     __syncwarp();
   } else if (warp < 8) {

@@ -22,11 +22,10 @@ constexpr int kNumLinear = 13;          // fc1, fc_layers x4, skip, fc_layers2 x
 constexpr int kKcoreBytes = 2048;       // 128 rows x 16 B
 constexpr int kActBytes = 32 * kKcoreBytes;   // 256 channels = 64 KB
 constexpr int kEncBytes = 8 * kKcoreBytes;    // 64 channels  = 16 KB
-constexpr int kRingSlots = 16;                // slabs in flight (the two tile slots take turns, each streams its own pass of a layer's slabs)
-constexpr int kRingSlotBytes = 128 * 32;      // one CTA's half (N/2 = 128 rows) of a K=16 step of an N=256 layer = 4 KB
-constexpr int kCommitGroup = 2;               // ring slots are released (one tcgen05.commit) per this many k-steps (the odd slot's barrier)
-constexpr int kLoadBatch = 2;                 // slabs a loader / relay warp handles per trip (one per lane): finer trips = shorter supply latency
-constexpr int kWaitGroup = 4;                 // k-steps whose full barriers an MMA warp polls back to back before issuing them
+constexpr int kSlabBytes = 128 * 32;          // one CTA's half (N/2 = 128 rows) of a K=16 step of an N=256 layer = 4 KB
+constexpr int kRingSlotBytes = 2 * kSlabBytes; // a ring slot holds a SLAB PAIR: two consecutive k-steps of one pass (the second half stays
+                                              // unused for the last k-step of a pass with an odd number of them)
+constexpr int kRingSlots = 8;                 // slab pairs in flight (the two tile slots take turns, each streams its own pass of a layer's slabs)
 
 // epilogue flags
 enum : int32_t {

@@ -78,6 +78,18 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// NON-BLOCKING probe (mbarrier.test_wait): try_wait may suspend the thread up to a system time limit when the phase is not
+// complete (measured: an early try_wait on a barrier thousands of cycles from completing held the MMA warp for ~3,000 cycles),
+// so anything probed AHEAD of need -- the next pass's A tile, the second half of a trip -- must use this form.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 // wait on a local mbarrier that CTAs of the whole cluster arrive on (acquire at cluster scope)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait_cluster(bar, parity)) return;
@@ -269,6 +281,26 @@ __device__ __forceinline__ void umma_bf16_pair_x4(uint32_t d_tmem, uint64_t a0, 
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %3, %7, %9, t;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %4, %8, %9, t;\n\t}"
       ::"r"(d_tmem), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(accumulate_first) : "memory");
+}
+// The same four k-steps with the two ring releases inside the block: the commit for the first slab pair goes out right behind
+// the second MMA (its slot returns to the loaders two MMA-times earlier than with both commits behind the fourth), the commit
+// for the second pair behind the fourth.  Both are multicast to the two CTAs of the pair (mask 3).
+__device__ __forceinline__ void umma_bf16_pair_x4_release2(uint32_t d_tmem, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3, uint64_t b0,
+                                                           uint64_t b1, uint64_t b2, uint64_t b3, uint32_t idesc, uint32_t accumulate_first,
+                                                           uint32_t bar0, uint32_t bar1) {
+  asm volatile(
+      "{\n\t.reg .pred p, t;\n\t.reg .b16 m;\n\t"
+      "setp.ne.b32 p, %10, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %5, %9, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %2, %6, %9, t;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%11], m;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %3, %7, %9, t;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %4, %8, %9, t;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%12], m;\n\t}"
+      ::"r"(d_tmem), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(accumulate_first),
+        "r"(bar0), "r"(bar1) : "memory");
 }
 // arrive on the mbarrier at this offset in every CTA of `cta_mask` once all previously issued pair MMAs completed
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
