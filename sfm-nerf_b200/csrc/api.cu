@@ -69,7 +69,7 @@ int device_info(DeviceInfo** out) {
     NERF_CUDA_TRY(cudaFuncSetAttribute(selftest_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
     // how many CTA pairs of the fused MLP kernel the device can hold at once (one CTA per SM, pairs share a TPC)
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(g_dev.sms & ~1); cfg.blockDim = dim3(mlp_threads<MODE_FWD, true>()); cfg.dynamicSmemBytes = MlpSmem::kTotal;
+    cfg.gridDim = dim3(g_dev.sms & ~1); cfg.blockDim = dim3(kMlpThreads); cfg.dynamicSmemBytes = MlpSmem::kTotal;
     cudaLaunchAttribute at{};
     at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
     cfg.attrs = &at; cfg.numAttrs = 1;
@@ -147,7 +147,7 @@ int launch_forward(const void* packed, int layout, const float* pos, const float
   a.stash = static_cast<uint8_t*>(stash);
   a.prog = m->fwd;
   const int grid = mlp_grid(*dev, a.n_tiles);
-  if (stash) mlp_fused_kernel<MODE_FWD, true><<<grid, mlp_threads<MODE_FWD, true>(), MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
+  if (stash) mlp_fused_kernel<MODE_FWD, true><<<grid, kMlpThreads, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
   else mlp_fused_kernel<MODE_FWD, false><<<grid, kMlpThreads, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
@@ -384,7 +384,7 @@ int nerf_mlp_dgrad(const void* packed, int layout, const void* stash, const floa
   a.dstash = static_cast<uint8_t*>(dstash);
   a.prog = m->bwd;
   const int grid = mlp_grid(*dev, a.n_tiles);
-  mlp_fused_kernel<MODE_BWD, false><<<grid, mlp_threads<MODE_BWD, false>(), MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
+  mlp_fused_kernel<MODE_BWD, false><<<grid, kMlpThreads, MlpSmem::kTotal, (cudaStream_t)stream>>>(a);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }

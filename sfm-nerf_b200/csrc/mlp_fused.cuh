@@ -40,21 +40,13 @@ constexpr int MODE_BWD = 1;
 // warp's index in the CTA tied to the SM sub-partition it runs on: with 320 threads the epilogue warps were seen in
 // rotated hardware slots (cuda-gdb) and tcgen05.ld raised "misaligned address", depending on what ran on the SM before.
 constexpr int kMlpThreads = 384;
-// The training forward and dgrad give warp 11 (idle in the leader, the second slab relay in the peer) a job: it prepares the NEXT
-// quad's tile inputs while the epilogue warpgroups work on the current one -- the positional / direction encodings (forward) or
-// the head cotangents and dR1 (dgrad) go to their blocks of the stash / dstash in HBM, where they have to be written anyway, and
-// come back into the encoding / activation tile as ONE bulk copy issued the moment the tile's last MMAs have completed.  Before
-// that the epilogue warps computed them between two quads with the tensor pipe idle: 6,300 (forward) / 11,000 (dgrad) cycles of
-// a 77,000 / 72,000-cycle quad (tools/trace_mlp.py).  One warp suffices (4 rows per lane and tile, ~10-30 % of its issue slots).
-// A fourth warpgroup of 128 threads with setmaxnreg was built first: the boundary vanished as well, but the steady-state layer
-// period grew by 10-15 % with 16 resident warps, for every register split tried (profiles/r2_prologue_warp.md).
-#ifndef NERF_PROLOGUE_WG
-#define NERF_PROLOGUE_WG 1          // 0: the epilogue warps compute the tile inputs themselves (the inference kernel always does)
-#endif
-template <int MODE, bool TRAIN>
-__host__ __device__ constexpr bool mlp_has_prologue_wg() { return (TRAIN || MODE == 1) && NERF_PROLOGUE_WG != 0; }
-template <int MODE, bool TRAIN>
-__host__ __device__ constexpr int mlp_threads() { return kMlpThreads; }
+// How a layer's output tile reaches the training stash (forward) / the gradient stash (dgrad): the forward's epilogue threads read
+// their rows of the tile back after the release and stream them with 16-byte stores; dgrad stores the packed words straight
+// from the accumulator read-out loop.  Round 2 built and A/B-timed every alternative -- stores from the read-out registers in
+// the forward, one bulk (TMA) store per tile, bulk stores in 2-8 KB pieces with 0-2 in flight, read-back for dgrad, read-back
+// stores that yield to the other slot's read-out -- and all were equal or slower: both kernels are bound by how fast an SM
+// streams these stores (22 B/clk = 6.3 TB/s chip-wide, tools/store_rate.py), not by who issues them.  The table is
+// profiles/r2_stash_store_variants.md; the code of the variants is in the history (commits 74f67cc .. a0e94fb).
 #ifndef NERF_WGRAD_PAIR
 #define NERF_WGRAD_PAIR 1           // 1: wgrad_pair.cuh (CTA pairs, heads on the tensor core); 0: wgrad.cuh + head_grad_kernel
 #endif
@@ -91,8 +83,7 @@ struct MlpSmem {
   static constexpr int kEnc = kAct + 2 * kActBytes;                // 2 x 16 KB
   static constexpr int kRing = kEnc + 2 * kEncBytes;               // 8 x 8 KB (slab pairs: this CTA's half of two k-steps each)
   static constexpr int kBars = kRing + kRingSlots * kRingSlotBytes;
-  // barriers (8 B each): full[8] @0, empty[8] @128, prologue-warp handshake @192 (dead[2], dedead[2] @208, tile[2] @224, de[2] @240),
-  // acc_full[2] @256, act_ready[2] @272, drain @288; tmem ptr @320
+  // barriers (8 B each): full[8] @0, empty[8] @128, acc_full[2] @256, act_ready[2] @272, drain @288; tmem ptr @320
   static constexpr int kTmemPtr = kBars + 320;
   static constexpr int kHead = kBars + 384;                        // fp32 head tables (w_d, b_d, W2, b2): 648 floats
   static constexpr int kHeadFloats = 648;
@@ -161,45 +152,6 @@ __device__ __forceinline__ void write_encoding(uint32_t enc_smem, int row, const
   }
 }
 
-// The same encoding for FOUR rows of a tile at once (rows row0 + 32 i: one lane of the prologue warp), written ONLY to global
-// memory, as compact code: a rolled loop over the levels, one range reduction per (row, level, coordinate) like write_encoding
-// (identical bits), the four rows interleaved for instruction-level parallelism -- a single warp has no other latency hiding --
-// and each bf16 stored on its own (st.global.b16; L2 merges them, the tile comes back as one bulk copy).  The fully unrolled
-// per-row form added ~20 KB of instructions to the kernel, and every other warp of the CTA then ran ~10 % slower.
-// Channel c of row r lives at gdst + (c / 8) * 2048 + r * 16 + (c % 8) * 2.  Channels past the last level are zero; ONE: the
-// last channel (8 * NKC - 1) is the constant 1.0.
-template <int NKC, bool ONE>
-__device__ __noinline__ void encode4_to_global(uint8_t* gdst, int row0, const float (&v)[4][3], int L) {
-  auto put = [&](int r, int c, float x) {
-    *reinterpret_cast<__nv_bfloat16*>(gdst + (c >> 3) * kKcoreBytes + (row0 + 32 * r) * 16 + (c & 7) * 2) = __float2bfloat16_rn(x);
-  };
-  TurnsF t[4][3];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { t[r][k] = pe_turns_f(v[r][k]); put(r, k, v[r][k]); }
-  }
-#pragma unroll 1
-  for (int level = 0; level < L; ++level) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        float sn, cs;
-        pe_sincos(t[r][k], level, sn, cs);
-        put(r, 3 + 6 * level + k, sn);
-        put(r, 6 + 6 * level + k, cs);
-      }
-    }
-  }
-#pragma unroll 1
-  for (int c = 3 + 6 * L; c < NKC * 8; ++c) {
-    const float x = (ONE && c == NKC * 8 - 1) ? 1.0f : 0.0f;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) put(r, c, x);
-  }
-}
-
 // word `i` (runtime) of eight mask words held in registers, without dynamic register indexing
 __device__ __forceinline__ uint32_t pick8(const uint4& a, const uint4& b, int i) {
   uint32_t r = a.x;
@@ -217,159 +169,14 @@ __device__ __forceinline__ float softplus_f(float x) {        // torch default b
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// Sample point and view direction of one row (train.py:220-228: pts = o + d * z, with the reference's two roundings).
-__device__ __forceinline__ void fwd_tile_inputs(const MlpArgs& a, int64_t grow, bool valid, float (&p)[3], float (&dirv)[3]) {
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { p[k] = 0.f; dirv[k] = 0.f; }
-  if (valid) {
-    if (a.n_sample > 0) {
-      const int64_t ray = grow / a.n_sample;
-      const float zz = a.z[grow];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        dirv[k] = a.dir[3 * ray + k];
-        p[k] = __fadd_rn(a.pos[3 * ray + k], __fmul_rn(dirv[k], zz));
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { p[k] = a.pos[3 * grow + k]; dirv[k] = a.dir[3 * grow + k]; }
-    }
-  }
-}
-
-// d(density pre-activation) of one row from the compositing gradient and the forward output (softplus'(x) = 1 - exp(-softplus(x)))
-__device__ __forceinline__ float bwd_dsigma_pre(const MlpArgs& a, float d_sigma, float sigma) {
-  return a.density_relu ? (sigma > 0.0f ? d_sigma : 0.0f) : d_sigma * (1.0f - expf(-sigma));
-}
-
-// Backward tile inputs of one row: d(rgb2 pre-act), d(density pre-act), the head cotangents for the weight-gradient kernel and
-// dR1 = d_rgb_pre . W2 masked by r1 > 0 (16 k-cores), written to the dstash and -- TO_SMEM -- into the activation tile.
-// Returns d(density pre-act).
-template <bool TO_SMEM>
-__device__ __forceinline__ float bwd_tile_inputs(const MlpArgs& a, const float* sm, int64_t grow, bool valid, bool tile_ok, int row,
-                                                 const uint8_t* stash_tile, uint8_t* dstash_tile, uint32_t s_act) {
-  float4 d = make_float4(0.f, 0.f, 0.f, 0.f), o = make_float4(0.f, 0.5f, 0.5f, 0.5f);
-  uint4 r1m = make_uint4(0u, 0u, 0u, 0u);
-  if (valid) {
-    d = reinterpret_cast<const float4*>(a.d_sigma_rgb)[grow];
-    o = reinterpret_cast<const float4*>(a.sigma_rgb)[grow];
-  }
-  if (tile_ok) r1m = __ldg(reinterpret_cast<const uint4*>(stash_tile + a.st_mask + 10 * 4096) + row * 2);
-  const float dsp = bwd_dsigma_pre(a, d.x, o.x);
-  const float d0 = d.y * o.y * (1.0f - o.y), d1 = d.z * o.z * (1.0f - o.z), d2 = d.w * o.w * (1.0f - o.w);
-  if (tile_ok) {
-    // head cotangents for the weight-gradient kernel: a bf16 hi + lo pair per value (k-core 0: hi, k-core 1: lo; channels
-    // 0-3 of 8), so the heads' gradients ride on the tensor core with ~16 mantissa bits
-    const float c4[4] = {dsp, d0, d1, d2};
-    uint32_t hi[2], lo[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float h0 = __bfloat162float(__float2bfloat16_rn(c4[2 * j])), h1 = __bfloat162float(__float2bfloat16_rn(c4[2 * j + 1]));
-      hi[j] = tc::pack_bf16x2(h0, h1);
-      lo[j] = tc::pack_bf16x2(c4[2 * j] - h0, c4[2 * j + 1] - h1);
-    }
-    uint4* cot = reinterpret_cast<uint4*>(dstash_tile + a.ds_cot);
-    cot[row] = make_uint4(hi[0], hi[1], 0u, 0u);
-    cot[128 + row] = make_uint4(lo[0], lo[1], 0u, 0u);
-#if NERF_WGRAD_PAIR == 0
-    reinterpret_cast<float4*>(dstash_tile + a.ds_sr)[row] = make_float4(dsp, d0, d1, d2);      // single-CTA wgrad + CUDA-core head kernel
-#endif
-  }
-  const float* w2 = sm + a.sm_w2;
-  const uint32_t r1w[4] = {r1m.x, r1m.y, r1m.z, r1m.w};
-#pragma unroll
-  for (int kc = 0; kc < 16; ++kc) {
-    float g[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = kc * 8 + j;
-      const float v = d0 * w2[c] + d1 * w2[128 + c] + d2 * w2[256 + c];
-      g[j] = ((r1w[kc >> 2] >> (((((kc & 3) * 8 + j)) >> 1) + 16 * (j & 1))) & 1u) ? v : 0.0f;
-    }
-    const uint4 pk = make_uint4(tc::pack_bf16x2(g[0], g[1]), tc::pack_bf16x2(g[2], g[3]),
-                                tc::pack_bf16x2(g[4], g[5]), tc::pack_bf16x2(g[6], g[7]));
-    tc::st_shared_v4(s_act + kc * kKcoreBytes + row * 16, pk.x, pk.y, pk.z, pk.w);
-    if (tile_ok) __stcs(reinterpret_cast<uint4*>(dstash_tile + a.ds_y10 + kc * kKcoreBytes) + row, pk);
-  }
-  return dsp;
-}
-
-// The same for FOUR rows of a tile at once (rows lane + 32 i: one lane of the prologue warp), to the dstash only, as compact
-// code: a rolled loop over the 16 k-cores of dR1 with rgb_layer2's weights loaded once per channel for the four rows (see
-// encode4_to_global for why).
-__device__ __noinline__ void bwd_tile_inputs4(const MlpArgs& a, const float* sm, int tile, int lane, const uint8_t* stash_tile, uint8_t* dstash_tile) {
-  float d0[4], d1[4], d2[4];
-  uint4 r1m[4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int row = lane + 32 * r;
-    const int64_t grow = (int64_t)tile * 128 + row;
-    float4 d = make_float4(0.f, 0.f, 0.f, 0.f), o = make_float4(0.f, 0.5f, 0.5f, 0.5f);
-    if (grow < a.n_rows) {
-      d = reinterpret_cast<const float4*>(a.d_sigma_rgb)[grow];
-      o = reinterpret_cast<const float4*>(a.sigma_rgb)[grow];
-    }
-    r1m[r] = __ldg(reinterpret_cast<const uint4*>(stash_tile + a.st_mask + 10 * 4096) + row * 2);
-    const float dsp = bwd_dsigma_pre(a, d.x, o.x);
-    d0[r] = d.y * o.y * (1.0f - o.y); d1[r] = d.z * o.z * (1.0f - o.z); d2[r] = d.w * o.w * (1.0f - o.w);
-    // head cotangents: a bf16 hi + lo pair per value (k-core 0: hi, k-core 1: lo; channels 0-3 of 8), as bwd_tile_inputs writes them
-    const float c4[4] = {dsp, d0[r], d1[r], d2[r]};
-    uint32_t hi[2], lo[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float h0 = __bfloat162float(__float2bfloat16_rn(c4[2 * j])), h1 = __bfloat162float(__float2bfloat16_rn(c4[2 * j + 1]));
-      hi[j] = tc::pack_bf16x2(h0, h1);
-      lo[j] = tc::pack_bf16x2(c4[2 * j] - h0, c4[2 * j + 1] - h1);
-    }
-    uint4* cot = reinterpret_cast<uint4*>(dstash_tile + a.ds_cot);
-    cot[row] = make_uint4(hi[0], hi[1], 0u, 0u);
-    cot[128 + row] = make_uint4(lo[0], lo[1], 0u, 0u);
-  }
-  const float* w2 = sm + a.sm_w2;
-#pragma unroll 1
-  for (int kc = 0; kc < 16; ++kc) {
-    uint32_t pk[4][4];
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {                   // two channels (one packed word) at a time
-      const int c = kc * 8 + 2 * jj;
-      const float wa0 = w2[c], wa1 = w2[128 + c], wa2 = w2[256 + c], wb0 = w2[c + 1], wb1 = w2[129 + c], wb2 = w2[257 + c];
-      const int bit = ((kc & 3) * 8 + 2 * jj) >> 1;    // mask bit of the even channel; the odd one sits 16 bits higher
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const uint32_t w = kc < 4 ? r1m[r].x : (kc < 8 ? r1m[r].y : (kc < 12 ? r1m[r].z : r1m[r].w));
-        const float ga = d0[r] * wa0 + d1[r] * wa1 + d2[r] * wa2, gb = d0[r] * wb0 + d1[r] * wb1 + d2[r] * wb2;
-        pk[r][jj] = tc::pack_bf16x2(((w >> bit) & 1u) ? ga : 0.0f, ((w >> (bit + 16)) & 1u) ? gb : 0.0f);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)                        // default caching: the bulk copy reads it back from L2
-      reinterpret_cast<uint4*>(dstash_tile + a.ds_y10 + kc * kKcoreBytes)[lane + 32 * r] = make_uint4(pk[r][0], pk[r][1], pk[r][2], pk[r][3]);
-  }
-}
-
 template <int MODE, bool TRAIN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((mlp_threads<MODE, TRAIN>()), 1) mlp_fused_kernel(const __grid_constant__ MlpArgs a) {
-  constexpr bool PWG = mlp_has_prologue_wg<MODE, TRAIN>();
-#ifdef NERF_PWG_Y
-  constexpr bool CONSUME = false;                      // experiment: the prologue warp runs, the epilogue warps ignore it
-#else
-  constexpr bool CONSUME = PWG;
-#endif
-#ifdef NERF_ONE_RELAY
-  constexpr bool ONE_RELAY = true;                     // experiment: the single-warp slab relay without the prologue warp
-#else
-  constexpr bool ONE_RELAY = PWG;
-#endif
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const __grid_constant__ MlpArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = tc::smem_u32(smem);
   const uint32_t s_ring = s_base + MlpSmem::kRing;
   const uint32_t s_bar = s_base + MlpSmem::kBars;
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 128, bar_acc = s_bar + 256, bar_act = s_bar + 272;
   const uint32_t bar_drain = s_bar + 288;
-  // prologue warp handshake (PWG kernels), per tile slot: dead = the epilogue warpgroup is done with the bytes the NEXT tile's inputs
-  // replace (128 arrivals), dedead = likewise for the direction encoding (forward), tile / de = the prologue warp's bulk copies of
-  // those inputs into the encoding / activation tile have landed (1 arrival + tx bytes)
-  const uint32_t bar_dead = s_bar + 192, bar_dedead = s_bar + 208, bar_tile = s_bar + 224, bar_de = s_bar + 240;
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + MlpSmem::kTmemPtr);
   const uint32_t rank = tc::cluster_ctarank();         // 0 = leader (issues the pair MMAs), 1 = peer
   // head weights live in shared memory: with 224 KB of it carved out there is no L1 left to cache them
@@ -385,7 +192,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((mlp_threads<MODE, T
     // act_ready lives in the leader: 128 epilogue threads of each CTA arrive on it
     for (int i = 0; i < 2; ++i) { tc::mbar_init(bar_acc + 8 * i, 1); tc::mbar_init(bar_act + 8 * i, 256); }
     tc::mbar_init(bar_drain, 1);                       // the MMA warp: "all my MMAs have completed" (multicast to both CTAs)
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(bar_dead + 8 * i, 128); tc::mbar_init(bar_dedead + 8 * i, 128); tc::mbar_init(bar_tile + 8 * i, 1); tc::mbar_init(bar_de + 8 * i, 1); }
     tc::fence_mbar_init();
   }
   if (warp == 8) tc::tmem_alloc_pair(tc::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
@@ -449,12 +255,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((mlp_threads<MODE, T
       tc::mbar_wait(bar_drain, 0);
     }
     __syncwarp();
-  } else if ((warp == 9 || (warp == 11 && !ONE_RELAY)) && rank != 0) {
+  } else if ((warp == 9 || warp == 11) && rank != 0) {
     // ===================== peer: relay "my half of slab pair j has landed" to the leader's full barrier ================
-    // Two relay warps taking alternate pairs (like the loaders), or -- when warp 11 prepares the next tiles -- one warp whose
-    // lanes 0 and 1 take alternate pairs.
+    // (alternate trips per warp, like the loaders)
     const int which = (warp - 9) >> 1;
-    const bool active = ONE_RELAY ? lane < 2 : lane == 0;
     const uint32_t leader_full = tc::mapa(bar_full, 0);
     uint32_t pj0 = 0, trip = 0;
     int si = 0;
@@ -463,28 +267,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((mlp_threads<MODE, T
       si = (si + 1 == P.n_steps) ? 0 : si + 1;
       const int n_pairs = (st.act_ksteps + st.enc_ksteps + st.bias_kstep + 1) >> 1;
       for (int slot = 0; slot < 2; ++slot) {
-        if (ONE_RELAY) {
-          for (int j = 0; j < n_pairs; j += 2) {
-            const int jj = j + lane;
-            if (active && jj < n_pairs) {
-              const uint32_t it = pj0 + (uint32_t)jj;
-              const uint32_t rs = it % kRingSlots;
-              tc::mbar_wait(bar_full + 8 * rs, (it / kRingSlots) & 1u);
-              tc::mbar_arrive_cluster(leader_full + 8 * rs);
-            }
-            __syncwarp();
+        for (int j = 0; j < n_pairs; ++j, ++trip) {
+          if ((int)(trip & 1u) != which) continue;
+          if (lane == 0) {
+            const uint32_t it = pj0 + (uint32_t)j;
+            const uint32_t rs = it % kRingSlots;
+            tc::mbar_wait(bar_full + 8 * rs, (it / kRingSlots) & 1u);
+            tc::mbar_arrive_cluster(leader_full + 8 * rs);
           }
-        } else {
-          for (int j = 0; j < n_pairs; ++j, ++trip) {
-            if ((int)(trip & 1u) != which) continue;
-            if (active) {
-              const uint32_t it = pj0 + (uint32_t)j;
-              const uint32_t rs = it % kRingSlots;
-              tc::mbar_wait(bar_full + 8 * rs, (it / kRingSlots) & 1u);
-              tc::mbar_arrive_cluster(leader_full + 8 * rs);
-            }
-            __syncwarp();
-          }
+          __syncwarp();
         }
         pj0 += (uint32_t)n_pairs;
       }
@@ -610,8 +401,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((mlp_threads<MODE, T
     const uint32_t leader_act = tc::mapa(bar_act + 8 * slot, 0);   // "A tile of this slot is ready" lives in the leader
     constexpr bool train = TRAIN || (MODE == MODE_BWD);   // the stash exists: written by the training forward, read (masks) by dgrad
     uint32_t acc_phase = 0;
-    int li = 0;                                        // index of the quad among this cluster's quads (phase of the handshake barriers)
-    for (int quad = cluster_id; quad < n_quads; quad += n_clusters, ++li) {
+    for (int quad = cluster_id; quad < n_quads; quad += n_clusters) {
       const int tile = 4 * quad + 2 * slot + (int)rank;
       const bool tile_ok = tile < a.n_tiles;           // tile count not a multiple of 4: the last quad has phantom tiles
       const int64_t grow = (int64_t)tile * 128 + row;
@@ -621,23 +411,79 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((mlp_threads<MODE, T
       const bool store_out = tile_ok && ((MODE == MODE_BWD) || train);
       float dirv[3] = {0.f, 0.f, 0.f};
       float sigma_keep = 0.0f, dsp = 0.0f;
-      bool de_pending = false;                         // PWG forward: the direction encoding was requested and not yet waited for
-      (void)sigma_keep; (void)dsp; (void)dirv; (void)de_pending;
+      (void)sigma_keep; (void)dsp;
 
       // ---------------- prologue ----------------
-      if constexpr (CONSUME) {
-        // the tile's inputs arrive by bulk copy (issued by the prologue warp when this slot's previous tile was done with the
-        // bytes they replace); only the row's d(density pre-act) is needed here again (the density-head term of dgrad's second step)
-        if (MODE == MODE_BWD && valid) dsp = bwd_dsigma_pre(a, a.d_sigma_rgb[4 * grow], a.sigma_rgb[4 * grow]);
-        tc::mbar_wait(bar_tile + 8 * slot, (uint32_t)li & 1u);
-      } else if (MODE == MODE_FWD) {
-        float p[3];
-        fwd_tile_inputs(a, grow, valid, p, dirv);
+      if (MODE == MODE_FWD) {
+        float p[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          if (a.n_sample > 0) {                        // train.py:220-228: pts = o + d * z
+            const int64_t ray = grow / a.n_sample;
+            const float zz = a.z[grow];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              dirv[k] = a.dir[3 * ray + k];
+              p[k] = __fadd_rn(a.pos[3 * ray + k], __fmul_rn(dirv[k], zz));
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { p[k] = a.pos[3 * grow + k]; dirv[k] = a.dir[3 * grow + k]; }
+          }
+        }
         uint8_t* g_pe = store_out ? stash_tile + a.st_pe : nullptr;
         if (a.pos_L > 0) write_encoding<10, 8, true>(s_enc, row, p, g_pe, a.pos_L);
         else write_encoding<0, 8, true>(s_enc, row, p, g_pe, 0);
       } else {
-        dsp = bwd_tile_inputs<true>(a, sm, grow, valid, tile_ok, row, stash_tile, dstash_tile, s_act);
+        // backward prologue: d(rgb2 pre-act), d(density pre-act), dR1 = d_rgb_pre . W2 masked by r1 > 0
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f), o = make_float4(0.f, 0.5f, 0.5f, 0.5f);
+        uint4 r1m = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
+          d = reinterpret_cast<const float4*>(a.d_sigma_rgb)[grow];
+          o = reinterpret_cast<const float4*>(a.sigma_rgb)[grow];
+        }
+        if (tile_ok) r1m = __ldg(reinterpret_cast<const uint4*>(stash_tile + a.st_mask + 10 * 4096) + row * 2);
+        dsp = a.density_relu ? (o.x > 0.0f ? d.x : 0.0f)                 // relu'
+                             : d.x * (1.0f - expf(-o.x));              // softplus'(x) = 1 - exp(-softplus(x))
+        const float d0 = d.y * o.y * (1.0f - o.y), d1 = d.z * o.z * (1.0f - o.z), d2 = d.w * o.w * (1.0f - o.w);
+        if (tile_ok) {
+          // head cotangents for the weight-gradient kernel: a bf16 hi + lo pair per value (k-core 0: hi, k-core 1: lo; channels
+          // 0-3 of 8), so the heads' gradients ride on the tensor core with ~16 mantissa bits
+          const float c4[4] = {dsp, d0, d1, d2};
+          uint32_t hi[2], lo[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float h0 = __bfloat162float(__float2bfloat16_rn(c4[2 * j])), h1 = __bfloat162float(__float2bfloat16_rn(c4[2 * j + 1]));
+            hi[j] = tc::pack_bf16x2(h0, h1);
+            lo[j] = tc::pack_bf16x2(c4[2 * j] - h0, c4[2 * j + 1] - h1);
+          }
+          uint4* cot = reinterpret_cast<uint4*>(dstash_tile + a.ds_cot);
+          cot[row] = make_uint4(hi[0], hi[1], 0u, 0u);
+          cot[128 + row] = make_uint4(lo[0], lo[1], 0u, 0u);
+#if NERF_WGRAD_PAIR == 0
+          reinterpret_cast<float4*>(dstash_tile + a.ds_sr)[row] = make_float4(dsp, d0, d1, d2);      // single-CTA wgrad + CUDA-core head kernel
+#endif
+        }
+        const float4* w2 = reinterpret_cast<const float4*>(sm + a.sm_w2);     // rgb_layer2.weight [3][128]: 16-byte loads (96 instead of 384)
+        const uint32_t r1w[4] = {r1m.x, r1m.y, r1m.z, r1m.w};
+#pragma unroll
+        for (int kc = 0; kc < 16; ++kc) {
+          float g[8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 wa = w2[2 * kc + h], wb = w2[32 + 2 * kc + h], wc = w2[64 + 2 * kc + h];
+            const float wa4[4] = {wa.x, wa.y, wa.z, wa.w}, wb4[4] = {wb.x, wb.y, wb.z, wb.w}, wc4[4] = {wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int j = 4 * h + q;
+              const float v = d0 * wa4[q] + d1 * wb4[q] + d2 * wc4[q];
+              g[j] = ((r1w[kc >> 2] >> (((((kc & 3) * 8 + j)) >> 1) + 16 * (j & 1))) & 1u) ? v : 0.0f;
+            }
+          }
+          const uint4 pk = make_uint4(tc::pack_bf16x2(g[0], g[1]), tc::pack_bf16x2(g[2], g[3]),
+                                      tc::pack_bf16x2(g[4], g[5]), tc::pack_bf16x2(g[6], g[7]));
+          tc::st_shared_v4(s_act + kc * kKcoreBytes + row * 16, pk.x, pk.y, pk.z, pk.w);
+          if (store_out) __stcs(reinterpret_cast<uint4*>(dstash_tile + a.ds_y10 + kc * kKcoreBytes) + row, pk);
+        }
       }
       tc::fence_proxy_async_smem();
       if (rank == 0) tc::mbar_arrive(bar_act + 8 * slot); else tc::mbar_arrive_cluster(leader_act);
@@ -652,12 +498,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((mlp_threads<MODE, T
         }
         tc::mbar_wait(my_acc, acc_phase & 1u); ++acc_phase;
         tc::tc_fence_after();
-        if constexpr (PWG && MODE == MODE_FWD) {
-          // this step's MMAs have completed, so the encoding-tile bytes they read are dead: tell the prologue warp, which then copies
-          // the direction encoding (after the skip layer) / the next tile's position encoding (after the last layer) over them
-          if (st.flags & EPI_WRITE_DIR) { tc::mbar_arrive(bar_dedead + 8 * slot); de_pending = true; }
-          if (st.flags & EPI_LAST) tc::mbar_arrive(bar_dead + 8 * slot);
-        }
 #ifdef NERF_DIAGNOSTICS
         long long* tr = (a.trace != nullptr && blockIdx.x == 0 && row == 0)
                             ? a.trace + ((size_t)((quad / n_clusters) * kMaxSteps + si) * 2 + slot) * 4 : nullptr;
@@ -729,12 +569,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((mlp_threads<MODE, T
         }
         tc::tc_fence_before();                         // TMEM reads retired before the next MMA overwrites
         tc::fence_proxy_async_smem();                  // ACT writes visible to UMMA
-        if constexpr (PWG && MODE == MODE_FWD) {       // the next step reads the direction encoding (rgb_layer1): it has landed
-          if (CONSUME && de_pending && P.s[si + 1].enc_ksteps > 0) { tc::mbar_wait(bar_de + 8 * slot, (uint32_t)li & 1u); de_pending = false; }
-        }
-        if constexpr (PWG && MODE == MODE_BWD) {       // dgrad: the tile is dead once the last step's read-out has written it for nothing
-          if (st.flags & EPI_LAST) tc::mbar_arrive(bar_dead + 8 * slot);
-        }
         if (!(st.flags & EPI_LAST)) {                  // the next layer's MMAs may start NOW
           if (rank == 0) tc::mbar_arrive(bar_act + 8 * slot); else tc::mbar_arrive_cluster(leader_act);
         }
@@ -744,7 +578,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((mlp_threads<MODE, T
 
         // ---- everything below is off the MMA -> epilogue -> MMA critical path ----
         if (MODE == MODE_FWD) {
-          if (!CONSUME && (st.flags & EPI_WRITE_DIR)) {    // ENC k-cores 0-3 <- direction encoding (used by rgb_layer1)
+          if (st.flags & EPI_WRITE_DIR) {              // ENC k-cores 0-3 <- direction encoding (used by rgb_layer1)
             uint8_t* g_de = store_out ? stash_tile + a.st_de : nullptr;
             // 27 channels (4 levels, the reference default) or fewer: k-cores 0-3, the constant-1 channel 63 of the position tile
             // stays; more levels: the whole 64-channel tile with its own constant 1
@@ -832,75 +666,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((mlp_threads<MODE, T
           uint4* mp = reinterpret_cast<uint4*>(stash_tile + st.mask_off) + row * 2;
           __stcs(mp, make_uint4(mw[0], mw[1], mw[2], mw[3]));
           __stcs(mp + 1, make_uint4(mw[4], mw[5], mw[6], mw[7]));
-        }
-      }
-    }
-  }
-  else if (PWG && warp == 11) {
-    // ===================== prologue warp (4 rows per lane and tile) =====================
-    // It PRODUCES the inputs of the cluster's next quad into HBM (stash: position / direction encodings; dstash: head cotangents, dR1)
-    // while the epilogue warpgroups work on the current quad, and it MOVES them into the tiles: one bulk copy per tile slot the
-    // moment the slot's epilogue warpgroup reports the bytes dead.  (The first form had a thread of each epilogue warpgroup issue
-    // the copies: the extra live state in a read-out loop that already wants 220 registers cost 800 cycles per layer.)
-    auto produce = [&](int quad) {
-      for (int slot = 0; slot < 2; ++slot) {
-        const int tile = 4 * quad + 2 * slot + (int)rank;
-        if (tile >= a.n_tiles) continue;
-        if (MODE == MODE_FWD) {
-          float p[4][3], dirv[4][3];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int64_t grow = (int64_t)tile * 128 + lane + 32 * r;
-            fwd_tile_inputs(a, grow, grow < a.n_rows, p[r], dirv[r]);
-          }
-          uint8_t* stash_tile = a.stash + (size_t)tile * a.stash_tile_bytes;
-          encode4_to_global<8, true>(stash_tile + a.st_pe, lane, p, a.pos_L);
-          // 27 channels (4 levels, the reference default) or fewer: k-cores 0-3, the constant-1 channel 63 of the position tile
-          // stays; more levels: the whole 64-channel tile with its own constant 1
-          if (a.dir_L > 4) encode4_to_global<8, true>(stash_tile + a.st_de, lane, dirv, a.dir_L);
-          else encode4_to_global<4, false>(stash_tile + a.st_de, lane, dirv, a.dir_L);
-        } else {
-          bwd_tile_inputs4(a, sm, tile, lane, a.stash + (size_t)tile * a.stash_tile_bytes, a.dstash + (size_t)tile * a.dstash_tile_bytes);
-        }
-      }
-      tc::fence_proxy_async_all();                     // every lane: its generic-proxy global writes before the bulk (async-proxy) reads
-      __syncwarp();
-    };
-    if (cluster_id < n_quads) produce(cluster_id);
-    int li = 0;
-    for (int quad = cluster_id; quad < n_quads; quad += n_clusters, ++li) {
-      for (int slot = 0; slot < 2; ++slot) {           // this quad's tiles -> encoding tile (forward: position encoding) / activation tile (dgrad: dR1)
-        if (lane == 0) {
-          const int tile = 4 * quad + 2 * slot + (int)rank;
-          if (li > 0) tc::mbar_wait_backoff(bar_dead + 8 * slot, (uint32_t)(li - 1) & 1u);
-          if (tile < a.n_tiles) {
-            const uint32_t bytes = (MODE == MODE_FWD) ? (uint32_t)kEncBytes : 16u * kKcoreBytes;
-            const uint8_t* src = (MODE == MODE_FWD) ? a.stash + (size_t)tile * a.stash_tile_bytes + a.st_pe
-                                                    : a.dstash + (size_t)tile * a.dstash_tile_bytes + a.ds_y10;
-            const uint32_t dst = s_base + ((MODE == MODE_FWD) ? MlpSmem::kEnc + slot * kEncBytes : MlpSmem::kAct + slot * kActBytes);
-            tc::bulk_g2s(dst, src, bytes, bar_tile + 8 * slot);
-            tc::mbar_arrive_expect_tx(bar_tile + 8 * slot, bytes);
-          } else {
-            tc::mbar_arrive(bar_tile + 8 * slot);      // phantom tile: nothing to load, the phase still completes
-          }
-        }
-        __syncwarp();
-      }
-      if (quad + n_clusters < n_quads) produce(quad + n_clusters);
-      if (MODE == MODE_FWD) {
-        for (int slot = 0; slot < 2; ++slot) {         // direction encoding -> ENC k-cores 0.. once the skip layer's MMAs are done with them
-          if (lane == 0) {
-            const int tile = 4 * quad + 2 * slot + (int)rank;
-            tc::mbar_wait_backoff(bar_dedead + 8 * slot, (uint32_t)li & 1u);
-            if (tile < a.n_tiles) {
-              const uint32_t de_bytes = (a.dir_L > 4 ? 8u : 4u) * kKcoreBytes;
-              tc::bulk_g2s(s_base + MlpSmem::kEnc + slot * kEncBytes, a.stash + (size_t)tile * a.stash_tile_bytes + a.st_de, de_bytes, bar_de + 8 * slot);
-              tc::mbar_arrive_expect_tx(bar_de + 8 * slot, de_bytes);
-            } else {
-              tc::mbar_arrive(bar_de + 8 * slot);
-            }
-          }
-          __syncwarp();
         }
       }
     }

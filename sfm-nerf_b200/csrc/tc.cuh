@@ -47,20 +47,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// Long wait by ONE thread: non-blocking probes with a sleep in between (no shared-memory polling pressure), bounded like mbar_wait.
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity);
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_test_wait(bar, parity)) {
-    __nanosleep(64);
-    if ((++spins & 0x3ffu) == 0 && (clock64() - t0) > 4000000000LL) {
-      printf("nerf_b200: mbarrier (back-off) timeout block %d thread %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-
 // ---------------------------------------------------------------- CTA pair (cluster of 2) --
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -159,18 +145,6 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-
-// generic-proxy writes to GLOBAL memory -> visible to a later bulk (async-proxy) read of the same bytes: executed by the writing
-// threads before they signal the thread that issues the copy
-__device__ __forceinline__ void fence_proxy_async_all() {
-  asm volatile("fence.proxy.async;" ::: "memory");
-}
-// Warpgroup register re-allocation (all four warps of a 128-thread warpgroup execute it): the launch gives every thread
-// 65536 / threads registers; warpgroups that need few hand theirs back, the ones that need many take them.
-template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // true in exactly one (converged) lane of the warp
 __device__ __forceinline__ bool elect_one() {
