@@ -474,6 +474,10 @@ __global__ void adam_reduce_kernel(float* __restrict__ p, PeerGrads peers, int n
                                    float* __restrict__ v, int64_t n4, AdamCoef c, float grad_scale, AdamSchedule sched,
                                    PeerFlags flags, int rank, const unsigned long long* __restrict__ epoch_ptr) {
   adam_device_schedule(sched, c);
+  // this rank's own operands do not depend on the other ranks: they are on their way while the kernel waits at the barrier
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), mi = pi, vi = pi;
+  if (i < n4) { pi = reinterpret_cast<float4*>(p)[i]; mi = reinterpret_cast<float4*>(m)[i]; vi = reinterpret_cast<float4*>(v)[i]; }
   if (epoch_ptr != nullptr) {                            // block-uniform
     const unsigned int epoch = (unsigned int)(*epoch_ptr) + 1u;
     if (blockIdx.x == 0 && (int)threadIdx.x < n_ranks) {
@@ -495,7 +499,6 @@ __global__ void adam_reduce_kernel(float* __restrict__ p, PeerGrads peers, int n
     }
     __syncthreads();
   }
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 g;
   if (mc_grads != nullptr) {
@@ -508,7 +511,6 @@ __global__ void adam_reduce_kernel(float* __restrict__ p, PeerGrads peers, int n
       g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
     }
   }
-  float4 pi = reinterpret_cast<float4*>(p)[i], mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
   const float gg[4] = {g.x * grad_scale, g.y * grad_scale, g.z * grad_scale, g.w * grad_scale};
   float* pp = &pi.x; float* mm = &mi.x; float* vv = &vi.x;
 #pragma unroll

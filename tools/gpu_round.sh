@@ -26,7 +26,7 @@ if [ "$a" = "full" ]; then
   # one full-section capture of each hot kernel (inference fwd, training fwd, dgrad, wgrad, head-grad) at the C2 shape
   python tools/profile_kernels.py > gpurun_out/profile_plain.log 2>&1 && \
   ncu --set full --import-source on --clock-control none --kernel-name 'regex:mlp_fused|wgrad' \
-      --launch-skip 10 -c 5 -f -o gpurun_out/prof_r2 python tools/profile_kernels.py > gpurun_out/ncu_full.log 2>&1
+      --launch-skip 8 -c 4 -f -o gpurun_out/prof_r2 python tools/profile_kernels.py > gpurun_out/ncu_full.log 2>&1
   tail -2 gpurun_out/ncu_full.log
 fi
 done
