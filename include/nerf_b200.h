@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NERF_ABI_VERSION 2
+#define NERF_ABI_VERSION 3
 
 enum {
   NERF_OK = 0,
