@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NERF_ABI_VERSION 3
+#define NERF_ABI_VERSION 4
 
 enum {
   NERF_OK = 0,
@@ -143,6 +143,13 @@ int nerf_mlp_forward(const void* packed, int layout, const float* pos, const flo
 int nerf_mlp_forward_rays(const void* packed, int layout, const float* rays_o,
                           const float* rays_d, const float* z, int64_t n_rays, int n_sample,
                           float* sigma_rgb, void* stash, void* stream);
+/* Fused render of rays with 64 samples (NeRFModel.py:158-202 + train.py:248-269 in ONE kernel): the volume
+ * compositing runs in the MLP kernel's epilogue -- a 128-row tile is exactly two rays -- so the per-sample (density, rgb) never
+ * leave the SM; rgb [n_rays,3], depth / acc [n_rays] or NULL.  Bit-identical to nerf_mlp_forward_rays + nerf_composite_forward.
+ * n_sample != 64: NERF_ERR_ARG (use the two calls; nerf_render_image chooses by itself). */
+int nerf_mlp_render_rays(const void* packed, int layout, const float* rays_o, const float* rays_d,
+                         const float* z, int64_t n_rays, int n_sample, float* rgb, float* depth,
+                         float* acc, void* stream);
 /* backward: d_sigma_rgb [n,4] = dL/d(density, rgb) -> grads (flat fp32 parameter layout).
  * accumulate == 0 overwrites grads, != 0 adds to them.  dstash is scratch. */
 int nerf_mlp_backward(const void* packed, int layout, const void* stash, const float* sigma_rgb,

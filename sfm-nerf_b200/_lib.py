@@ -94,6 +94,7 @@ PROTOTYPES = {
     "nerf_mlp_dstash_bytes": (_L, [_I, _L]),
     "nerf_mlp_forward": (_I, [_P, _I, _P, _P, _L, _P, _P, _P]),
     "nerf_mlp_forward_rays": (_I, [_P, _I, _P, _P, _P, _L, _I, _P, _P, _P]),
+    "nerf_mlp_render_rays": (_I, [_P, _I, _P, _P, _P, _L, _I, _P, _P, _P, _P]),
     "nerf_mlp_backward": (_I, [_P, _I, _P, _P, _P, _L, _P, _P, _I, _P]),
     "nerf_mlp_dgrad": (_I, [_P, _I, _P, _P, _P, _L, _P, _P]),
     "nerf_mlp_wgrad": (_I, [_I, _P, _P, _L, _P, _I, _P]),

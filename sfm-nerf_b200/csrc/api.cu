@@ -130,7 +130,8 @@ void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t
 }
 
 int launch_forward(const void* packed, int layout, const float* pos, const float* dir, const float* z,
-                   int64_t n_rows, int n_sample, float* sigma_rgb, void* stash, void* stream) {
+                   int64_t n_rows, int n_sample, float* sigma_rgb, void* stash, void* stream,
+                   float* comp_rgb = nullptr, float* comp_depth = nullptr, float* comp_acc = nullptr) {
   DeviceInfo* dev;
   int rc = device_info(&dev);
   if (rc != NERF_OK) return rc;
@@ -138,12 +139,13 @@ int launch_forward(const void* packed, int layout, const float* pos, const float
   if (!m) return NERF_ERR_LAYOUT;
   if (!packed || n_rows < 0 || n_rows > (int64_t)128 * 0x7fffff00) return NERF_ERR_ARG;
   if (n_rows == 0) return NERF_OK;                      /* empty batch: nothing to read or write */
-  if (!pos || !dir || !sigma_rgb) return NERF_ERR_ARG;
-  if (!nerf_aligned(packed, 16) || !nerf_aligned(sigma_rgb, 16) || (stash && !nerf_aligned(stash, 16))) return NERF_ERR_ALIGN;
+  if (!pos || !dir || (!sigma_rgb && !comp_rgb)) return NERF_ERR_ARG;
+  if (!nerf_aligned(packed, 16) || (sigma_rgb && !nerf_aligned(sigma_rgb, 16)) || (stash && !nerf_aligned(stash, 16))) return NERF_ERR_ALIGN;
   MlpArgs a;
   fill_mlp_args(a, *m, packed, n_rows);
   a.pos = pos; a.dir = dir; a.z = z; a.n_sample = n_sample;
   a.sigma_rgb = sigma_rgb;
+  a.comp_rgb = comp_rgb; a.comp_depth = comp_depth; a.comp_acc = comp_acc;
   a.stash = static_cast<uint8_t*>(stash);
   a.prog = m->fwd;
   const int grid = mlp_grid(*dev, a.n_tiles);
@@ -364,6 +366,13 @@ int nerf_mlp_forward_rays(const void* packed, int layout, const float* rays_o, c
   return launch_forward(packed, layout, rays_o, rays_d, z, n_rays * n_sample, n_sample, sigma_rgb, stash, stream);
 }
 
+int nerf_mlp_render_rays(const void* packed, int layout, const float* rays_o, const float* rays_d, const float* z, int64_t n_rays,
+                         int n_sample, float* rgb, float* depth, float* acc, void* stream) {
+  if (!z || !rgb || n_rays < 0) return NERF_ERR_ARG;
+  if (n_sample != 64) return NERF_ERR_ARG;            /* a 128-row tile must be exactly two rays */
+  return launch_forward(packed, layout, rays_o, rays_d, z, n_rays * n_sample, n_sample, nullptr, nullptr, stream, rgb, depth, acc);
+}
+
 int nerf_mlp_dgrad(const void* packed, int layout, const void* stash, const float* sigma_rgb,
                    const float* d_sigma_rgb, int64_t n_rows, void* dstash, void* stream) {
   DeviceInfo* dev;
@@ -533,6 +542,8 @@ int nerf_render_image(const void* packed, int layout, const double* poses, int p
   int rc;
   if ((rc = nerf_raygen_image(poses, pose_index, fx, fy, cx, cy, width, height, ray_begin, ray_count, o, d, stream))) return rc;
   if ((rc = nerf_sample_z(ray_count, n_sample, near, far, perturb, nullptr, seed, offset, z, stream))) return rc;
+  // 64 samples per ray: the compositing runs in the MLP kernel's epilogue (sigma_rgb never leaves the SM); else two kernels
+  if (n_sample == 64 && rgb) return nerf_mlp_render_rays(packed, layout, o, d, z, ray_count, n_sample, rgb, depth, acc, stream);
   if ((rc = nerf_mlp_forward_rays(packed, layout, o, d, z, ray_count, n_sample, sr, nullptr, stream))) return rc;
   return nerf_composite_forward(sr, z, ray_count, n_sample, rgb, depth, acc, stream);
 }

@@ -28,6 +28,7 @@
 // image carries the bias in that K column, so the epilogue does no bias loads or adds.
 #pragma once
 #include "common.cuh"
+#include "composite.cuh"
 #include "mlp_layout.cuh"
 #include "tc.cuh"
 
@@ -75,6 +76,8 @@ struct MlpArgs {
   int32_t stash_tile_bytes, dstash_tile_bytes;
   int32_t st_pe, st_de, st_r1, st_mask, ds_y10, ds_sr, ds_cot;
   long long* trace;          // diagnostics: per-(pair,step,slot) clock64 stamps of CTA 0 (or null)
+  // fused render (inference, n_sample == 64): per-RAY outputs composited in the epilogue (train.py:248-269); sigma_rgb is then not written
+  float* comp_rgb; float* comp_depth; float* comp_acc;
   Program prog;
 };
 
@@ -625,11 +628,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
                 c0 = fmaf(y[4 * h + 3], wa.w, c0); c1 = fmaf(y[4 * h + 3], wb.w, c1); c2 = fmaf(y[4 * h + 3], wc.w, c2);
               }
             }
-            if (valid) {
-              const float* b2 = sm + a.sm_b2;
-              reinterpret_cast<float4*>(a.sigma_rgb)[grow] =
-                  make_float4(sigma_keep, sigmoid_f(c0 + b2[0]), sigmoid_f(c1 + b2[1]), sigmoid_f(c2 + b2[2]));
+            const float* b2 = sm + a.sm_b2;
+            const float cr = sigmoid_f(c0 + b2[0]), cg = sigmoid_f(c1 + b2[1]), cb = sigmoid_f(c2 + b2[2]);
+            bool composited = false;
+            if constexpr (!TRAIN) {
+              if (a.comp_rgb != nullptr) {                     // uniform: fused render, 64 samples per ray
+                // A 128-row tile is two rays: warps 0, 1 of the warpgroup hold samples 0-31 / 32-63 of the first, warps 2, 3 of the
+                // second.  The arithmetic is composite_forward_exact_kernel<2>'s, operation for operation (lane l of that kernel's warp
+                // handles samples l and l + 32), so the result has the same bits: the second warp of a ray needs the first one's
+                // transmittance product, the first one then folds the second one's (weight, colour, depth) into its own sums.
+                composited = true;
+                const int wq = warp & 3, chunk = wq & 1;
+                const int64_t ray = (int64_t)tile * 2 + (wq >> 1);
+                float* sc = reinterpret_cast<float*>(smem + MlpSmem::kAct + slot * kActBytes + 16 * kKcoreBytes) + (wq >> 1) * 168;   // free k-cores of the tile
+                const float zz = valid ? a.z[grow] : 0.0f;
+                const float zn = (valid && !(chunk == 1 && lane == 31)) ? a.z[grow + 1] : zz;
+                float delta = __fsub_rn(zn, zz);
+                if (chunk == 1 && lane == 31) delta = 1e-3f;    // train.py:250
+                const float alpha = __fsub_rn(1.0f, expf(-__fmul_rn(sigma_keep, delta)));
+                const float om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);   // train.py:262
+                const float incl = warp_incl_prod(om, lane);
+                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 1.0f;
+                if (chunk == 0 && lane == 31) sc[160] = incl;
+                tc::named_bar_sync(1 + slot, 128);
+                const float carry = chunk == 0 ? 1.0f : sc[160];
+                const float w = alpha * (carry * excl);         // train.py:261-266
+                if (chunk == 1) { sc[lane] = w; sc[32 + lane] = cr; sc[64 + lane] = cg; sc[96 + lane] = cb; sc[128 + lane] = zz; }
+                tc::named_bar_sync(1 + slot, 128);
+                if (chunk == 0) {
+                  float ar = w * cr, ag = w * cg, ab = w * cb, ad = w * zz, aa = w;
+                  const float w1 = sc[lane];
+                  ar = fmaf(w1, sc[32 + lane], ar); ag = fmaf(w1, sc[64 + lane], ag); ab = fmaf(w1, sc[96 + lane], ab);
+                  ad = fmaf(w1, sc[128 + lane], ad); aa += w1;
+                  const float r = warp_sum4_scatter(ar, ag, ab, ad, lane);
+                  aa = warp_sum(aa);
+                  if ((lane & 7) == 0 && tile_ok && ray * a.n_sample < a.n_rows) {
+                    if (lane < 24) a.comp_rgb[3 * ray + (lane >> 3)] = r;               // train.py:269
+                    else if (a.comp_depth) a.comp_depth[ray] = r;
+                    if (lane == 0 && a.comp_acc) a.comp_acc[ray] = aa;
+                  }
+                }
+              }
             }
+            if (!composited && valid) reinterpret_cast<float4*>(a.sigma_rgb)[grow] = make_float4(sigma_keep, cr, cg, cb);
           }
         }
         if (MODE == MODE_FWD && TRAIN && store_out) {

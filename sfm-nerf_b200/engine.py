@@ -193,6 +193,18 @@ def mlp_forward_rays(st, rays_o, rays_d, z, stash=None):
     return out
 
 
+def mlp_render_rays(st, rays_o, rays_d, z, extras=True):
+    """Fused render of 64-sample rays: the MLP and the volume compositing (NeRFModel.py:158-202 + train.py:248-269) in ONE kernel;
+    bit-identical to ``composite_forward(mlp_forward_rays(...), z)``."""
+    n_rays, S = z.shape
+    rgb = torch.empty((n_rays, 3), dtype=torch.float32, device=z.device)
+    depth = torch.empty((n_rays,), dtype=torch.float32, device=z.device) if extras else None
+    acc = torch.empty((n_rays,), dtype=torch.float32, device=z.device) if extras else None
+    call("nerf_mlp_render_rays", ptr(st.packed), st.layout, ptr(rays_o), ptr(rays_d), ptr(z), n_rays, S, ptr(rgb), ptr(depth), ptr(acc),
+         stream_ptr())
+    return rgb, depth, acc
+
+
 def mlp_backward(st, stash, sigma_rgb, d_sigma_rgb, grads, dstash=None, accumulate=False):
     n_rows = sigma_rgb.numel() // 4
     if dstash is None:

@@ -84,7 +84,7 @@ def test_train_step_struct_matches_header(libmod, tmp_path):
 
 def test_abi_queries_without_gpu(libmod):
     lib = libmod.load()
-    assert lib.nerf_abi_version() == 3
+    assert lib.nerf_abi_version() == 4
     assert lib.nerf_param_count(0) == 661636 and lib.nerf_param_count(1) == 627844
     assert lib.nerf_param_count(2) == 661636 and lib.nerf_param_count(3) == 627844      # ReLU-density (legacy checkpoint) layouts
     assert lib.nerf_param_count(4) == -4
