@@ -143,10 +143,10 @@ int nerf_mlp_forward(const void* packed, int layout, const float* pos, const flo
 int nerf_mlp_forward_rays(const void* packed, int layout, const float* rays_o,
                           const float* rays_d, const float* z, int64_t n_rays, int n_sample,
                           float* sigma_rgb, void* stash, void* stream);
-/* Fused render of rays with 64 samples (NeRFModel.py:158-202 + train.py:248-269 in ONE kernel): the volume
- * compositing runs in the MLP kernel's epilogue -- a 128-row tile is exactly two rays -- so the per-sample (density, rgb) never
- * leave the SM; rgb [n_rays,3], depth / acc [n_rays] or NULL.  Bit-identical to nerf_mlp_forward_rays + nerf_composite_forward.
- * n_sample != 64: NERF_ERR_ARG (use the two calls; nerf_render_image chooses by itself). */
+/* Fused render of rays with 64 or 128 samples (NeRFModel.py:158-202 + train.py:248-269 in ONE kernel): the volume
+ * compositing runs in the MLP kernel's epilogue -- a 128-row tile is exactly two rays or one -- so the per-sample (density, rgb)
+ * never leave the SM; rgb [n_rays,3], depth / acc [n_rays] or NULL.  Bit-identical to nerf_mlp_forward_rays + nerf_composite_forward.
+ * Other n_sample: NERF_ERR_ARG (use the two calls; nerf_render_image chooses by itself). */
 int nerf_mlp_render_rays(const void* packed, int layout, const float* rays_o, const float* rays_d,
                          const float* z, int64_t n_rays, int n_sample, float* rgb, float* depth,
                          float* acc, void* stream);

@@ -369,7 +369,7 @@ int nerf_mlp_forward_rays(const void* packed, int layout, const float* rays_o, c
 int nerf_mlp_render_rays(const void* packed, int layout, const float* rays_o, const float* rays_d, const float* z, int64_t n_rays,
                          int n_sample, float* rgb, float* depth, float* acc, void* stream) {
   if (!z || !rgb || n_rays < 0) return NERF_ERR_ARG;
-  if (n_sample != 64) return NERF_ERR_ARG;            /* a 128-row tile must be exactly two rays */
+  if (n_sample != 64 && n_sample != 128) return NERF_ERR_ARG;      /* a 128-row tile must be exactly two rays or one */
   return launch_forward(packed, layout, rays_o, rays_d, z, n_rays * n_sample, n_sample, nullptr, nullptr, stream, rgb, depth, acc);
 }
 
@@ -542,8 +542,8 @@ int nerf_render_image(const void* packed, int layout, const double* poses, int p
   int rc;
   if ((rc = nerf_raygen_image(poses, pose_index, fx, fy, cx, cy, width, height, ray_begin, ray_count, o, d, stream))) return rc;
   if ((rc = nerf_sample_z(ray_count, n_sample, near, far, perturb, nullptr, seed, offset, z, stream))) return rc;
-  // 64 samples per ray: the compositing runs in the MLP kernel's epilogue (sigma_rgb never leaves the SM); else two kernels
-  if (n_sample == 64 && rgb) return nerf_mlp_render_rays(packed, layout, o, d, z, ray_count, n_sample, rgb, depth, acc, stream);
+  // 64 / 128 samples per ray: the compositing runs in the MLP kernel's epilogue (sigma_rgb never leaves the SM); else two kernels
+  if ((n_sample == 64 || n_sample == 128) && rgb) return nerf_mlp_render_rays(packed, layout, o, d, z, ray_count, n_sample, rgb, depth, acc, stream);
   if ((rc = nerf_mlp_forward_rays(packed, layout, o, d, z, ray_count, n_sample, sr, nullptr, stream))) return rc;
   return nerf_composite_forward(sr, z, ray_count, n_sample, rgb, depth, acc, stream);
 }

@@ -632,35 +632,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             const float cr = sigmoid_f(c0 + b2[0]), cg = sigmoid_f(c1 + b2[1]), cb = sigmoid_f(c2 + b2[2]);
             bool composited = false;
             if constexpr (!TRAIN) {
-              if (a.comp_rgb != nullptr) {                     // uniform: fused render, 64 samples per ray
-                // A 128-row tile is two rays: warps 0, 1 of the warpgroup hold samples 0-31 / 32-63 of the first, warps 2, 3 of the
-                // second.  The arithmetic is composite_forward_exact_kernel<2>'s, operation for operation (lane l of that kernel's warp
-                // handles samples l and l + 32), so the result has the same bits: the second warp of a ray needs the first one's
-                // transmittance product, the first one then folds the second one's (weight, colour, depth) into its own sums.
+              if (a.comp_rgb != nullptr) {                     // uniform: fused render, 64 or 128 samples per ray
+                // A 128-row tile is two rays of 64 samples or one of 128: warp q of the warpgroup holds chunk q % NC (32 samples) of
+                // local ray q / NC.  The arithmetic is composite_forward_exact_kernel<NC>'s, operation for operation (lane l of that
+                // kernel's warp handles samples l, l + 32, ...), so the result has the same bits: a warp needs the transmittance
+                // product of the chunks before it, and the first warp of a ray then folds the other chunks' (weight, colour, depth)
+                // into its own per-lane sums in chunk order.
                 composited = true;
-                const int wq = warp & 3, chunk = wq & 1;
-                const int64_t ray = (int64_t)tile * 2 + (wq >> 1);
-                float* sc = reinterpret_cast<float*>(smem + MlpSmem::kAct + slot * kActBytes + 16 * kKcoreBytes) + (wq >> 1) * 168;   // free k-cores of the tile
+                const int nc = a.n_sample >> 5;                // chunks per ray: 2 or 4
+                const int wq = warp & 3, chunk = wq & (nc - 1), lr = wq / nc;
+                const int64_t ray = (int64_t)tile * (4 / nc) + lr;
+                float* sc = reinterpret_cast<float*>(smem + MlpSmem::kAct + slot * kActBytes + 16 * kKcoreBytes) + lr * 512;   // free k-cores of the tile
+                const bool last_sample = chunk == nc - 1 && lane == 31;
                 const float zz = valid ? a.z[grow] : 0.0f;
-                const float zn = (valid && !(chunk == 1 && lane == 31)) ? a.z[grow + 1] : zz;
+                const float zn = (valid && !last_sample) ? a.z[grow + 1] : zz;
                 float delta = __fsub_rn(zn, zz);
-                if (chunk == 1 && lane == 31) delta = 1e-3f;    // train.py:250
+                if (last_sample) delta = 1e-3f;                 // train.py:250
                 const float alpha = __fsub_rn(1.0f, expf(-__fmul_rn(sigma_keep, delta)));
                 const float om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);   // train.py:262
                 const float incl = warp_incl_prod(om, lane);
                 float excl = __shfl_up_sync(0xffffffffu, incl, 1);
                 if (lane == 0) excl = 1.0f;
-                if (chunk == 0 && lane == 31) sc[160] = incl;
+                if (lane == 31) sc[480 + chunk] = incl;
                 tc::named_bar_sync(1 + slot, 128);
-                const float carry = chunk == 0 ? 1.0f : sc[160];
+                float carry = 1.0f;
+                for (int j = 0; j < chunk; ++j) carry *= sc[480 + j];
                 const float w = alpha * (carry * excl);         // train.py:261-266
-                if (chunk == 1) { sc[lane] = w; sc[32 + lane] = cr; sc[64 + lane] = cg; sc[96 + lane] = cb; sc[128 + lane] = zz; }
+                if (chunk > 0) {
+                  float* q = sc + (chunk - 1) * 160 + lane;
+                  q[0] = w; q[32] = cr; q[64] = cg; q[96] = cb; q[128] = zz;
+                }
                 tc::named_bar_sync(1 + slot, 128);
                 if (chunk == 0) {
                   float ar = w * cr, ag = w * cg, ab = w * cb, ad = w * zz, aa = w;
-                  const float w1 = sc[lane];
-                  ar = fmaf(w1, sc[32 + lane], ar); ag = fmaf(w1, sc[64 + lane], ag); ab = fmaf(w1, sc[96 + lane], ab);
-                  ad = fmaf(w1, sc[128 + lane], ad); aa += w1;
+                  for (int k = 1; k < nc; ++k) {
+                    const float* q = sc + (k - 1) * 160 + lane;
+                    const float wk = q[0];
+                    ar = fmaf(wk, q[32], ar); ag = fmaf(wk, q[64], ag); ab = fmaf(wk, q[96], ab); ad = fmaf(wk, q[128], ad); aa += wk;
+                  }
                   const float r = warp_sum4_scatter(ar, ag, ab, ad, lane);
                   aa = warp_sum(aa);
                   if ((lane & 7) == 0 && tile_ok && ray * a.n_sample < a.n_rows) {

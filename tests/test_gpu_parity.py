@@ -803,20 +803,20 @@ def test_render_image_one_call_equals_the_four_launches(pkg, model_pe):
 
 
 def test_fused_render_of_64_sample_rays_is_bit_identical(pkg, model_pe):
-    """nerf_mlp_render_rays (compositing in the MLP kernel's epilogue; a 128-row tile = two 64-sample rays) gives the
+    """nerf_mlp_render_rays (compositing in the MLP kernel's epilogue; a 128-row tile = two 64-sample rays or one of 128) gives the
     bits of mlp_forward_rays + composite_forward -- ragged and odd ray counts, more tiles than CTA pairs, with and without the
     optional outputs; nerf_render_image takes the fused kernel for 64 samples; other ray lengths are refused."""
     E = pkg.engine
     with torch.no_grad():
         st = model_pe.kernel_state()
         g = torch.Generator(device="cuda").manual_seed(5)
-        for n_rays in (1, 2, 7, 301, 4099, 20001):
+        for n_rays, S in ((1, 64), (2, 64), (7, 64), (301, 64), (4099, 64), (20001, 64), (1, 128), (5, 128), (302, 128), (9001, 128)):
             o = torch.randn(n_rays, 3, device="cuda", generator=g) * 0.3 + torch.tensor([0.0, 0.0, -4.0], device="cuda")
             d = torch.nn.functional.normalize(torch.randn(n_rays, 3, device="cuda", generator=g) * 0.3 + torch.tensor([0.0, 0.0, 1.0], device="cuda"), dim=-1)
-            z = E.sample_z(n_rays, 64, 2.0, 6.0, "cuda", perturb=True, seed=n_rays)
+            z = E.sample_z(n_rays, S, 2.0, 6.0, "cuda", perturb=True, seed=n_rays)
             rgb, depth, acc = E.composite_forward(E.mlp_forward_rays(st, o, d, z, None), z, extras=True)
             rgb2, depth2, acc2 = E.mlp_render_rays(st, o, d, z, extras=True)
-            assert torch.equal(rgb, rgb2) and torch.equal(depth, depth2) and torch.equal(acc, acc2), n_rays
+            assert torch.equal(rgb, rgb2) and torch.equal(depth, depth2) and torch.equal(acc, acc2), (n_rays, S)
             rgb3, none_d, none_a = E.mlp_render_rays(st, o, d, z, extras=False)
             assert torch.equal(rgb, rgb3) and none_d is None and none_a is None
         # the one-call frame slice with 64 samples goes through the fused kernel and still equals the four launches
