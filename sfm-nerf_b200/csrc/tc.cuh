@@ -121,27 +121,7 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
-// shared -> global, tracked by bulk async-groups.
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-               ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void bulk_s2g_hint(void* dst_gmem, uint32_t src_smem, uint32_t bytes, uint64_t policy) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-               ::"l"(dst_gmem), "r"(src_smem), "r"(bytes), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// generic-proxy smem writes -> visible to the async proxy (UMMA operand reads, bulk stores)
+// generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -232,7 +212,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 }
 // Eight consecutive contraction steps into one accumulator from ONE asm block (single-CTA form): the sixteen descriptors
 // are live inputs in distinct registers, so the UTCHMMAs do not serialise on each other's descriptor-register scoreboard
-// (see umma_bf16_pair_x4).  a[i] / b[i] are full 64-bit shared-memory descriptors.
+// (see umma_bf16_pair_x4_release2).  a[i] / b[i] are full 64-bit shared-memory descriptors.
 __device__ __forceinline__ void umma_bf16_x8(uint32_t d_tmem, const uint64_t (&a)[8], const uint64_t (&b)[8], uint32_t idesc,
                                              uint32_t accumulate_first) {
   asm volatile(
@@ -270,21 +250,9 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc,
 // in distinct (uniform) registers.  Issued one by one, consecutive MMAs reuse the same uniform registers and each
 // waits on the previous UTCHMMA's scoreboard, which is released only about when that MMA completes (~225 cycles per
 // MMA instead of 128, measured).
-__device__ __forceinline__ void umma_bf16_pair_x4(uint32_t d_tmem, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3, uint64_t b0,
-                                                  uint64_t b1, uint64_t b2, uint64_t b3, uint32_t idesc, uint32_t accumulate_first) {
-  asm volatile(
-      "{\n\t.reg .pred p, t;\n\t"
-      "setp.ne.b32 p, %10, 0;\n\t"
-      "setp.eq.b32 t, 0, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %5, %9, p;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %2, %6, %9, t;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %3, %7, %9, t;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %4, %8, %9, t;\n\t}"
-      ::"r"(d_tmem), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(accumulate_first) : "memory");
-}
-// The same four k-steps with the two ring releases inside the block: the commit for the first slab pair goes out right behind
-// the second MMA (its slot returns to the loaders two MMA-times earlier than with both commits behind the fourth), the commit
-// for the second pair behind the fourth.  Both are multicast to the two CTAs of the pair (mask 3).
+// The two ring releases are inside the block: the commit for the first slab pair goes out right behind the second MMA (its slot
+// returns to the loaders two MMA-times earlier than with both commits behind the fourth), the commit for the second pair behind the
+// fourth.  Both are multicast to the two CTAs of the pair (mask 3).
 __device__ __forceinline__ void umma_bf16_pair_x4_release2(uint32_t d_tmem, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3, uint64_t b0,
                                                            uint64_t b1, uint64_t b2, uint64_t b3, uint32_t idesc, uint32_t accumulate_first,
                                                            uint32_t bar0, uint32_t bar1) {
