@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cstdlib>
 
+#include <cuda.h>
 #include "common.cuh"
 #include "composite.cuh"
 #include "mlp_fused.cuh"
@@ -114,6 +115,30 @@ const ModelLayout* get_layout(int layout) {
   return m;
 }
 
+// The weight images as a 2-D tensor for TMA: [rows][256] uint32 (1 KB rows); a box of 4 (2) rows is one CTA's half of an N = 256 (128)
+// slab.  cuTensorMapEncodeTiled comes from the driver through the runtime (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_weight_maps(MlpArgs& a, const ModelLayout& m, const void* packed) {
+  static const EncodeTiledFn encode = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  if (!encode) return NERF_ERR_ARCH;
+  const cuuint64_t dims[2] = {256, (cuuint64_t)((m.fwd.image_bytes + m.bwd.image_bytes) / 1024)};
+  const cuuint64_t strides[1] = {1024};
+  const cuuint32_t estr[2] = {1, 1};
+  for (int which = 0; which < 2; ++which) {
+    const cuuint32_t box[2] = {256, which == 0 ? 4u : 2u};
+    if (encode(which == 0 ? &a.tm4 : &a.tm2, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(packed), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return NERF_ERR_ARG;
+  }
+  return NERF_OK;
+}
+
 void fill_mlp_args(MlpArgs& a, const ModelLayout& m, const void* packed, int64_t n_rows) {
   std::memset(&a, 0, sizeof(a));
   a.packed = static_cast<const uint8_t*>(packed);
@@ -143,6 +168,7 @@ int launch_forward(const void* packed, int layout, const float* pos, const float
   if (!nerf_aligned(packed, 16) || (sigma_rgb && !nerf_aligned(sigma_rgb, 16)) || (stash && !nerf_aligned(stash, 16))) return NERF_ERR_ALIGN;
   MlpArgs a;
   fill_mlp_args(a, *m, packed, n_rows);
+  if ((rc = make_weight_maps(a, *m, packed))) return rc;
   a.pos = pos; a.dir = dir; a.z = z; a.n_sample = n_sample;
   a.sigma_rgb = sigma_rgb;
   a.comp_rgb = comp_rgb; a.comp_depth = comp_depth; a.comp_acc = comp_acc;
@@ -387,6 +413,7 @@ int nerf_mlp_dgrad(const void* packed, int layout, const void* stash, const floa
   if (n_rows == 0) return NERF_OK;
   MlpArgs a;
   fill_mlp_args(a, *m, packed, n_rows);
+  if ((rc = make_weight_maps(a, *m, packed))) return rc;
   a.sigma_rgb = const_cast<float*>(sigma_rgb);
   a.d_sigma_rgb = d_sigma_rgb;
   a.stash = static_cast<uint8_t*>(const_cast<void*>(stash));

@@ -20,13 +20,14 @@
 // than the load latency.
 //   warps 0-3 / 4-7 : epilogue of tile slot 0 / 1 (thread = row = TMEM lane), both CTAs:
 //                     TMEM -> regs -> ReLU+bf16 pack (one cvt) -> next layer's A tile, in place
-//   warps 8, 10     : weight loaders (1-D bulk copies of this CTA's half slabs into the ring), both CTAs
+//   warps 8, 10     : weight loaders (tensor-map copies of this CTA's half slabs into the ring, completion signalled on the
+//                     LEADER's barriers from both CTAs), both CTAs
 //   warp 9          : leader: MMA issuer (one elected lane), tcgen05.mma cta_group::2 kind::f16 256xNx16,
 //                     completion multicast to both CTAs' barriers
-//   warps 9, 11     : peer: relay "my half slab has landed" to the leader's full barriers
 // Biases ride on the MMA: channel 63 of the encoding tile is the constant 1.0 and the packed weight
 // image carries the bias in that K column, so the epilogue does no bias loads or adds.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 #include "composite.cuh"
 #include "mlp_layout.cuh"
@@ -36,7 +37,7 @@ namespace nerf {
 
 constexpr int MODE_FWD = 0;
 constexpr int MODE_BWD = 1;
-// 8 epilogue warps + 2 loaders + MMA issuer (leader) / 2 slab relays (peer): the CTA must be a whole number of
+// 8 epilogue warps + 2 loaders + MMA issuer (leader; warp 11 and the peer's warp 9 have no role): the CTA must be a whole number of
 // 128-thread warpgroups.  tcgen05.ld lets warp w touch TMEM lanes 32*(w%4).., and only for warpgroup-aligned CTAs is a
 // warp's index in the CTA tied to the SM sub-partition it runs on: with 320 threads the epilogue warps were seen in
 // rotated hardware slots (cuda-gdb) and tcgen05.ld raised "misaligned address", depending on what ran on the SM before.
@@ -56,6 +57,7 @@ constexpr int kMlpThreads = 384;
 #endif
 
 struct MlpArgs {
+  CUtensorMap tm4, tm2;      // the weight images as [rows][256] uint32 (1 KB rows), boxes of 4 / 2 rows = this CTA's half of an N = 256 / 128 slab
   const uint8_t* packed;     // weight images
   const float* small;        // heads (fp32)
   // forward inputs: per-row (pos, dir) or per-ray (rays_o, rays_d, z) with n_sample > 0
@@ -190,8 +192,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   // (barrier addresses, descriptors, counters) on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    // leader full[i]: its own expect_tx arrival + the peer's relayed arrival; peer full[i]: its own only
-    for (int i = 0; i < kRingSlots; ++i) { tc::mbar_init(bar_full + 8 * i, rank == 0 ? 2 : 1); tc::mbar_init(bar_empty + 8 * i, 1); }
+    // only the LEADER's full barriers are used: its loader's expect_tx arrival, transaction bytes from both CTAs' copies
+    for (int i = 0; i < kRingSlots; ++i) { tc::mbar_init(bar_full + 8 * i, 1); tc::mbar_init(bar_empty + 8 * i, 1); }
     // act_ready lives in the leader: 128 epilogue threads of each CTA arrive on it
     for (int i = 0; i < 2; ++i) { tc::mbar_init(bar_acc + 8 * i, 1); tc::mbar_init(bar_act + 8 * i, 256); }
     tc::mbar_init(bar_drain, 1);                       // the MMA warp: "all my MMAs have completed" (multicast to both CTAs)
@@ -205,7 +207,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   const Program& P = a.prog;
   const int n_quads = (a.n_tiles + 3) >> 2;            // 4 tiles per cluster iteration: tile = 4*quad + 2*slot + rank
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  // The MMA issuer, the loaders and the relays walk ONE sequence of passes: pass p = layer p % n_steps of this cluster's quad
+  // The MMA issuer and the loaders walk ONE sequence of passes: pass p = layer p % n_steps of this cluster's quad
   // p / n_steps, tile slot 0's pass p and then tile slot 1's pass p.  The ring is addressed in SLAB PAIRS (two consecutive
   // k-steps of a pass, 2 x 4 KB per CTA, one full and one empty barrier per pair): every pass starts on a fresh pair, a pass with
   // an odd number of k-steps (16 activation k-steps + the bias k-step) leaves the second half of its last pair unused.  Before
@@ -217,12 +219,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
 
   if (warp == 8 || warp == 10) {
     // ===================== weight loaders (both CTAs: this CTA's N/2 rows of every slab, every layer twice) ==========
-    // One slab pair per trip, the two loader warps taking alternate trips (a single thread doing wait(empty) -> bulk copies ->
-    // arrive.expect_tx pair after pair is a chain of ~130-cycle barrier operations; two warps overlap their trips).  The
-    // copies are issued before the expect_tx arrival (the phase cannot complete while that arrival is pending, so the order
-    // is free) to get them on their way ~130 cycles earlier.
+    // One slab pair per trip, the two loader warps taking alternate trips (a single thread doing wait(empty) -> copies ->
+    // arrive.expect_tx pair after pair is a chain of ~130-cycle barrier operations; two warps overlap their trips).  The copies
+    // are 2-D tensor-map (TMA) loads in the cta_group::2 form, whose completion may be signalled on the OTHER CTA's mbarrier: both
+    // CTAs' halves of a pair report their bytes to the leader's full barrier, which the leader's loader arms with one
+    // expect_tx for all of them (the copies are issued before that arrival: the phase cannot complete while it is pending).
+    // Round 1 / early round 2 used 1-D bulk copies onto the CTA's own barrier and two relay warps in the peer that forwarded
+    // "landed" to the leader (remote mbarrier arrive): one hop more in the ring's round trip, ~1 % on every MLP kernel.
     const int which = (warp - 8) >> 1;
     const uint64_t keep_in_l2 = tc::l2_policy_evict_last();    // the 2.6 MB of weight images are re-read by every CTA, all the time
+    const uint32_t leader_full = tc::mapa(bar_full, 0);
     uint32_t pj0 = 0, trip = 0;                          // slab pairs issued before the current pass; trip counter
     int si = 0;
     for (int ps = 0; ps < n_pass; ++ps) {
@@ -231,7 +237,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
       const uint32_t bytes = (uint32_t)st.n * 16u;
       const int total = st.act_ksteps + st.enc_ksteps + st.bias_kstep;
       const int n_pairs = (total + 1) >> 1;
-      const uint8_t* src = a.packed + st.w_off + rank * bytes;
+      const uint64_t tmap = reinterpret_cast<uint64_t>(bytes == 4096u ? &a.tm4 : &a.tm2);
       for (int slot = 0; slot < 2; ++slot) {             // slot 0's pass, then slot 1's
         for (int j = 0; j < n_pairs; ++j, ++trip) {
           if ((int)(trip & 1u) != which) continue;
@@ -240,9 +246,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             const uint32_t rs = it % kRingSlots, ph = (it / kRingSlots) & 1u;
             const bool two = 2 * j + 1 < total;
             tc::mbar_wait(bar_empty + 8 * rs, ph ^ 1u);
-            tc::bulk_g2s_hint(s_ring + rs * kRingSlotBytes, src + (size_t)(2 * j) * (2u * bytes), bytes, bar_full + 8 * rs, keep_in_l2);
-            if (two) tc::bulk_g2s_hint(s_ring + rs * kRingSlotBytes + kSlabBytes, src + (size_t)(2 * j + 1) * (2u * bytes), bytes, bar_full + 8 * rs, keep_in_l2);
-            tc::mbar_arrive_expect_tx(bar_full + 8 * rs, two ? 2u * bytes : bytes);
+            // row (1 KB) of this CTA's half of k-step 2j inside the weight buffer; both CTAs' copies report to the LEADER's barrier
+            const int32_t row0 = (int32_t)(((uint32_t)st.w_off + (uint32_t)(2 * j) * (2u * bytes) + rank * bytes) >> 10);
+            const int32_t step_rows = (int32_t)((2u * bytes) >> 10);
+            tc::tma_g2s_2d_pair(s_ring + rs * kRingSlotBytes, tmap, 0, row0, leader_full + 8 * rs, keep_in_l2);
+            if (two) tc::tma_g2s_2d_pair(s_ring + rs * kRingSlotBytes + kSlabBytes, tmap, 0, row0 + step_rows, leader_full + 8 * rs, keep_in_l2);
+            if (rank == 0) tc::mbar_arrive_expect_tx(bar_full + 8 * rs, 2u * (two ? 2u * bytes : bytes));
           }
           __syncwarp();
         }
@@ -258,32 +267,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
       tc::mbar_wait(bar_drain, 0);
     }
     __syncwarp();
-  } else if ((warp == 9 || warp == 11) && rank != 0) {
-    // ===================== peer: relay "my half of slab pair j has landed" to the leader's full barrier ================
-    // (alternate trips per warp, like the loaders)
-    const int which = (warp - 9) >> 1;
-    const uint32_t leader_full = tc::mapa(bar_full, 0);
-    uint32_t pj0 = 0, trip = 0;
-    int si = 0;
-    for (int ps = 0; ps < n_pass; ++ps) {
-      const Step& st = P.s[si];
-      si = (si + 1 == P.n_steps) ? 0 : si + 1;
-      const int n_pairs = (st.act_ksteps + st.enc_ksteps + st.bias_kstep + 1) >> 1;
-      for (int slot = 0; slot < 2; ++slot) {
-        for (int j = 0; j < n_pairs; ++j, ++trip) {
-          if ((int)(trip & 1u) != which) continue;
-          if (lane == 0) {
-            const uint32_t it = pj0 + (uint32_t)j;
-            const uint32_t rs = it % kRingSlots;
-            tc::mbar_wait(bar_full + 8 * rs, (it / kRingSlots) & 1u);
-            tc::mbar_arrive_cluster(leader_full + 8 * rs);
-          }
-          __syncwarp();
-        }
-        pj0 += (uint32_t)n_pairs;
-      }
-    }
-  } else if (warp == 9) {
+  } else if (warp == 9 && rank == 0) {
     // ===================== leader MMA issuer =====================
     // The warp runs with warp-uniform control flow (all lanes poll the barriers) and one elected lane issues the
     // cta_group::2 instructions (M = 256: this CTA's tile + the peer's tile of the same slot).  What shaped this loop

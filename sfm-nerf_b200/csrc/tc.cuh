@@ -121,6 +121,13 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
+// 2-D tiled (tensor-map) copy global -> this CTA's shared memory whose completion is signalled on an mbarrier of EITHER CTA of the
+// pair (cta_group::2; `bar_cluster` = shared::cluster address, e.g. mapa(bar, 0) for the leader's): the peer's half of a weight slab
+// then reports straight to the leader's full barrier, with no relay warp in between.  `tmap` = generic address of the CUtensorMap.
+__device__ __forceinline__ void tma_g2s_2d_pair(uint32_t dst_smem, uint64_t tmap, int32_t c0, int32_t c1, uint32_t bar_cluster, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(dst_smem), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
