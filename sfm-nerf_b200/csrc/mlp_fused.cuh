@@ -20,7 +20,7 @@
 // than the load latency.
 //   warps 0-3 / 4-7 : epilogue of tile slot 0 / 1 (thread = row = TMEM lane), both CTAs:
 //                     TMEM -> regs -> ReLU+bf16 pack (one cvt) -> next layer's A tile, in place
-//   warps 8, 10     : weight loaders (tensor-map copies of this CTA's half slabs into the ring, completion signalled on the
+//   warps 8, 10 (+ 11 in the inference kernel) : weight loaders (tensor-map copies of this CTA's half slabs into the ring, completion signalled on the
 //                     LEADER's barriers from both CTAs), both CTAs
 //   warp 9          : leader: MMA issuer (one elected lane), tcgen05.mma cta_group::2 kind::f16 256xNx16,
 //                     completion multicast to both CTAs' barriers
@@ -217,16 +217,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   const int n_local = cluster_id < n_quads ? (n_quads - cluster_id + n_clusters - 1) / n_clusters : 0;   // quads of this cluster
   const int n_pass = n_local * P.n_steps;
 
-  if (warp == 8 || warp == 10) {
+  // Loader warps: 8 and 10, and in the inference kernel also warp 11.  Inference is bound by the slab supply (no stash stores: the
+  // tensor pipe waits for weights), and a third warp taking every third slab pair shortens the chain wait(empty) -> copies ->
+  // expect_tx per pair: 0.271 -> 0.248 ms at 4096 x 64 (1.39 PFLOP/s).  The training forward and dgrad are bound by their stores:
+  // three loaders measured 1 % slower there; four in the peer (its warp 9 has no role) and three in the leader: 0.31 ms.
+  constexpr bool kInfer = (MODE == MODE_FWD) && !TRAIN;
+  const int n_loaders = kInfer ? 3 : 2;
+  const int loader_idx = warp == 8 ? 0 : warp == 10 ? 1 : warp == 11 ? 2 : -1;
+  if (loader_idx >= 0 && loader_idx < n_loaders) {
     // ===================== weight loaders (both CTAs: this CTA's N/2 rows of every slab, every layer twice) ==========
-    // One slab pair per trip, the two loader warps taking alternate trips (a single thread doing wait(empty) -> copies ->
-    // arrive.expect_tx pair after pair is a chain of ~130-cycle barrier operations; two warps overlap their trips).  The copies
+    // One slab pair per trip, the loader warps taking the trips in turn (a single thread doing wait(empty) -> copies ->
+    // arrive.expect_tx pair after pair is a chain of ~130-cycle barrier operations; several warps overlap their trips).  The copies
     // are 2-D tensor-map (TMA) loads in the cta_group::2 form, whose completion may be signalled on the OTHER CTA's mbarrier: both
     // CTAs' halves of a pair report their bytes to the leader's full barrier, which the leader's loader arms with one
     // expect_tx for all of them (the copies are issued before that arrival: the phase cannot complete while it is pending).
     // Round 1 / early round 2 used 1-D bulk copies onto the CTA's own barrier and two relay warps in the peer that forwarded
     // "landed" to the leader (remote mbarrier arrive): one hop more in the ring's round trip, ~1 % on every MLP kernel.
-    const int which = (warp - 8) >> 1;
+    const int which = loader_idx;
     const uint64_t keep_in_l2 = tc::l2_policy_evict_last();    // the 2.6 MB of weight images are re-read by every CTA, all the time
     const uint32_t leader_full = tc::mapa(bar_full, 0);
     uint32_t pj0 = 0, trip = 0;                          // slab pairs issued before the current pass; trip counter
@@ -240,7 +247,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
       const uint64_t tmap = reinterpret_cast<uint64_t>(bytes == 4096u ? &a.tm4 : &a.tm2);
       for (int slot = 0; slot < 2; ++slot) {             // slot 0's pass, then slot 1's
         for (int j = 0; j < n_pairs; ++j, ++trip) {
-          if ((int)(trip & 1u) != which) continue;
+          if ((int)(trip % (uint32_t)n_loaders) != which) continue;
           if (lane == 0) {
             const uint32_t it = pj0 + (uint32_t)j;
             const uint32_t rs = it % kRingSlots, ph = (it / kRingSlots) & 1u;
