@@ -223,10 +223,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   // three loaders measured 1 % slower there; four in the peer (its warp 9 has no role) and three in the leader: 0.31 ms.
   constexpr bool kInfer = (MODE == MODE_FWD) && !TRAIN;
   const int n_loaders = kInfer ? 3 : 2;
+  // ... and there every loader warp takes TWO consecutive slab pairs per trip, one per lane (the lanes wait for their slots side by
+  // side): 0.248 -> 0.225 ms.  Six pairs in flight is the limit: with nine or twelve (3-4 lanes) a lane can be a whole ring round
+  // ahead of an unloaded slot, its parity wait aliases, and the kernel deadlocks (measured: mbarrier time-outs).
+  const int n_lanes = kInfer ? 2 : 1;
   const int loader_idx = warp == 8 ? 0 : warp == 10 ? 1 : warp == 11 ? 2 : -1;
   if (loader_idx >= 0 && loader_idx < n_loaders) {
     // ===================== weight loaders (both CTAs: this CTA's N/2 rows of every slab, every layer twice) ==========
-    // One slab pair per trip, the loader warps taking the trips in turn (a single thread doing wait(empty) -> copies ->
+    // One slab pair per trip and lane, the loader warps taking the trips in turn (a single thread doing wait(empty) -> copies ->
     // arrive.expect_tx pair after pair is a chain of ~130-cycle barrier operations; several warps overlap their trips).  The copies
     // are 2-D tensor-map (TMA) loads in the cta_group::2 form, whose completion may be signalled on the OTHER CTA's mbarrier: both
     // CTAs' halves of a pair report their bytes to the leader's full barrier, which the leader's loader arms with one
@@ -246,9 +250,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
       const int n_pairs = (total + 1) >> 1;
       const uint64_t tmap = reinterpret_cast<uint64_t>(bytes == 4096u ? &a.tm4 : &a.tm2);
       for (int slot = 0; slot < 2; ++slot) {             // slot 0's pass, then slot 1's
-        for (int j = 0; j < n_pairs; ++j, ++trip) {
+        for (int j0 = 0; j0 < n_pairs; j0 += n_lanes, ++trip) {
           if ((int)(trip % (uint32_t)n_loaders) != which) continue;
-          if (lane == 0) {
+          const int j = j0 + lane;
+          if (lane < n_lanes && j < n_pairs) {
             const uint32_t it = pj0 + (uint32_t)j;
             const uint32_t rs = it % kRingSlots, ph = (it / kRingSlots) & 1u;
             const bool two = 2 * j + 1 < total;
