@@ -380,6 +380,8 @@ class Trainer:
         self._graphs, self._graph_tried = {}, set() # (from_batch9, step parity, segment) -> torch.cuda.CUDAGraph
         self.graph_error = ""
         self._loss_host, self._loss_event = None, None
+        self._b9_buf, self._copy_stream, self._copy_event = 0, None, None    # double-buffered batch upload of the whole-step path
+        self._b9_read = [None, None]                # per input buffer: event behind the launches that last read it
 
     def lr(self):
         return self.lr0 * self.lr_decay ** (self.iteration // self.lr_decay_steps)
@@ -395,14 +397,14 @@ class Trainer:
     def close(self):
         self.st.frozen = False
 
-    def _train_step_cfg(self, from_batch9, parity):
+    def _train_step_cfg(self, from_batch9, parity, buf=0):
         import ctypes
         st, dev, n, S = self.st, self.st.device, self.n_rays, self.n_sample
         if self._fixed is None:
             ws = torch.zeros(int(_lib.load().nerf_composite_train_workspace_bytes(n)) // 4 + 1, dtype=torch.float32, device=dev)
             self._fixed = (torch.empty((3, n, 3), dtype=torch.float32, device=dev), torch.empty((n, S), dtype=torch.float32, device=dev),
                            torch.empty((n, S, 4), dtype=torch.float32, device=dev), torch.empty((n, S, 4), dtype=torch.float32, device=dev),
-                           torch.empty((n, 9), dtype=torch.float32, device=dev), ws)
+                           torch.empty((2, n, 9), dtype=torch.float32, device=dev), ws)
         odt, z, sigma_rgb, dsr, batch9, ws = self._fixed
         c = _lib.NerfTrainStep()
         c.struct_bytes = ctypes.sizeof(_lib.NerfTrainStep)
@@ -411,7 +413,7 @@ class Trainer:
         c.lr0, c.lr_decay, c.lr_decay_steps = self.lr0, self.lr_decay, self.lr_decay_steps
         c.beta1, c.beta2, c.eps, c.grad_scale = self.betas[0], self.betas[1], self.eps, parallel.mean_scale(self.world)
         if from_batch9:
-            c.batch9 = batch9.data_ptr()
+            c.batch9 = batch9[buf].data_ptr()              # two input buffers: the upload of a step overlaps the previous step's backward
         else:
             c.fx, c.fy, c.cx, c.cy = _intrinsics(self.cam)
             c.n_images, c.width, c.height = int(self.images.shape[0]), int(self.cam["width"]), int(self.cam["height"])
@@ -456,6 +458,11 @@ class Trainer:
                 self.use_graph, self.graph_error = False, f"{type(e).__name__}: {e}"
                 torch.cuda.synchronize()
 
+    def _mark_b9_read(self, buf):
+        if self._b9_read[buf] is None:
+            self._b9_read[buf] = torch.cuda.Event()
+        self._b9_read[buf].record()
+
     def _step_whole(self, batch9, loss_to_host=False):
         """The whole step through nerf_train_step (one C call per phase group, CUDA-graph replays after the first step).
         ``loss_to_host``: the forward phase, an async D2H copy of the loss, then the rest; the host waits for that copy only
@@ -465,14 +472,32 @@ class Trainer:
         import ctypes
         key, ex = batch9 is not None, self.exchange
         parity = self.iteration & 1 if ex is not None else 0
-        if (key, parity) not in self._cfg:
-            self._cfg[(key, parity)] = self._train_step_cfg(key, parity)
-        cfg = ctypes.byref(self._cfg[(key, parity)])
+        buf = 0
+        if key:
+            self._b9_buf ^= 1
+            buf = self._b9_buf
+        if (key, parity, buf) not in self._cfg:
+            self._cfg[(key, parity, buf)] = self._train_step_cfg(key, parity, buf)
+        cfg = ctypes.byref(self._cfg[(key, parity, buf)])
         if self._dev_iteration != self.iteration:            # the per-kernel path ran in between, or a checkpoint was resumed
             self.step_state.fill_(self.iteration)
             self._dev_iteration = self.iteration
         if key:
-            self._fixed[4].copy_(batch9, non_blocking=True)   # H2D (pinned host batch) or D2D, straight into the step's input
+            # H2D (pinned host batch) or D2D, straight into the step's input buffer -- on a side stream, into the buffer the PREVIOUS
+            # step did not use, so the copy runs while that step's backward kernels are still busy; the forward waits for it.
+            # (The buffer's last reader, the batch kernel two steps back, finished before the host got that step's loss.)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.st.device)
+                self._copy_event = torch.cuda.Event()
+            main = torch.cuda.current_stream()
+            if batch9.device.type == "cuda":
+                self._copy_stream.wait_stream(main)            # a device-resident batch may still be being produced on this stream
+            if self._b9_read[buf] is not None:
+                self._copy_stream.wait_event(self._b9_read[buf])   # the batch kernel that last read this buffer has finished
+            with torch.cuda.stream(self._copy_stream):
+                self._fixed[4][buf].copy_(batch9, non_blocking=True)
+                self._copy_event.record()
+            main.wait_event(self._copy_event)
 
         def phases(mask):
             call("nerf_train_step", cfg, mask, stream_ptr())
@@ -484,12 +509,16 @@ class Trainer:
             if self._loss_host is None:
                 self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
                 self._loss_event = torch.cuda.Event()
-            self._run_segment((key, parity, "forward"), lambda: phases(1))
+            self._run_segment((key, parity, buf, "forward"), lambda: phases(1))
+            if key:
+                self._mark_b9_read(buf)
             self._loss_host.copy_(self.loss, non_blocking=True)
             self._loss_event.record()
-            self._run_segment((key, parity, "backward"), lambda: rest(0))
+            self._run_segment((key, parity, buf, "backward"), lambda: rest(0))
         else:
-            self._run_segment((key, parity, "step"), lambda: rest(1))
+            self._run_segment((key, parity, buf, "step"), lambda: rest(1))
+            if key:
+                self._mark_b9_read(buf)
         self.iteration += 1
         self._dev_iteration += 1
         self.launches_per_step = 7                  # batch, mlp fwd, composite_train, dgrad, wgrad (pairs), adam, pack (+1 memset)

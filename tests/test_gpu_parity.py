@@ -858,7 +858,8 @@ def test_whole_step_call_and_graph_replay_match_per_kernel_path(pkg, orc):
                 losses.append(float((tr.step(rays=rays) if whole else tr.step(rays=rays, timers={})).item()))
         assert tr.iteration == steps
         if whole:
-            assert int(tr.step_state.item()) == steps and len(tr._graphs) == (2 if host_loss else 1)
+            # one graph per segment (forward | backward when the loss goes to the host) and per input buffer of an uploaded batch
+            assert int(tr.step_state.item()) == steps and len(tr._graphs) == (2 if host_loss else 1) * (1 if host_batches is None else 2)
         w = tr.st.flat.clone()
         tr.close()
         return losses, w
@@ -1095,7 +1096,7 @@ def test_psnr_after_2k_steps_matches_reference_band(pkg, orc):
             loss = tr.step(rays=batches[it])
             if it == 0:
                 first = float(loss.item())
-        assert tr.graph_error == "" and len(tr._graphs) == 1, tr.graph_error       # the graph-replayed whole-step path ran
+        assert tr.graph_error == "" and len(tr._graphs) == 2, tr.graph_error       # the graph-replayed whole-step path ran (one graph per input buffer)
         tr.close()
         ref_first = band["loss_first"][band["seeds"].index(seed)]
         assert abs(first - ref_first) < 2e-3, (seed, first, ref_first)                # same init, same first batch
